@@ -1,0 +1,158 @@
+/*
+ * ekf_b200.h -- C ABI of the B200-native per-frame EKF hot path (libekf_b200.so).
+ *
+ * Drop-in boundary: the bodies of EKF::init / EKF::step of the reference
+ * (kalmanFilter/modules/1PointRansacEKF/EKF.h:41-63, EKF.cpp:170-666) call these entry points;
+ * everything behind them runs as hand-written sm_100a CUDA kernels.  Plain pointers and sizes
+ * only, no exceptions across the boundary, int status return (0 = ok, otherwise an ekfb_status).
+ * One handle owns `n_filters` independent filters (the reference's one-EKF-per-process becomes a
+ * batch; n_filters = 1 is the single-filter drop-in), one CUDA stream and all device memory.
+ * A handle is not thread-safe; distinct handles are independent.  There is NO CPU fallback: every
+ * call fails with EKFB_ERR_CUDA if no sm_100 device is usable.
+ *
+ * Each entry point cites the reference code it replaces.  "E/" = kalmanFilter/modules/1PointRansacEKF/.
+ */
+#ifndef EKF_B200_H
+#define EKF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ekfb_status {
+    EKFB_OK = 0,
+    EKFB_ERR_ARG = 1,      /* bad argument (null pointer, size over capacity, bad filter index) */
+    EKFB_ERR_CUDA = 2,     /* CUDA runtime error; ekfb_last_error() has the text */
+    EKFB_ERR_CAPACITY = 3, /* state / keypoint count exceeds what ekfb_create reserved */
+    EKFB_ERR_NUMERIC = 4   /* innovation covariance not positive definite */
+} ekfb_status;
+
+/* POD mirror of CameraCalibration (modules/Configuration/ConfigurationDataReader/
+ * CameraCalibrationConfiguration/CameraCalibration.h:37-63) and of the fields of
+ * ExtendedKalmanFilterParameters (.../ExtendedKalmanFilterParameters.h:37-76) the per-frame path
+ * reads.  Replaces the process-global ConfigurationManager singleton
+ * (modules/Configuration/ConfigurationManager.h:45-64): parameters are per handle. */
+typedef struct ekfb_params {
+    int32_t pixels_x, pixels_y;
+    double fx, fy, k1, k2, cx, cy, dx, dy;
+    double pixel_error_x, pixel_error_y;
+    double angular_vision_x, angular_vision_y;
+    double init_inv_depth_rho, init_linear_accel_sd, init_angular_accel_sd;
+    double linear_accel_sd, angular_accel_sd, inverse_depth_rho_sd;
+    double matching_coef;           /* MatchingCompCoefSecondBestVSFirst */
+    double ransac_threshold;        /* RansacThresholdPredictDistance    */
+    double ransac_all_inliers_prob; /* RansacAllInliersProbability       */
+    double ransac_chi2;             /* RansacChi2Threshold               */
+} ekfb_params;
+
+/* per-filter counters of the last frame (what EKF::step writes to output.yml: totalMatches,
+ * liInliers, hiInliers -- E/EKF.cpp:412-416,515-516) */
+typedef struct ekfb_frame_info {
+    int32_t n;            /* state dimension 13 + 3*N_xyz + 6*N_id */
+    int32_t n_features;
+    int32_t n_keypoints;
+    int32_t n_predicted;  /* features predicted inside the frame        */
+    int32_t n_matches;    /* totalMatches                               */
+    int32_t n_hypotheses; /* RANSAC hypotheses the sequential rule used */
+    int32_t best_hypothesis;
+    int32_t n_inliers;    /* liInliers                                  */
+    int32_t n_outliers;
+    int32_t n_rescued;    /* hiInliers                                  */
+    int32_t status;       /* 0, or EKFB_ERR_NUMERIC if a Cholesky pivot was not positive */
+    int32_t reserved;
+} ekfb_frame_info;
+
+/* fixed-size per-filter result record (what callers read back: main.cpp:91,137,141 read
+ * ekf.state / P; A/jni/EKFNative.cpp:191-193 reads state.position).  This is also the payload of
+ * the multi-GPU gather. */
+typedef struct ekfb_record {
+    double x_cam[13];       /* r(3) q(4: w,x,y,z) v(3) omega(3) */
+    double P_cam[13 * 13];  /* stateCovarianceMatrix(0:13, 0:13) */
+    ekfb_frame_info info;
+} ekfb_record;
+
+typedef struct ekfb_ctx* ekfb_handle;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* Replaces EKF::EKF (E/EKF.cpp:124-144) minus file outputs.  max_features bounds N per filter
+ * (state capacity 13 + 6*max_features rows), max_keypoints bounds the per-frame front-end output. */
+int ekfb_create(const ekfb_params* params, int device, int n_filters, int max_features, int max_keypoints,
+                ekfb_handle* out);
+int ekfb_destroy(ekfb_handle h);                 /* EKF::~EKF, State::~State (E/State.cpp:75-103) */
+const char* ekfb_last_error(void);
+int ekfb_sync(ekfb_handle h);                    /* wait for the handle's stream */
+
+/* ---- state in / out ------------------------------------------------------------------------------ */
+/* Upload one filter: x (n doubles: camera 13 + features at their covarianceMatrixPos), feature
+ * type (1 = XYZ, 2 = inverse depth; E/MapFeature.h:39-44), feat_off (covarianceMatrixPos,
+ * E/MapFeature.h:68), P (n x n row-major, E/EKF.h:50), descriptors (N x 32 bytes, E/MapFeature.h:70).
+ * This is the state EKF::init leaves behind (E/EKF.cpp:170-237) or any later state. */
+int ekfb_set_state(ekfb_handle h, int filter, int n, int n_features, const double* x, const int32_t* feat_type,
+                   const int32_t* feat_off, const double* P, const uint8_t* desc);
+/* Download.  x and/or P may be NULL.  cam_block_only != 0 copies x[0:13] and P[0:13,0:13] only. */
+int ekfb_get_state(ekfb_handle h, int filter, double* x, double* P, int cam_block_only);
+int ekfb_get_descriptors(ekfb_handle h, int filter, uint8_t* desc, int32_t* times_predicted, int32_t* times_matched);
+int ekfb_get_dims(ekfb_handle h, int filter, int32_t* n, int32_t* n_features);
+
+/* ---- front-end output (what detector->detect + extractor->compute return, E/Matching.cpp:204-215) */
+/* host buffers: xy = n_kp x 2 float32 pixel coordinates, desc = n_kp x 32 bytes; copied to the device */
+int ekfb_set_keypoints(ekfb_handle h, int filter, const float* xy, const uint8_t* desc, int n_kp);
+/* device-resident sequences: upload all frames once, then select a frame with no host traffic.
+ * kp_offset has n_frames+1 entries (prefix sums of per-frame keypoint counts). */
+int ekfb_load_sequence(ekfb_handle h, int filter, int n_frames, const int32_t* kp_offset, const float* xy,
+                       const uint8_t* desc);
+int ekfb_select_frame(ekfb_handle h, int frame); /* all filters take frame `frame` of their sequence */
+
+/* ---- the hot path, phase by phase, all filters of the handle (asynchronous on the handle's stream) */
+int ekfb_predict(ekfb_handle h);   /* stateAndCovariancePrediction, E/StateAndCovariancePrediction.cpp:244-253 */
+int ekfb_measure(ekfb_handle h);   /* predictCameraMeasurements on all features, E/MeasurementPrediction.cpp:705-719 */
+int ekfb_match(ekfb_handle h);     /* matchPredictedFeatures from the ellipse mask on, E/Matching.cpp:181-264 */
+int ekfb_ransac(ekfb_handle h);    /* ransac, E/1PointRansac.cpp:101-234 */
+int ekfb_update(ekfb_handle h, int which); /* update(), E/Update.cpp:282-319; which 0 = low-innovation
+                                              inliers (E/EKF.cpp:430), 1 = rescued (E/EKF.cpp:527-532) */
+int ekfb_rescue(ekfb_handle h);    /* re-prediction of outliers + rescueOutliers, E/EKF.cpp:448-506, :68-119 */
+int ekfb_update_map_features(ekfb_handle h); /* updateMapFeatures, E/MapManagement.cpp:77-113 */
+/* the whole frame in EKF::step order (E/EKF.cpp:242-572): predict, measure, match, ransac, update LI,
+ * rescue, update HI, updateMapFeatures */
+int ekfb_step(ekfb_handle h);
+
+/* ---- results ----------------------------------------------------------------------------------- */
+int ekfb_get_frame_info(ekfb_handle h, int filter, ekfb_frame_info* info);
+/* per-filter records of all filters, to a host buffer (n_filters records) */
+int ekfb_get_records(ekfb_handle h, ekfb_record* out);
+/* same, written to a caller-provided DEVICE buffer on the handle's stream (NCCL gather payload) */
+int ekfb_write_records_device(ekfb_handle h, void* device_out);
+
+/* per-feature results of the last frame, arrays of length N (any pointer may be NULL):
+ * predicted flag, h[2N], S_i[4N], Hx[14N] (2x7), Hf[12N] (2x6), matched flag, z[2N], matched keypoint
+ * index, descriptor distance, inlier / outlier / rescued flags.  For parity tests and for the host
+ * side map management (E/MapManagement.cpp). */
+int ekfb_get_feature_results(ekfb_handle h, int filter, uint8_t* predicted, double* hpred, double* S, double* Hx,
+                             double* Hf, uint8_t* matched, double* z, int32_t* kp_index, float* dist,
+                             uint8_t* inlier, uint8_t* outlier, uint8_t* rescued);
+/* the detector mask of the last ekfb_match (pixels_y x pixels_x bytes) and the per-keypoint pass flag */
+int ekfb_get_mask(ekfb_handle h, int filter, uint8_t* mask, uint8_t* kp_ok);
+
+/* ---- isolated kernels for the stress sweep (BASELINE.json config 5) and for tests ---------------- */
+/* Covariance downdate alone on filter 0: P <- P - W W^T with W^T given as k x n row-major (host). */
+int ekfb_test_downdate(ekfb_handle h, int n, int k, const double* P_in, const double* Wt, double* P_out);
+/* Full gain + update on filter 0 from caller Jacobians: for a = 0..m-1 feature index feat[a] with
+ * z (2m), using the handle's current state / P / last ekfb_measure.  Returns timings in ms. */
+int ekfb_time_update(ekfb_handle h, int which, int reps, float* ms_total, float* ms_downdate);
+
+/* ---- device timing on the handle's stream (bench.py cannot see this stream from torch) ------------ */
+int ekfb_timer_record(ekfb_handle h, int slot);                 /* slot in [0, 64) */
+int ekfb_timer_elapsed_ms(ekfb_handle h, int slot_a, int slot_b, float* ms);
+/* enable per-kernel-group timing of ekfb_step (adds event records; off by default) */
+int ekfb_profile_enable(ekfb_handle h, int on);
+/* accumulated ms per group since the last call: predict, measure, match, ransac, gain, chol, downdate,
+ * rescue, misc (9 floats), plus launch counts (9 ints) */
+int ekfb_profile_read(ekfb_handle h, float* ms9, int32_t* launches9);
+int64_t ekfb_kernel_launches(ekfb_handle h);     /* kernels launched by this handle so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKF_B200_H */

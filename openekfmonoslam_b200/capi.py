@@ -1,0 +1,214 @@
+"""ctypes binding of libekf_b200.so (include/ekf_b200.h).  No torch types cross this boundary.
+
+``EkfBatch`` is the host-side object a caller drives: a batch of independent filters on one GPU
+(n_filters = 1 is the single-filter drop-in for the reference's EKF object).  It raises
+``EkfError`` -- never falls back to a CPU path -- when the CUDA library or a usable device is missing.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+from .params import EkfParams
+
+
+class EkfError(RuntimeError):
+    pass
+
+
+class FrameInfo(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("n", "n_features", "n_keypoints", "n_predicted", "n_matches",
+                                              "n_hypotheses", "best_hypothesis", "n_inliers", "n_outliers",
+                                              "n_rescued", "status", "reserved")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Record(ctypes.Structure):
+    _fields_ = [("x_cam", ctypes.c_double * 13), ("P_cam", ctypes.c_double * 169), ("info", FrameInfo)]
+
+
+RECORD_BYTES = ctypes.sizeof(Record)
+PROFILE_GROUPS = ("predict", "measure", "match", "ransac", "gain", "chol", "downdate", "rescue", "misc")
+
+_lib = None
+
+
+def lib_path():
+    return _build.OUT
+
+
+def load(build_if_missing=True):
+    """Load libekf_b200.so; build it in-tree with nvcc if it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.OUT
+    if build_if_missing:
+        try:
+            path = _build.build()
+        except Exception as exc:  # nvcc missing on a box that already has the .so
+            if not os.path.exists(path):
+                raise EkfError(f"libekf_b200.so is missing and could not be built: {exc}") from exc
+    if not os.path.exists(path):
+        raise EkfError("libekf_b200.so is missing; run python -m openekfmonoslam_b200.build")
+    L = ctypes.CDLL(path)
+    L.ekfb_last_error.restype = ctypes.c_char_p
+    L.ekfb_kernel_launches.restype = ctypes.c_int64
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class EkfBatch:
+    def __init__(self, params: EkfParams, n_filters=1, max_features=64, max_keypoints=4096, device=0):
+        self.L = load()
+        self.params = params
+        self.n_filters, self.max_features, self.max_keypoints = n_filters, max_features, max_keypoints
+        self.h = ctypes.c_void_p()
+        self._ck(self.L.ekfb_create(ctypes.byref(params), ctypes.c_int(device), ctypes.c_int(n_filters),
+                                    ctypes.c_int(max_features), ctypes.c_int(max_keypoints), ctypes.byref(self.h)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.L.ekfb_last_error()
+            raise EkfError(f"libekf_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.ekfb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ----
+    def set_state(self, f, x, P, ftype, foff, desc):
+        x = np.ascontiguousarray(x, np.float64); P = np.ascontiguousarray(P, np.float64)
+        ftype = np.ascontiguousarray(ftype, np.int32); foff = np.ascontiguousarray(foff, np.int32)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        self._ck(self.L.ekfb_set_state(self.h, ctypes.c_int(f), ctypes.c_int(x.shape[0]), ctypes.c_int(ftype.shape[0]),
+                                       _ptr(x), _ptr(ftype), _ptr(foff), _ptr(P), _ptr(desc)))
+
+    def dims(self, f=0):
+        n, N = ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self.L.ekfb_get_dims(self.h, ctypes.c_int(f), ctypes.byref(n), ctypes.byref(N)))
+        return n.value, N.value
+
+    def get_state(self, f=0, cam_only=False):
+        n, _ = self.dims(f)
+        if cam_only:
+            n = 13
+        x = np.zeros(n); P = np.zeros((n, n))
+        self._ck(self.L.ekfb_get_state(self.h, ctypes.c_int(f), _ptr(x), _ptr(P), ctypes.c_int(1 if cam_only else 0)))
+        return x, P
+
+    def get_descriptors(self, f=0):
+        _, N = self.dims(f)
+        d = np.zeros((N, 32), np.uint8); tp = np.zeros(N, np.int32); tm = np.zeros(N, np.int32)
+        self._ck(self.L.ekfb_get_descriptors(self.h, ctypes.c_int(f), _ptr(d), _ptr(tp), _ptr(tm)))
+        return d, tp, tm
+
+    # ---- keypoints ----
+    def set_keypoints(self, f, xy, desc):
+        """xy (Kp,2) float32, desc (Kp,32) uint8 host arrays (numpy, or pinned torch tensors via .numpy())."""
+        xy = np.ascontiguousarray(xy, np.float32); desc = np.ascontiguousarray(desc, np.uint8)
+        self._ck(self.L.ekfb_set_keypoints(self.h, ctypes.c_int(f), _ptr(xy), _ptr(desc), ctypes.c_int(xy.shape[0])))
+
+    def set_keypoints_raw(self, f, xy_ptr, desc_ptr, n_kp):
+        self._ck(self.L.ekfb_set_keypoints(self.h, ctypes.c_int(f), ctypes.c_void_p(xy_ptr), ctypes.c_void_p(desc_ptr),
+                                           ctypes.c_int(n_kp)))
+
+    def load_sequence(self, f, frames):
+        """frames: list of (xy, desc) per frame; uploads them all to device memory."""
+        off = np.zeros(len(frames) + 1, np.int32)
+        for t, (xy, _) in enumerate(frames):
+            off[t + 1] = off[t] + xy.shape[0]
+        xy = np.ascontiguousarray(np.concatenate([fr[0] for fr in frames], axis=0), np.float32)
+        ds = np.ascontiguousarray(np.concatenate([fr[1] for fr in frames], axis=0), np.uint8)
+        self._ck(self.L.ekfb_load_sequence(self.h, ctypes.c_int(f), ctypes.c_int(len(frames)), _ptr(off), _ptr(xy), _ptr(ds)))
+
+    def select_frame(self, t):
+        self._ck(self.L.ekfb_select_frame(self.h, ctypes.c_int(t)))
+
+    # ---- phases ----
+    def predict(self): self._ck(self.L.ekfb_predict(self.h))
+    def measure(self): self._ck(self.L.ekfb_measure(self.h))
+    def match(self): self._ck(self.L.ekfb_match(self.h))
+    def ransac(self): self._ck(self.L.ekfb_ransac(self.h))
+    def update(self, which): self._ck(self.L.ekfb_update(self.h, ctypes.c_int(which)))
+    def rescue(self): self._ck(self.L.ekfb_rescue(self.h))
+    def update_map_features(self): self._ck(self.L.ekfb_update_map_features(self.h))
+    def step(self): self._ck(self.L.ekfb_step(self.h))
+    def sync(self): self._ck(self.L.ekfb_sync(self.h))
+
+    # ---- results ----
+    def frame_info(self, f=0):
+        info = FrameInfo()
+        self._ck(self.L.ekfb_get_frame_info(self.h, ctypes.c_int(f), ctypes.byref(info)))
+        return info.as_dict()
+
+    def records(self):
+        arr = (Record * self.n_filters)()
+        self._ck(self.L.ekfb_get_records(self.h, arr))
+        return arr
+
+    def write_records_device(self, device_ptr):
+        self._ck(self.L.ekfb_write_records_device(self.h, ctypes.c_void_p(device_ptr)))
+
+    def feature_results(self, f=0):
+        _, N = self.dims(f)
+        r = dict(vis=np.zeros(N, np.uint8), h=np.zeros((N, 2)), S=np.zeros((N, 4)), Hx=np.zeros((N, 14)),
+                 Hf=np.zeros((N, 12)), matched=np.zeros(N, np.uint8), z=np.zeros((N, 2)), kp=np.zeros(N, np.int32),
+                 dist=np.zeros(N, np.float32), inlier=np.zeros(N, np.uint8), outlier=np.zeros(N, np.uint8),
+                 rescued=np.zeros(N, np.uint8))
+        self._ck(self.L.ekfb_get_feature_results(self.h, ctypes.c_int(f), _ptr(r["vis"]), _ptr(r["h"]), _ptr(r["S"]),
+                                                 _ptr(r["Hx"]), _ptr(r["Hf"]), _ptr(r["matched"]), _ptr(r["z"]),
+                                                 _ptr(r["kp"]), _ptr(r["dist"]), _ptr(r["inlier"]), _ptr(r["outlier"]),
+                                                 _ptr(r["rescued"])))
+        return r
+
+    def get_mask(self, f=0, n_kp=0):
+        p = self.params
+        mask = np.zeros((p.pixels_y, p.pixels_x), np.uint8)
+        ok = np.zeros(max(n_kp, 1), np.uint8)
+        self._ck(self.L.ekfb_get_mask(self.h, ctypes.c_int(f), _ptr(mask), _ptr(ok)))
+        return mask, ok[:n_kp]
+
+    # ---- isolated kernels / timing ----
+    def test_downdate(self, P, Wt):
+        P = np.ascontiguousarray(P, np.float64); Wt = np.ascontiguousarray(Wt, np.float64)
+        out = np.zeros_like(P)
+        self._ck(self.L.ekfb_test_downdate(self.h, ctypes.c_int(P.shape[0]), ctypes.c_int(Wt.shape[0]), _ptr(P), _ptr(Wt),
+                                           _ptr(out)))
+        return out
+
+    def time_update(self, which, reps):
+        a, b = ctypes.c_float(), ctypes.c_float()
+        self._ck(self.L.ekfb_time_update(self.h, ctypes.c_int(which), ctypes.c_int(reps), ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def timer_record(self, slot): self._ck(self.L.ekfb_timer_record(self.h, ctypes.c_int(slot)))
+
+    def timer_elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        self._ck(self.L.ekfb_timer_elapsed_ms(self.h, ctypes.c_int(a), ctypes.c_int(b), ctypes.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True): self._ck(self.L.ekfb_profile_enable(self.h, ctypes.c_int(1 if on else 0)))
+
+    def profile_read(self):
+        ms = (ctypes.c_float * 9)(); ln = (ctypes.c_int32 * 9)()
+        self._ck(self.L.ekfb_profile_read(self.h, ms, ln))
+        return dict(zip(PROFILE_GROUPS, list(ms))), dict(zip(PROFILE_GROUPS, list(ln)))
+
+    def kernel_launches(self):
+        return int(self.L.ekfb_kernel_launches(self.h))

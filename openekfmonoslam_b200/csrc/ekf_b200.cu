@@ -1,0 +1,771 @@
+// ekf_b200.cu -- context management and the C ABI of include/ekf_b200.h.
+// Host side of the B200-native EKF hot path: owns device memory, the stream and the per-frame
+// launch sequence (EKF::step order, E/EKF.cpp:242-572).  Two small device->host reads per frame
+// (after RANSAC and after the rescue gate) size the update launches; everything else is
+// asynchronous on the handle's stream.
+#include "../../include/ekf_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ekf_linalg.cuh"
+
+using namespace ekf;
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char buf_[512];                                                                            \
+            snprintf(buf_, sizeof(buf_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            g_err = buf_;                                                                              \
+            return EKFB_ERR_CUDA;                                                                      \
+        }                                                                                              \
+    } while (0)
+
+#define REQUIRE(cond, msg)          \
+    do {                            \
+        if (!(cond)) {              \
+            g_err = msg;            \
+            return EKFB_ERR_ARG;    \
+        }                           \
+    } while (0)
+
+enum ProfGroup { G_PREDICT = 0, G_MEASURE, G_MATCH, G_RANSAC, G_GAIN, G_CHOL, G_DOWNDATE, G_RESCUE, G_MISC, G_COUNT };
+
+struct SeqDev {
+    float* xy = nullptr;
+    uint8_t* desc = nullptr;
+    std::vector<int> off;
+};
+
+struct ekfb_ctx {
+    ekfb_params prm;
+    int device = 0, F = 0, Nmax = 0, nmax = 0, ld = 0, Kpmax = 0, kmax = 0, ldS = 0, supWords = 0;
+    cudaStream_t stream = nullptr;
+    DevView v;
+    std::vector<void*> allocs;
+    std::vector<int> hn, hN, hKp;  // host copies of per-filter sizes
+    int* h_dims = nullptr;          // pinned mirror of v.dims
+    float* d_kpxy = nullptr;        // staging for ekfb_set_keypoints
+    uint8_t* d_kpdesc = nullptr;
+    const float** h_kpxy_ptr = nullptr;  // pinned
+    const uint8_t** h_kpdesc_ptr = nullptr;
+    const float** d_kpxy_ptr = nullptr;
+    const uint8_t** d_kpdesc_ptr = nullptr;
+    std::vector<SeqDev> seq;
+    RecordDev* d_rec = nullptr;
+    RecordDev* h_rec = nullptr;  // pinned
+    cudaEvent_t timers[64];
+    // profiling
+    bool prof = false;
+    cudaEvent_t pe[2];
+    float prof_ms[G_COUNT];
+    int prof_launch[G_COUNT];
+    int cur_group = G_MISC;
+    int64_t launches = 0;
+    float last_downdate_ms = 0.f;
+};
+
+template <typename T>
+static int dev_alloc(ekfb_ctx* c, T** p, size_t count)
+{
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    CK(cudaMemsetAsync(q, 0, std::max<size_t>(count, 1) * sizeof(T), c->stream));
+    c->allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return EKFB_OK;
+}
+
+#define ALLOC(ptr, count)                                   \
+    do {                                                    \
+        int rc_ = dev_alloc(c, &(ptr), (size_t)(count));    \
+        if (rc_ != EKFB_OK) return rc_;                     \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int rup(int a, int b) { return cdiv(a, b) * b; }
+
+struct GroupScope {
+    ekfb_ctx* c;
+    int g;
+    GroupScope(ekfb_ctx* c_, int g_) : c(c_), g(g_)
+    {
+        c->cur_group = g;
+        if (c->prof) cudaEventRecord(c->pe[0], c->stream);
+    }
+    ~GroupScope()
+    {
+        if (c->prof) {
+            cudaEventRecord(c->pe[1], c->stream);
+            cudaEventSynchronize(c->pe[1]);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->pe[0], c->pe[1]);
+            c->prof_ms[g] += ms;
+        }
+        c->cur_group = G_MISC;
+    }
+};
+
+static inline void count_launch(ekfb_ctx* c, int nlaunch = 1)
+{
+    c->launches += nlaunch;
+    c->prof_launch[c->cur_group] += nlaunch;
+}
+
+extern "C" const char* ekfb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int max_features, int max_keypoints,
+                           ekfb_handle* out)
+{
+    REQUIRE(p && out, "null argument");
+    REQUIRE(n_filters > 0 && max_features > 0 && max_keypoints > 0, "sizes must be positive");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        g_err = "libekf_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return EKFB_ERR_CUDA;
+    }
+    ekfb_ctx* c = new ekfb_ctx();
+    c->prm = *p;
+    c->device = device;
+    c->F = n_filters;
+    c->Nmax = max_features;
+    c->nmax = 13 + 6 * max_features;
+    c->ld = rup(c->nmax + 1, 16);
+    c->Kpmax = max_keypoints;
+    c->kmax = rup(2 * max_features, kNB);
+    c->ldS = rup(c->kmax, 16);
+    c->supWords = cdiv(max_features, 32);
+    std::memset(c->prof_ms, 0, sizeof(c->prof_ms));
+    std::memset(c->prof_launch, 0, sizeof(c->prof_launch));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 64; ++i) CK(cudaEventCreate(&c->timers[i]));
+    CK(cudaEventCreate(&c->pe[0]));
+    CK(cudaEventCreate(&c->pe[1]));
+
+    const size_t F = c->F, N = c->Nmax;
+    DevView& v = c->v;
+    std::memset(&v, 0, sizeof(v));
+    v.F = c->F; v.Nmax = c->Nmax; v.nmax = c->nmax; v.ld = c->ld; v.Kpmax = c->Kpmax; v.kmax = c->kmax;
+    v.ldS = c->ldS; v.W = p->pixels_x; v.H = p->pixels_y; v.supWords = c->supWords;
+    v.maxAxes = (int)(2.0 * std::max(p->pixels_x, p->pixels_y));  // E/Matching.cpp:198
+    v.cam.fx = p->fx; v.cam.fy = p->fy; v.cam.k1 = p->k1; v.cam.k2 = p->k2; v.cam.cx = p->cx; v.cam.cy = p->cy;
+    v.cam.dx = p->dx; v.cam.dy = p->dy; v.cam.fov_x = p->angular_vision_x; v.cam.fov_y = p->angular_vision_y;
+    v.cam.width = p->pixels_x; v.cam.height = p->pixels_y;
+    v.sd_lin = p->linear_accel_sd; v.sd_ang = p->angular_accel_sd; v.sigma_px = p->pixel_error_x;
+    v.match_coef = p->matching_coef; v.ransac_thr = p->ransac_threshold; v.ransac_p = p->ransac_all_inliers_prob;
+    v.chi2 = p->ransac_chi2;
+
+    ALLOC(v.x, F * c->ld);
+    ALLOC(v.P, F * c->nmax * c->ld);
+    ALLOC(v.ftype, F * N); ALLOC(v.foff, F * N); ALLOC(v.desc, F * N * 32);
+    ALLOC(v.tpred, F * N); ALLOC(v.tmatch, F * N); ALLOC(v.dims, F * D_STRIDE);
+    ALLOC(v.vis, F * N); ALLOC(v.h, F * N * 2); ALLOC(v.Si, F * N * 4); ALLOC(v.Hx, F * N * 14); ALLOC(v.Hf, F * N * 12);
+    ALLOC(v.ellax, F * N * 2); ALLOC(v.ellang, F * N);
+    ALLOC(v.vis2, F * N); ALLOC(v.h2, F * N * 2); ALLOC(v.Si2, F * N * 4); ALLOC(v.Hx2, F * N * 14); ALLOC(v.Hf2, F * N * 12);
+    ALLOC(v.mflag, F * N); ALLOC(v.z, F * N * 2); ALLOC(v.mkp, F * N); ALLOC(v.mdist, F * N); ALLOC(v.mlist, F * N);
+    ALLOC(v.inl, F * N); ALLOC(v.outl, F * N); ALLOC(v.resc, F * N); ALLOC(v.ulist, F * N);
+    ALLOC(v.kpok, F * c->Kpmax); ALLOC(v.mask, F * (size_t)v.W * v.H);
+    ALLOC(v.hypcount, F * N); ALLOC(v.hypsup, F * N * c->supWords);
+    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.Dinv, F * kNB * kNB); ALLOC(v.Jq, F * 16);
+    ALLOC(c->d_kpxy, F * c->Kpmax * 2); ALLOC(c->d_kpdesc, F * c->Kpmax * 32);
+    ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F);
+    ALLOC(c->d_rec, F);
+    v.kpxy = c->d_kpxy_ptr;
+    v.kpdesc = c->d_kpdesc_ptr;
+    CK(cudaMallocHost(&c->h_dims, F * D_STRIDE * sizeof(int)));
+    CK(cudaMallocHost(&c->h_kpxy_ptr, F * sizeof(void*)));
+    CK(cudaMallocHost(&c->h_kpdesc_ptr, F * sizeof(void*)));
+    CK(cudaMallocHost(&c->h_rec, F * sizeof(RecordDev)));
+    std::memset(c->h_dims, 0, F * D_STRIDE * sizeof(int));
+    for (int f = 0; f < c->F; ++f) {
+        c->h_kpxy_ptr[f] = c->d_kpxy + (size_t)f * c->Kpmax * 2;
+        c->h_kpdesc_ptr[f] = c->d_kpdesc + (size_t)f * c->Kpmax * 32;
+    }
+    CK(cudaMemcpyAsync(c->d_kpxy_ptr, c->h_kpxy_ptr, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_kpdesc_ptr, c->h_kpdesc_ptr, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    c->hn.assign(c->F, 13);
+    c->hN.assign(c->F, 0);
+    c->hKp.assign(c->F, 0);
+    c->seq.resize(c->F);
+
+    CK(cudaFuncSetAttribute(k_gemm_tn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_tn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_tn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDiagSmem));
+    CK(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholPanelSmem));
+    CK(cudaFuncSetAttribute(k_ransac_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            std::min<int>(227 * 1024 - 2048, c->ld * (int)sizeof(double))));
+    const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
+    CK(cudaFuncSetAttribute(k_mask_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, rasterSmem));
+    CK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_destroy(ekfb_handle c)
+{
+    if (!c) return EKFB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    for (SeqDev& s : c->seq) {
+        if (s.xy) cudaFree(s.xy);
+        if (s.desc) cudaFree(s.desc);
+    }
+    cudaFreeHost(c->h_dims);
+    cudaFreeHost(c->h_kpxy_ptr);
+    cudaFreeHost(c->h_kpdesc_ptr);
+    cudaFreeHost(c->h_rec);
+    for (int i = 0; i < 64; ++i) cudaEventDestroy(c->timers[i]);
+    cudaEventDestroy(c->pe[0]);
+    cudaEventDestroy(c->pe[1]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_sync(ekfb_handle c)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+// ---- state in / out ---------------------------------------------------------------------------
+extern "C" int ekfb_set_state(ekfb_handle c, int f, int n, int N, const double* x, const int32_t* ftype,
+                              const int32_t* foff, const double* P, const uint8_t* desc)
+{
+    REQUIRE(c && x && P && (N == 0 || (ftype && foff)), "null argument");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    if (n > c->nmax || N > c->Nmax || n < 13) {
+        g_err = "state exceeds the capacity reserved by ekfb_create";
+        return EKFB_ERR_CAPACITY;
+    }
+    CK(cudaSetDevice(c->device));
+    DevView& v = c->v;
+    CK(cudaMemsetAsync(v.x + (size_t)f * c->ld, 0, sizeof(double) * c->ld, c->stream));
+    CK(cudaMemcpyAsync(v.x + (size_t)f * c->ld, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpy2DAsync(v.P + (size_t)f * c->nmax * c->ld, sizeof(double) * c->ld, P, sizeof(double) * n,
+                         sizeof(double) * n, n, cudaMemcpyHostToDevice, c->stream));
+    if (N > 0) {
+        CK(cudaMemcpyAsync(v.ftype + (size_t)f * c->Nmax, ftype, sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(v.foff + (size_t)f * c->Nmax, foff, sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
+        if (desc)
+            CK(cudaMemcpyAsync(v.desc + (size_t)f * c->Nmax * 32, desc, (size_t)N * 32, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(v.tpred + (size_t)f * c->Nmax, 0, sizeof(int) * N, c->stream));
+        CK(cudaMemsetAsync(v.tmatch + (size_t)f * c->Nmax, 0, sizeof(int) * N, c->stream));
+    }
+    int* hd = c->h_dims + (size_t)f * D_STRIDE;
+    std::memset(hd, 0, sizeof(int) * D_STRIDE);
+    hd[D_N_STATE] = n;
+    hd[D_N_FEAT] = N;
+    hd[D_N_KP] = c->hKp[f];
+    CK(cudaMemcpyAsync(v.dims + (size_t)f * D_STRIDE, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // caller buffers may be pageable
+    c->hn[f] = n;
+    c->hN[f] = N;
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_state(ekfb_handle c, int f, double* x, double* P, int cam_only)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    const int n = cam_only ? 13 : c->hn[f];
+    if (x) CK(cudaMemcpyAsync(x, c->v.x + (size_t)f * c->ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (P)
+        CK(cudaMemcpy2DAsync(P, sizeof(double) * n, c->v.P + (size_t)f * c->nmax * c->ld, sizeof(double) * c->ld,
+                             sizeof(double) * n, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_descriptors(ekfb_handle c, int f, uint8_t* desc, int32_t* tp, int32_t* tm)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    const int N = c->hN[f];
+    if (desc) CK(cudaMemcpyAsync(desc, c->v.desc + (size_t)f * c->Nmax * 32, (size_t)N * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (tp) CK(cudaMemcpyAsync(tp, c->v.tpred + (size_t)f * c->Nmax, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+    if (tm) CK(cudaMemcpyAsync(tm, c->v.tmatch + (size_t)f * c->Nmax, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_dims(ekfb_handle c, int f, int32_t* n, int32_t* N)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    if (n) *n = c->hn[f];
+    if (N) *N = c->hN[f];
+    return EKFB_OK;
+}
+
+// ---- keypoints ----------------------------------------------------------------------------------
+static int push_kp_meta(ekfb_ctx* c)
+{
+    const size_t F = c->F;
+    for (int f = 0; f < c->F; ++f) c->h_dims[(size_t)f * D_STRIDE + D_N_KP] = c->hKp[f];
+    CK(cudaMemcpyAsync(c->d_kpxy_ptr, c->h_kpxy_ptr, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_kpdesc_ptr, c->h_kpdesc_ptr, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    for (int f = 0; f < c->F; ++f)
+        CK(cudaMemcpyAsync(c->v.dims + (size_t)f * D_STRIDE + D_N_KP, c->h_dims + (size_t)f * D_STRIDE + D_N_KP,
+                           sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_set_keypoints(ekfb_handle c, int f, const float* xy, const uint8_t* desc, int n_kp)
+{
+    REQUIRE(c && (n_kp == 0 || (xy && desc)), "null argument");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    if (n_kp > c->Kpmax || n_kp < 0) {
+        g_err = "keypoint count exceeds the capacity reserved by ekfb_create";
+        return EKFB_ERR_CAPACITY;
+    }
+    CK(cudaSetDevice(c->device));
+    float* dxy = c->d_kpxy + (size_t)f * c->Kpmax * 2;
+    uint8_t* dds = c->d_kpdesc + (size_t)f * c->Kpmax * 32;
+    if (n_kp > 0) {
+        CK(cudaMemcpyAsync(dxy, xy, sizeof(float) * 2 * n_kp, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(dds, desc, (size_t)32 * n_kp, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->hKp[f] = n_kp;
+    c->h_kpxy_ptr[f] = dxy;
+    c->h_kpdesc_ptr[f] = dds;
+    c->h_dims[(size_t)f * D_STRIDE + D_N_KP] = n_kp;
+    CK(cudaMemcpyAsync(c->d_kpxy_ptr + f, c->h_kpxy_ptr + f, sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_kpdesc_ptr + f, c->h_kpdesc_ptr + f, sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v.dims + (size_t)f * D_STRIDE + D_N_KP, c->h_dims + (size_t)f * D_STRIDE + D_N_KP, sizeof(int),
+                       cudaMemcpyHostToDevice, c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_load_sequence(ekfb_handle c, int f, int n_frames, const int32_t* kp_offset, const float* xy,
+                                  const uint8_t* desc)
+{
+    REQUIRE(c && kp_offset && xy && desc && n_frames > 0, "null argument");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    SeqDev& s = c->seq[f];
+    if (s.xy) cudaFree(s.xy);
+    if (s.desc) cudaFree(s.desc);
+    s.xy = nullptr;
+    s.desc = nullptr;
+    s.off.assign(kp_offset, kp_offset + n_frames + 1);
+    for (int t = 0; t < n_frames; ++t)
+        if (s.off[t + 1] - s.off[t] > c->Kpmax || s.off[t + 1] < s.off[t]) {
+            g_err = "a frame of the sequence exceeds max_keypoints";
+            return EKFB_ERR_CAPACITY;
+        }
+    const size_t total = (size_t)s.off[n_frames];
+    CK(cudaMalloc(&s.xy, std::max<size_t>(total, 1) * 2 * sizeof(float)));
+    CK(cudaMalloc(&s.desc, std::max<size_t>(total, 1) * 32));
+    CK(cudaMemcpyAsync(s.xy, xy, total * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(s.desc, desc, total * 32, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_select_frame(ekfb_handle c, int frame)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    for (int f = 0; f < c->F; ++f) {
+        SeqDev& s = c->seq[f];
+        REQUIRE(s.xy && frame >= 0 && frame + 1 < (int)s.off.size(), "no such frame in the loaded sequence");
+        c->h_kpxy_ptr[f] = s.xy + (size_t)s.off[frame] * 2;
+        c->h_kpdesc_ptr[f] = s.desc + (size_t)s.off[frame] * 32;
+        c->hKp[f] = s.off[frame + 1] - s.off[frame];
+    }
+    return push_kp_meta(c);
+}
+
+// ---- phases ----------------------------------------------------------------------------------------
+static int max_of(const std::vector<int>& a)
+{
+    int m = 0;
+    for (int x : a) m = std::max(m, x);
+    return m;
+}
+
+static int read_dims(ekfb_ctx* c)
+{
+    CK(cudaMemcpyAsync(c->h_dims, c->v.dims, (size_t)c->F * D_STRIDE * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_predict(ekfb_handle c)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    GroupScope gs(c, G_PREDICT);
+    const int n = max_of(c->hn);
+    dim3 grid(1 + cdiv(std::max(n - 13, 0), 256), c->F);
+    k_predict_cov<<<grid, 256, 0, c->stream>>>(c->v);
+    k_predict_state<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->v);
+    count_launch(c, 2);
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+static int launch_measure(ekfb_ctx* c, int mode)
+{
+    const int N = max_of(c->hN);
+    if (N == 0) return EKFB_OK;
+    dim3 grid(cdiv(N, 8), c->F);
+    k_measure<<<grid, 256, 0, c->stream>>>(c->v, mode);
+    count_launch(c);
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_measure(ekfb_handle c)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    GroupScope gs(c, G_MEASURE);
+    return launch_measure(c, 0);
+}
+
+extern "C" int ekfb_match(ekfb_handle c)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    GroupScope gs(c, G_MATCH);
+    const int N = max_of(c->hN), Kp = max_of(c->hKp);
+    DevView& v = c->v;
+    CK(cudaMemsetAsync(v.mask, 0, (size_t)c->F * v.W * v.H, c->stream));
+    if (N > 0) {
+        const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
+        k_mask_raster<<<dim3(cdiv(N, 4), c->F), 128, rasterSmem, c->stream>>>(v);
+        count_launch(c);
+        if (Kp > 0) {
+            k_kp_mask<<<dim3(cdiv(Kp, 256), c->F), 256, 0, c->stream>>>(v);
+            count_launch(c);
+        }
+        k_match<<<dim3(cdiv(N, 8), c->F), 256, 0, c->stream>>>(v);
+        count_launch(c);
+    }
+    k_after_match<<<c->F, 256, 0, c->stream>>>(v);
+    count_launch(c);
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_ransac(ekfb_handle c)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    GroupScope gs(c, G_RANSAC);
+    const int CH = 16;
+    const int n = max_of(c->hn), N = max_of(c->hN);
+    const size_t smem = sizeof(double) * (size_t)n;
+    for (int chunk0 = 0; chunk0 < std::max(N, 1); chunk0 += CH) {
+        k_ransac_hyp<<<dim3(CH, c->F), 256, smem, c->stream>>>(c->v, chunk0);
+        k_ransac_select<<<c->F, 256, 0, c->stream>>>(c->v, chunk0, CH);
+        count_launch(c, 2);
+        CK(cudaGetLastError());
+        int rc = read_dims(c);
+        if (rc != EKFB_OK) return rc;
+        bool all = true;
+        for (int f = 0; f < c->F; ++f) all = all && c->h_dims[(size_t)f * D_STRIDE + D_RANSAC_DONE];
+        if (all) break;
+    }
+    return EKFB_OK;
+}
+
+// update() for the list currently in ulist (host mirror of the counts must be fresh)
+static int run_update(ekfb_ctx* c, int which)
+{
+    DevView& v = c->v;
+    int ku = 0;
+    for (int f = 0; f < c->F; ++f) ku = std::max(ku, c->h_dims[(size_t)f * D_STRIDE + D_ULIST]);
+    if (ku == 0) return EKFB_OK;
+    const int k = 2 * ku, n = max_of(c->hn);
+    {
+        GroupScope gs(c, G_GAIN);
+        k_gain_rows<<<dim3(cdiv(c->ld, 256), ku, c->F), 256, 0, c->stream>>>(v, which);
+        k_build_S<<<dim3(cdiv(k, 16), cdiv(k, 16), c->F), dim3(16, 16), 0, c->stream>>>(v, which);
+        count_launch(c, 2);
+    }
+    {
+        GroupScope gs(c, G_CHOL);
+        const int steps = cdiv(k, kNB);
+        for (int J = 0; J < steps; ++J) {
+            const int J1 = (J + 1) * kNB;
+            k_chol_diag<<<c->F, 256, kCholDiagSmem, c->stream>>>(v, J);
+            const int nS = k > J1 ? cdiv(k - J1, 128) : 0;
+            const int nB = cdiv(n + 1, 128);
+            k_chol_panel<<<dim3(nS + nB, c->F), 256, kCholPanelSmem, c->stream>>>(v, J);
+            count_launch(c, 2);
+            if (k > J1) {
+                const int mt = cdiv(k - J1, kTM);
+                k_gemm_tn<0><<<dim3(mt, mt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, J);
+                k_gemm_tn<1><<<dim3(cdiv(n + 1, kTN), mt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, J);
+                count_launch(c, 2);
+            }
+        }
+        k_state_update<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
+        k_quat_norm<<<cdiv(c->F, 128), 128, 0, c->stream>>>(v);
+        count_launch(c, 2);
+    }
+    {
+        GroupScope gs(c, G_DOWNDATE);
+        const int nt = cdiv(n, kTM);
+        k_gemm_tn<2><<<dim3(nt, nt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, 0);
+        k_quat_cov<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
+        count_launch(c, 2);
+    }
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_update(ekfb_handle c, int which)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(which == 0 || which == 1, "which must be 0 (low innovation) or 1 (high innovation)");
+    CK(cudaSetDevice(c->device));
+    return run_update(c, which);
+}
+
+extern "C" int ekfb_rescue(ekfb_handle c)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    GroupScope gs(c, G_RESCUE);
+    int rc = launch_measure(c, 1);
+    if (rc != EKFB_OK) return rc;
+    k_rescue_gate<<<c->F, 256, 0, c->stream>>>(c->v);
+    count_launch(c);
+    CK(cudaGetLastError());
+    return read_dims(c);
+}
+
+extern "C" int ekfb_update_map_features(ekfb_handle c)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    GroupScope gs(c, G_MISC);
+    const int N = max_of(c->hN);
+    if (N == 0) return EKFB_OK;
+    k_update_map_features<<<dim3(cdiv(N, 256), c->F), 256, 0, c->stream>>>(c->v);
+    count_launch(c);
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_step(ekfb_handle c)
+{
+    int rc;
+    if ((rc = ekfb_predict(c)) != EKFB_OK) return rc;
+    if ((rc = ekfb_measure(c)) != EKFB_OK) return rc;
+    if ((rc = ekfb_match(c)) != EKFB_OK) return rc;
+    if ((rc = ekfb_ransac(c)) != EKFB_OK) return rc;
+    if ((rc = ekfb_update(c, 0)) != EKFB_OK) return rc;
+    if ((rc = ekfb_rescue(c)) != EKFB_OK) return rc;
+    if ((rc = ekfb_update(c, 1)) != EKFB_OK) return rc;
+    if ((rc = ekfb_update_map_features(c)) != EKFB_OK) return rc;
+    return EKFB_OK;
+}
+
+// ---- results -----------------------------------------------------------------------------------
+static void fill_info(const int* d, ekfb_frame_info* o)
+{
+    o->n = d[D_N_STATE]; o->n_features = d[D_N_FEAT]; o->n_keypoints = d[D_N_KP]; o->n_predicted = d[D_N_PRED];
+    o->n_matches = d[D_N_MATCH]; o->n_hypotheses = d[D_N_HYP]; o->best_hypothesis = d[D_BEST_HYP];
+    o->n_inliers = d[D_N_INL]; o->n_outliers = d[D_N_OUT]; o->n_rescued = d[D_N_RESC]; o->status = d[D_STATUS];
+    o->reserved = 0;
+}
+
+extern "C" int ekfb_get_frame_info(ekfb_handle c, int f, ekfb_frame_info* info)
+{
+    REQUIRE(c && info, "null argument");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    int rc = read_dims(c);
+    if (rc != EKFB_OK) return rc;
+    fill_info(c->h_dims + (size_t)f * D_STRIDE, info);
+    return EKFB_OK;
+}
+
+static_assert(sizeof(RecordDev) == sizeof(ekfb_record), "record layouts must match");
+
+extern "C" int ekfb_write_records_device(ekfb_handle c, void* device_out)
+{
+    REQUIRE(c && device_out, "null argument");
+    CK(cudaSetDevice(c->device));
+    k_write_records<<<c->F, 192, 0, c->stream>>>(c->v, reinterpret_cast<RecordDev*>(device_out));
+    count_launch(c);
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_records(ekfb_handle c, ekfb_record* out)
+{
+    REQUIRE(c && out, "null argument");
+    int rc = ekfb_write_records_device(c, c->d_rec);
+    if (rc != EKFB_OK) return rc;
+    CK(cudaMemcpyAsync(c->h_rec, c->d_rec, sizeof(RecordDev) * c->F, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(out, c->h_rec, sizeof(RecordDev) * c->F);
+    return EKFB_OK;
+}
+
+#define D2H(dst, src, count, T)                                                                              \
+    do {                                                                                                     \
+        if (dst) CK(cudaMemcpyAsync(dst, (src), sizeof(T) * (size_t)(count), cudaMemcpyDeviceToHost, c->stream)); \
+    } while (0)
+
+extern "C" int ekfb_get_feature_results(ekfb_handle c, int f, uint8_t* predicted, double* hpred, double* S, double* Hx,
+                                        double* Hf, uint8_t* matched, double* z, int32_t* kp_index, float* dist,
+                                        uint8_t* inlier, uint8_t* outlier, uint8_t* rescued)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    const size_t fo = (size_t)f * c->Nmax;
+    const int N = c->hN[f];
+    DevView& v = c->v;
+    D2H(predicted, v.vis + fo, N, uint8_t);
+    D2H(hpred, v.h + fo * 2, N * 2, double);
+    D2H(S, v.Si + fo * 4, N * 4, double);
+    D2H(Hx, v.Hx + fo * 14, N * 14, double);
+    D2H(Hf, v.Hf + fo * 12, N * 12, double);
+    D2H(matched, v.mflag + fo, N, uint8_t);
+    D2H(z, v.z + fo * 2, N * 2, double);
+    D2H(kp_index, v.mkp + fo, N, int);
+    D2H(dist, v.mdist + fo, N, float);
+    D2H(inlier, v.inl + fo, N, uint8_t);
+    D2H(outlier, v.outl + fo, N, uint8_t);
+    D2H(rescued, v.resc + fo, N, uint8_t);
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_mask(ekfb_handle c, int f, uint8_t* mask, uint8_t* kp_ok)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    DevView& v = c->v;
+    D2H(mask, v.mask + (size_t)f * v.W * v.H, (size_t)v.W * v.H, uint8_t);
+    D2H(kp_ok, v.kpok + (size_t)f * c->Kpmax, c->hKp[f], uint8_t);
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+// ---- isolated kernels -------------------------------------------------------------------------------
+extern "C" int ekfb_test_downdate(ekfb_handle c, int n, int k, const double* P_in, const double* Wt, double* P_out)
+{
+    REQUIRE(c && P_in && Wt && P_out, "null argument");
+    REQUIRE(n >= 13 && n <= c->nmax && k > 0 && k <= c->kmax && (k % 2) == 0, "n or k out of range (k must be even)");
+    CK(cudaSetDevice(c->device));
+    DevView& v = c->v;
+    CK(cudaMemcpy2DAsync(v.P, sizeof(double) * c->ld, P_in, sizeof(double) * n, sizeof(double) * n, n,
+                         cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(v.Bu, 0, sizeof(double) * (size_t)k * c->ld, c->stream));
+    CK(cudaMemcpy2DAsync(v.Bu, sizeof(double) * c->ld, Wt, sizeof(double) * n, sizeof(double) * n, k,
+                         cudaMemcpyHostToDevice, c->stream));
+    int* hd = c->h_dims;
+    const int save_n = hd[D_N_STATE], save_u = hd[D_ULIST];
+    hd[D_N_STATE] = n;
+    hd[D_ULIST] = k / 2;
+    CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    const int nt = cdiv(n, kTM);
+    CK(cudaEventRecord(c->pe[0], c->stream));
+    k_gemm_tn<2><<<dim3(nt, nt, 1), 256, kGemmSmemBytes, c->stream>>>(v, 0);
+    CK(cudaEventRecord(c->pe[1], c->stream));
+    count_launch(c);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(P_out, sizeof(double) * n, v.P, sizeof(double) * c->ld, sizeof(double) * n, n,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->last_downdate_ms, c->pe[0], c->pe[1]));
+    hd[D_N_STATE] = save_n;
+    hd[D_ULIST] = save_u;
+    CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_time_update(ekfb_handle c, int which, int reps, float* ms_total, float* ms_downdate)
+{
+    REQUIRE(c && reps > 0, "bad argument");
+    CK(cudaSetDevice(c->device));
+    // total: reps full updates on the current list; downdate: the P -= W W^T kernel alone, reps times
+    CK(cudaEventRecord(c->timers[62], c->stream));
+    for (int r = 0; r < reps; ++r) {
+        int rc = run_update(c, which);
+        if (rc != EKFB_OK) return rc;
+    }
+    CK(cudaEventRecord(c->timers[63], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->timers[62], c->timers[63]));
+    if (ms_total) *ms_total = ms / reps;
+    const int n = max_of(c->hn), nt = cdiv(n, kTM);
+    CK(cudaEventRecord(c->timers[62], c->stream));
+    for (int r = 0; r < reps; ++r) k_gemm_tn<2><<<dim3(nt, nt, c->F), 256, kGemmSmemBytes, c->stream>>>(c->v, 0);
+    CK(cudaEventRecord(c->timers[63], c->stream));
+    count_launch(c, reps);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&ms, c->timers[62], c->timers[63]));
+    if (ms_downdate) *ms_downdate = ms / reps;
+    return EKFB_OK;
+}
+
+// ---- timing ------------------------------------------------------------------------------------------
+extern "C" int ekfb_timer_record(ekfb_handle c, int slot)
+{
+    REQUIRE(c && slot >= 0 && slot < 62, "bad timer slot");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->timers[slot], c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_timer_elapsed_ms(ekfb_handle c, int a, int b, float* ms)
+{
+    REQUIRE(c && ms && a >= 0 && a < 62 && b >= 0 && b < 62, "bad timer slot");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->timers[b]));
+    CK(cudaEventElapsedTime(ms, c->timers[a], c->timers[b]));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_profile_enable(ekfb_handle c, int on)
+{
+    REQUIRE(c, "null handle");
+    c->prof = on != 0;
+    std::memset(c->prof_ms, 0, sizeof(c->prof_ms));
+    std::memset(c->prof_launch, 0, sizeof(c->prof_launch));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_profile_read(ekfb_handle c, float* ms9, int32_t* launches9)
+{
+    REQUIRE(c, "null handle");
+    for (int g = 0; g < G_COUNT; ++g) {
+        if (ms9) ms9[g] = c->prof_ms[g];
+        if (launches9) launches9[g] = c->prof_launch[g];
+    }
+    std::memset(c->prof_ms, 0, sizeof(c->prof_ms));
+    std::memset(c->prof_launch, 0, sizeof(c->prof_launch));
+    return EKFB_OK;
+}
+
+extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches : 0; }

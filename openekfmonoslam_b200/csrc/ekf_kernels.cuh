@@ -1,0 +1,605 @@
+// ekf_kernels.cuh -- per-frame kernels other than the dense linear algebra: covariance/state
+// prediction, measurement prediction + Jacobians, mask + descriptor matching, 1-point RANSAC
+// hypothesis scoring, outlier rescue, map-feature bookkeeping.  sm_100a, FP64 maths, one grid
+// dimension always indexes the filter of the batch.
+//
+// Data layout (device, per filter f, all arrays filter-major with fixed strides):
+//   x[f][ld]            state vector: camera 13, then features at their covarianceMatrixPos
+//   P[f][nmax][ld]      covariance, row-major, leading dimension ld (multiple of 16 doubles = 128 B)
+//   ftype/foff[f][Nmax] feature type (1 XYZ / 2 inverse depth) and covarianceMatrixPos
+//   per-frame, indexed by FEATURE (lists are ascending feature order everywhere in the reference,
+//   so a list is a flag array plus a rank->feature table built by an ordered block scan):
+//   vis,h,Si,Hx,Hf,ell  measurement prediction;  mflag,z,mkp,mdist  matches;  inl/outl/resc flags
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ekf_math.cuh"
+#include "ekf_raster.cuh"
+
+namespace ekf {
+
+enum DimSlot {
+    D_N_STATE = 0, D_N_FEAT = 1, D_N_KP = 2, D_N_PRED = 3, D_N_MATCH = 4, D_N_HYP = 5, D_BEST_HYP = 6, D_N_INL = 7,
+    D_N_OUT = 8, D_N_RESC = 9, D_STATUS = 10, D_RANSAC_DONE = 11, D_RANSAC_NEXT = 12, D_RANSAC_CAP = 13,
+    D_BEST_COUNT = 14, D_ULIST = 15, D_N_PRED2 = 16, D_STRIDE = 32
+};
+
+struct DevView {
+    int F, Nmax, nmax, ld, Kpmax, kmax, ldS, W, H, supWords, maxAxes;
+    CamParams cam;
+    double sd_lin, sd_ang, sigma_px, match_coef, ransac_thr, ransac_p, chi2;
+    double* x; double* P;
+    int* ftype; int* foff; uint8_t* desc; int* tpred; int* tmatch; int* dims;
+    uint8_t* vis; double* h; double* Si; double* Hx; double* Hf; float* ellax; double* ellang;
+    uint8_t* vis2; double* h2; double* Si2; double* Hx2; double* Hf2;
+    uint8_t* mflag; double* z; int* mkp; float* mdist; int* mlist;
+    uint8_t* inl; uint8_t* outl; uint8_t* resc; int* ulist;
+    const float* const* kpxy; const uint8_t* const* kpdesc; uint8_t* kpok; uint8_t* mask;
+    int* hypcount; uint32_t* hypsup;
+    double* Bu; double* S; double* Dinv; double* Jq;
+};
+
+__device__ __forceinline__ int* fdims(const DevView& v, int f) { return v.dims + (size_t)f * D_STRIDE; }
+
+// ---------------------------------------------------------------------------------------------
+// P1: P <- F P F^T + G Q G^T on the 13 camera rows / columns (E/StateAndCovariancePrediction.cpp:154-240).
+// Only rows 0..12 and their mirror columns change: a batched row-block update.  Block 0 does the
+// 13x13 block, the others own 256 columns each: thread j reads P[0:13, j], forms F * col and writes
+// the 13 new row entries (coalesced across j) plus the mirrored 13-double row segment P[j, 0:13].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_predict_cov(DevView v)
+{
+    const int f = blockIdx.y;
+    const int n = fdims(v, f)[D_N_STATE];
+    __shared__ double F[169], GQG[169], Pxx[169], T[169];
+    double* P = v.P + (size_t)f * v.nmax * v.ld;
+    const double* x = v.x + (size_t)f * v.ld;
+    if (threadIdx.x == 0) motion_jacobians(x, v.sd_lin, v.sd_ang, F, GQG);
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < 169; e += blockDim.x) Pxx[e] = P[(size_t)(e / 13) * v.ld + (e % 13)];
+        __syncthreads();
+        for (int e = threadIdx.x; e < 169; e += blockDim.x) {
+            const int i = e / 13, j = e % 13;
+            double s = 0.;
+            for (int k = 0; k < 13; ++k) s += F[i * 13 + k] * Pxx[k * 13 + j];
+            T[e] = s;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 169; e += blockDim.x) {
+            const int i = e / 13, j = e % 13;
+            if (j > i) continue;  // lower triangle, mirrored: the block stays exactly symmetric
+            double s = 0.;
+            for (int k = 0; k < 13; ++k) s += T[i * 13 + k] * F[j * 13 + k];
+            s += GQG[i * 13 + j];
+            P[(size_t)i * v.ld + j] = s;
+            P[(size_t)j * v.ld + i] = s;
+        }
+    } else {
+        const int j = 13 + (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+        if (j < n) {
+            double col[13], out[13];
+#pragma unroll
+            for (int k = 0; k < 13; ++k) col[k] = P[(size_t)k * v.ld + j];
+#pragma unroll
+            for (int i = 0; i < 13; ++i) {
+                double s = 0.;
+#pragma unroll
+                for (int k = 0; k < 13; ++k) s += F[i * 13 + k] * col[k];
+                out[i] = s;
+            }
+#pragma unroll
+            for (int i = 0; i < 13; ++i) {
+                P[(size_t)i * v.ld + j] = out[i];
+                P[(size_t)j * v.ld + i] = out[i];
+            }
+        }
+    }
+}
+
+// P2: x <- f(x), after P1 (E/StateAndCovariancePrediction.cpp:43-65,252)
+__global__ void k_predict_state(DevView v)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= v.F) return;
+    motion_predict(v.x + (size_t)f * v.ld);
+}
+
+// ---------------------------------------------------------------------------------------------
+// H1 + H2: one warp per feature.  Every lane evaluates the scalar chain h(x), H_x, H_f (no
+// divergence); the 2x2 innovation covariance S_i = H_i P H_i^T + I is a gather of the (7+d)^2
+// block of P split over the lanes and reduced with shuffles (E/MeasurementPrediction.cpp:203-265,
+// 595-658).  mode 0: all features -> vis,h,Si,Hx,Hf,ell.  mode 1: the outlier subset after the
+// low-innovation update -> vis2,h2,Si2,Hx2,Hf2 (E/EKF.cpp:464-468).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_measure(DevView v, int mode)
+{
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    const int N = dm[D_N_FEAT];
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= N) return;
+    const size_t fj = (size_t)f * v.Nmax + j;
+    uint8_t* visOut = mode ? v.vis2 : v.vis;
+    if (mode && !v.outl[fj]) {
+        if (lane == 0) visOut[fj] = 0;
+        return;
+    }
+    const double* x = v.x + (size_t)f * v.ld;
+    const double* P = v.P + (size_t)f * v.nmax * v.ld;
+    const int type = v.ftype[fj], off = v.foff[fj];
+    const int d = (type == kTypeInvDepth) ? 6 : 3;
+    double R[9], Rinv[9], Rt[9], y[6], hh[2];
+    quat_to_rot(x + 3, R);
+    inv3(R, Rinv);
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) Rt[a * 3 + b] = R[b * 3 + a];
+    for (int a = 0; a < 6; ++a) y[a] = (a < d) ? x[off + a] : 0.;
+    const bool visible = predict_pixel(v.cam, x, Rt, Rinv, type, y, hh);
+    if (!visible) {
+        if (lane == 0) visOut[fj] = 0;
+        return;
+    }
+    double Hx[14], Hf[12];
+    measurement_jacobian(v.cam, x, x + 3, Rinv, type, y, hh, Hx, Hf);
+    // S = sum_{a,b in A} H[.,a] P[ia,ib] H[.,b],  A = camera cols 0..6 and the feature's d cols
+    const int na = 7 + d;
+    double s00 = 0., s01 = 0., s10 = 0., s11 = 0.;
+    for (int e = lane; e < na * na; e += 32) {
+        const int a = e / na, b = e % na;
+        const int ia = a < 7 ? a : off + a - 7, ib = b < 7 ? b : off + b - 7;
+        const double p = P[(size_t)ia * v.ld + ib];
+        const double h0a = a < 7 ? Hx[a] : Hf[a - 7], h1a = a < 7 ? Hx[7 + a] : Hf[6 + a - 7];
+        const double h0b = b < 7 ? Hx[b] : Hf[b - 7], h1b = b < 7 ? Hx[7 + b] : Hf[6 + b - 7];
+        s00 += h0a * p * h0b;
+        s01 += h0a * p * h1b;
+        s10 += h1a * p * h0b;
+        s11 += h1a * p * h1b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s00 += __shfl_xor_sync(0xffffffffu, s00, o);
+        s01 += __shfl_xor_sync(0xffffffffu, s01, o);
+        s10 += __shfl_xor_sync(0xffffffffu, s10, o);
+        s11 += __shfl_xor_sync(0xffffffffu, s11, o);
+    }
+    if (lane == 0) {
+        double* hO = (mode ? v.h2 : v.h) + fj * 2;
+        double* sO = (mode ? v.Si2 : v.Si) + fj * 4;
+        double* hxO = (mode ? v.Hx2 : v.Hx) + fj * 14;
+        double* hfO = (mode ? v.Hf2 : v.Hf) + fj * 12;
+        visOut[fj] = 1;
+        hO[0] = hh[0]; hO[1] = hh[1];
+        const double S[4] = {s00 + 1.0, s01, s10, s11 + 1.0};
+        for (int a = 0; a < 4; ++a) sO[a] = S[a];
+        for (int a = 0; a < 14; ++a) hxO[a] = Hx[a];
+        for (int a = 0; a < 12; ++a) hfO[a] = Hf[a];
+        if (!mode) {
+            float aw, ah;
+            double ang;
+            gate_ellipse(S, &aw, &ah, &ang);
+            v.ellax[fj * 2] = aw;
+            v.ellax[fj * 2 + 1] = ah;
+            v.ellang[fj] = ang;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// M1(1): mask = union of filled gate ellipses (E/Matching.cpp:193-202 -> Gui/Draw.cpp:42-64).
+// One warp per predicted feature; dynamic smem: per warp a RasterScratch and 2*H span ints.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mask_raster(DevView v)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.y;
+    const int N = fdims(v, f)[D_N_FEAT];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + wib;
+    const size_t perWarp = sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H;
+    RasterScratch* sc = reinterpret_cast<RasterScratch*>(smem_raw + perWarp * wib);
+    int* spans = reinterpret_cast<int*>(smem_raw + perWarp * wib + sizeof(RasterScratch));
+    if (j >= N) return;
+    const size_t fj = (size_t)f * v.Nmax + j;
+    if (!v.vis[fj]) return;
+    // cv::Point2d -> Point2f -> Point (truncation); Size2f -> MIN(axis, maxAxes) -> int (truncation)
+    const float cxf = (float)v.h[fj * 2], cyf = (float)v.h[fj * 2 + 1];
+    const int icx = (int)cxf, icy = (int)cyf;
+    const float mw = fminf(v.ellax[fj * 2], (float)v.maxAxes), mh = fminf(v.ellax[fj * 2 + 1], (float)v.maxAxes);
+    const int iw = (int)mw, ih = (int)mh;
+    const double angDeg = v.ellang[fj] * 180.0 / kPiTrunc;
+    raster_ellipse_warp(v.mask + (size_t)f * v.W * v.H, v.W, v.H, icx, icy, iw, ih, angDeg, sc, spans, lane);
+}
+
+// keypoint survives the detector mask iff mask[(int)(y+0.5f)][(int)(x+0.5f)] != 0
+// (cv::KeyPointsFilter::runByPixelsMask, applied inside detector->detect, E/Matching.cpp:206)
+__global__ void k_kp_mask(DevView v)
+{
+    const int f = blockIdx.y;
+    const int Kp = fdims(v, f)[D_N_KP];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Kp) return;
+    const float* xy = v.kpxy[f];
+    const int yy = (int)(xy[2 * j + 1] + 0.5f), xx = (int)(xy[2 * j] + 0.5f);
+    const bool ok = xx >= 0 && xx < v.W && yy >= 0 && yy < v.H && v.mask[((size_t)f * v.H + yy) * v.W + xx] != 0;
+    v.kpok[(size_t)f * v.Kpmax + j] = ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// M1(4) + M2 + M3: one warp per predicted feature.  Lanes stride over the keypoints, gate them
+// with the foci test (C/EKFMath.cpp:302-351), ballot-compact the candidates IN KEYPOINT ORDER and
+// replay the reference's order-dependent push-front 2-best rule (E/Matching.cpp:116-144) and its
+// ratio test (:169-175).  Hamming distance of 32-byte descriptors with __popc.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_match(DevView v)
+{
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    const int N = dm[D_N_FEAT], Kp = dm[D_N_KP];
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= N) return;
+    const size_t fj = (size_t)f * v.Nmax + j;
+    if (!v.vis[fj]) {
+        if (lane == 0) v.mflag[fj] = 0;
+        return;
+    }
+    const float* xy = v.kpxy[f];
+    const uint8_t* kd = v.kpdesc[f];
+    const uint8_t* ok = v.kpok + (size_t)f * v.Kpmax;
+    const int iw = __float2int_rn(v.ellax[fj * 2]), ih = __float2int_rn(v.ellax[fj * 2 + 1]);  // Size2f -> Size rounds
+    const float cxf = (float)v.h[fj * 2], cyf = (float)v.h[fj * 2 + 1];
+    const double ang = v.ellang[fj];
+    const uint32_t* fd = reinterpret_cast<const uint32_t*>(v.desc + fj * 32);
+    uint32_t q[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) q[a] = fd[a];
+
+    float minD = -1.f;
+    int size = 0;
+    float dFront = 0.f, dBack = 0.f;
+    int iFront = -1, iBack = -1;
+    for (int base = 0; base < Kp; base += 32) {
+        const int kidx = base + lane;
+        bool cand = false;
+        float dist = 0.f;
+        if (kidx < Kp && ok[kidx]) {
+            cand = inside_gate(xy[2 * kidx], xy[2 * kidx + 1], cxf, cyf, iw, ih, ang);
+            if (cand) {
+                const uint32_t* cdp = reinterpret_cast<const uint32_t*>(kd + (size_t)kidx * 32);
+                int dd = 0;
+#pragma unroll
+                for (int a = 0; a < 8; ++a) dd += __popc(q[a] ^ cdp[a]);
+                dist = (float)dd;
+            }
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, cand);
+        while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const float dcur = __shfl_sync(0xffffffffu, dist, src);
+            if (dcur < minD || size < 2) {
+                minD = (minD < 0.f) ? dcur : fminf(minD, dcur);
+                dBack = dFront; iBack = iFront;  // push_front; a 3rd element falls off the back
+                dFront = dcur; iFront = base + src;
+                if (size < 2) size++;
+            }
+        }
+    }
+    if (lane == 0) {
+        const bool accept = (size == 1) || (size >= 2 && (double)dFront <= (double)dBack * v.match_coef);
+        if (accept) {
+            v.mflag[fj] = 1;
+            v.mkp[fj] = iFront;
+            v.mdist[fj] = dFront;
+            v.z[fj * 2] = (double)xy[2 * iFront];
+            v.z[fj * 2 + 1] = (double)xy[2 * iFront + 1];
+        } else {
+            v.mflag[fj] = 0;
+            v.mkp[fj] = -1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ordered compaction of a per-feature flag array into a rank -> feature list (one CTA per filter)
+// ---------------------------------------------------------------------------------------------
+__device__ inline int block_compact(const uint8_t* flags, int N, int* list)
+{
+    __shared__ int warpTot[32];
+    __shared__ int running;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < N; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        const bool fl = (j < N) && flags[j];
+        const unsigned bal = __ballot_sync(0xffffffffu, fl);
+        if (lane == 0) warpTot[wid] = __popc(bal);
+        __syncthreads();
+        int before = running;
+        for (int w = 0; w < wid; ++w) before += warpTot[w];
+        if (fl) list[before + __popc(bal & ((1u << lane) - 1))] = j;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = running;
+            for (int w = 0; w < nw; ++w) t += warpTot[w];
+            running = t;
+        }
+        __syncthreads();
+    }
+    return running;
+}
+
+// after matching: counts, match list, RANSAC state reset (E/1PointRansac.cpp:101-125)
+__global__ void __launch_bounds__(256) k_after_match(DevView v)
+{
+    const int f = blockIdx.x;
+    int* dm = fdims(v, f);
+    const int N = dm[D_N_FEAT];
+    const size_t fo = (size_t)f * v.Nmax;
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        c += v.vis[fo + j] ? 1 : 0;
+        v.inl[fo + j] = 0;
+        v.outl[fo + j] = 0;
+        v.resc[fo + j] = 0;
+    }
+    atomicAdd(&cnt, c);
+    const int m = block_compact(v.mflag + fo, N, v.mlist + fo);
+    if (threadIdx.x == 0) {
+        dm[D_N_PRED] = cnt;
+        dm[D_N_MATCH] = m;
+        dm[D_N_HYP] = 0;
+        dm[D_BEST_HYP] = -1;
+        dm[D_N_INL] = 0;
+        dm[D_N_OUT] = 0;
+        dm[D_N_RESC] = 0;
+        dm[D_RANSAC_DONE] = (m == 0) ? 1 : 0;
+        dm[D_RANSAC_NEXT] = 0;
+        dm[D_RANSAC_CAP] = 1000;
+        dm[D_BEST_COUNT] = 0;
+        dm[D_ULIST] = 0;
+        dm[D_N_PRED2] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// R1: one CTA per hypothesis (E/1PointRansac.cpp:125-161).  Hypothesis i = i-th match.  The
+// state-only EKF update uses K_i = P H_i^T (H_i P H_i^T + sigma I)^-1 with the symmetric-row
+// gather P[:, c] = P[c, :] (13 coalesced row reads); x_i is staged in shared memory, then every
+// feature is re-projected with the un-normalised q_i and the support of matched features within
+// the pixel threshold is ballot-packed.  Hypotheses of a chunk are evaluated speculatively; the
+// sequential acceptance rule is replayed by k_ransac_select.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ransac_hyp(DevView v, int chunk0)
+{
+    extern __shared__ __align__(16) double xh[];  // n doubles
+    __shared__ double sK[4], sNu[2], sHx[14], sHf[12], sR[27];
+    __shared__ int sCount;
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    const int i = chunk0 + blockIdx.x;
+    const int m = dm[D_N_MATCH];
+    if (dm[D_RANSAC_DONE] || i >= m || (unsigned)i >= (unsigned)dm[D_RANSAC_CAP]) return;
+    const int n = dm[D_N_STATE], N = dm[D_N_FEAT];
+    const size_t fo = (size_t)f * v.Nmax;
+    const int j0 = v.mlist[fo + i];
+    const double* x = v.x + (size_t)f * v.ld;
+    const double* P = v.P + (size_t)f * v.nmax * v.ld;
+    const int off0 = v.foff[fo + j0];
+    const int d0 = v.ftype[fo + j0] == kTypeInvDepth ? 6 : 3;
+    if (threadIdx.x == 0) {
+        // S = H P H^T + sigma I: the measurement kernel already formed H P H^T + I
+        const double* Si = v.Si + (fo + j0) * 4;
+        const double S2[4] = {Si[0] - 1.0 + v.sigma_px, Si[1], Si[2], Si[3] - 1.0 + v.sigma_px};
+        inv2(S2, sK);
+        sNu[0] = deadband(v.z[(fo + j0) * 2] - v.h[(fo + j0) * 2]);
+        sNu[1] = deadband(v.z[(fo + j0) * 2 + 1] - v.h[(fo + j0) * 2 + 1]);
+        sCount = 0;
+    }
+    if (threadIdx.x < 14) sHx[threadIdx.x] = v.Hx[(fo + j0) * 14 + threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 44) sHf[threadIdx.x - 32] = v.Hf[(fo + j0) * 12 + threadIdx.x - 32];
+    __syncthreads();
+    for (int row = threadIdx.x; row < n; row += blockDim.x) {
+        double p0 = 0., p1 = 0.;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const double pv = P[(size_t)c * v.ld + row];
+            p0 += pv * sHx[c];
+            p1 += pv * sHx[7 + c];
+        }
+        for (int c = 0; c < d0; ++c) {
+            const double pv = P[(size_t)(off0 + c) * v.ld + row];
+            p0 += pv * sHf[c];
+            p1 += pv * sHf[6 + c];
+        }
+        const double k0 = p0 * sK[0] + p1 * sK[2];
+        const double k1 = p0 * sK[1] + p1 * sK[3];
+        const double dx = deadband(k0 * sNu[0] + k1 * sNu[1]);
+        xh[row] = x[row] + dx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        quat_to_rot(xh + 3, sR);       // R(q_i), q_i not normalised (E/Update.cpp:168)
+        inv3(sR, sR + 9);
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) sR[18 + a * 3 + b] = sR[b * 3 + a];
+    }
+    __syncthreads();
+    uint32_t* sup = v.hypsup + ((size_t)f * v.Nmax + i) * v.supWords;
+    int local = 0;
+    for (int base = 0; base < N; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        bool s = false;
+        if (j < N && v.mflag[fo + j]) {
+            const int type = v.ftype[fo + j], off = v.foff[fo + j];
+            double y[6], hh[2];
+            const int d = type == kTypeInvDepth ? 6 : 3;
+            for (int a = 0; a < 6; ++a) y[a] = a < d ? xh[off + a] : 0.;
+            if (predict_pixel(v.cam, xh, sR + 18, sR + 9, type, y, hh)) {
+                const double ex = v.z[(fo + j) * 2] - hh[0], ey = v.z[(fo + j) * 2 + 1] - hh[1];
+                s = sqrt(ex * ex + ey * ey) < v.ransac_thr;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, s);
+        if ((threadIdx.x & 31) == 0) {
+            if ((j >> 5) < v.supWords) sup[j >> 5] = bal;
+            local += __popc(bal);
+        }
+    }
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sCount, local);
+    __syncthreads();
+    if (threadIdx.x == 0) v.hypcount[(size_t)f * v.Nmax + i] = sCount;
+}
+
+// Sequential replay of the acceptance / adaptive-cap rule over one evaluated chunk
+// (E/1PointRansac.cpp:125-186), then -- once the loop has ended -- the inlier/outlier split in
+// match order (:201-227) and the inlier list for the low-innovation update.
+__global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, int chunkLen)
+{
+    const int f = blockIdx.x;
+    int* dm = fdims(v, f);
+    const size_t fo = (size_t)f * v.Nmax;
+    const int N = dm[D_N_FEAT], m = dm[D_N_MATCH];
+    __shared__ int finished;
+    if (threadIdx.x == 0) {
+        finished = 0;
+        if (!dm[D_RANSAC_DONE]) {
+            int cap = dm[D_RANSAC_CAP], best = dm[D_BEST_COUNT], bestHyp = dm[D_BEST_HYP], i = dm[D_RANSAC_NEXT];
+            const int end = chunk0 + chunkLen;
+            bool done = false;
+            for (; i < end; ++i) {
+                if (!((unsigned)i < (unsigned)cap && i < m)) { done = true; break; }
+                const int cnt = v.hypcount[fo + i];
+                if (cnt > best) {
+                    best = cnt;
+                    bestHyp = i;
+                    // numberOfHipotesis = (uint) static_cast<int>( log(1-p) / log(1 - (1 - e)) ), e = 1 - best/m
+                    const double e = 1.0 - (double)best / (double)m;
+                    const double ratio = log(1.0 - v.ransac_p) / log(1.0 - (1.0 - e));
+                    int asInt;
+                    if (!(ratio > -2147483649.0 && ratio < 2147483648.0)) asInt = (int)0x80000000;  // x86 "indefinite"
+                    else asInt = (int)ratio;
+                    cap = asInt;  // compared as unsigned above, like the reference's uint
+                }
+            }
+            if (!done && !((unsigned)i < (unsigned)cap && i < m)) done = true;
+            dm[D_RANSAC_CAP] = cap;
+            dm[D_BEST_COUNT] = best;
+            dm[D_BEST_HYP] = bestHyp;
+            dm[D_RANSAC_NEXT] = i;
+            dm[D_N_HYP] = i;
+            if (done) {
+                dm[D_RANSAC_DONE] = 1;
+                finished = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (!finished) return;
+    const int bestHyp = dm[D_BEST_HYP];
+    const uint32_t* sup = v.hypsup + ((size_t)f * v.Nmax + (bestHyp < 0 ? 0 : bestHyp)) * v.supWords;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const bool mt = v.mflag[fo + j];
+        const bool in = mt && bestHyp >= 0 && ((sup[j >> 5] >> (j & 31)) & 1u);
+        v.inl[fo + j] = in;
+        v.outl[fo + j] = mt && !in;
+    }
+    __syncthreads();
+    const int ni = block_compact(v.inl + fo, N, v.ulist + fo);
+    if (threadIdx.x == 0) {
+        dm[D_N_INL] = ni;
+        dm[D_N_OUT] = m - ni;
+        dm[D_ULIST] = ni;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// X1: chi-square gate on the re-predicted outliers (E/EKF.cpp:477-506 + :68-119), then the
+// rescued list for the high-innovation update.  One CTA per filter.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rescue_gate(DevView v)
+{
+    const int f = blockIdx.x;
+    int* dm = fdims(v, f);
+    const size_t fo = (size_t)f * v.Nmax;
+    const int N = dm[D_N_FEAT];
+    __shared__ int npred2;
+    if (threadIdx.x == 0) npred2 = 0;
+    __syncthreads();
+    int c = 0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) c += (v.outl[fo + j] && v.vis2[fo + j]) ? 1 : 0;
+    atomicAdd(&npred2, c);
+    __syncthreads();
+    // npred2 == 0 with outliers present: the reference indexes an empty vector (undefined); rescue nothing.
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        bool r = false;
+        if (npred2 > 0 && v.outl[fo + j] && v.vis2[fo + j]) {
+            const double d0 = v.z[(fo + j) * 2] - v.h2[(fo + j) * 2], d1 = v.z[(fo + j) * 2 + 1] - v.h2[(fo + j) * 2 + 1];
+            double Sinv[4];
+            inv2(v.Si2 + (fo + j) * 4, Sinv);
+            const double t0 = d0 * Sinv[0] + d1 * Sinv[2];
+            const double t1 = d0 * Sinv[1] + d1 * Sinv[3];
+            r = (t0 * d0 + t1 * d1) < v.chi2;
+        }
+        v.resc[fo + j] = r;
+    }
+    __syncthreads();
+    const int nr = block_compact(v.resc + fo, N, v.ulist + fo);
+    if (threadIdx.x == 0) {
+        dm[D_N_RESC] = nr;
+        dm[D_ULIST] = nr;
+        dm[D_N_PRED2] = npred2;
+    }
+}
+
+// updateMapFeatures (E/MapManagement.cpp:77-113): hit counters and descriptor refresh of inliers + rescued
+__global__ void k_update_map_features(DevView v)
+{
+    const int f = blockIdx.y;
+    const int N = fdims(v, f)[D_N_FEAT];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const size_t fj = (size_t)f * v.Nmax + j;
+    if (v.vis[fj]) v.tpred[fj] += 1;
+    if (v.inl[fj] || v.resc[fj]) {
+        v.tmatch[fj] += 1;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(v.kpdesc[f] + (size_t)v.mkp[fj] * 32);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(v.desc + fj * 32);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) dst[a] = src[a];
+    }
+}
+
+// fixed-size result record per filter (13-state, 13x13 covariance block, counters)
+struct RecordDev {
+    double x_cam[13];
+    double P_cam[169];
+    int info[12];
+};
+
+__global__ void k_write_records(DevView v, RecordDev* out)
+{
+    const int f = blockIdx.x;
+    const int* dm = fdims(v, f);
+    const double* x = v.x + (size_t)f * v.ld;
+    const double* P = v.P + (size_t)f * v.nmax * v.ld;
+    RecordDev* r = out + f;
+    for (int e = threadIdx.x; e < 169; e += blockDim.x) r->P_cam[e] = P[(size_t)(e / 13) * v.ld + (e % 13)];
+    if (threadIdx.x < 13) r->x_cam[threadIdx.x] = x[threadIdx.x];
+    if (threadIdx.x == 32) {
+        r->info[0] = dm[D_N_STATE];  r->info[1] = dm[D_N_FEAT];   r->info[2] = dm[D_N_KP];
+        r->info[3] = dm[D_N_PRED];   r->info[4] = dm[D_N_MATCH];  r->info[5] = dm[D_N_HYP];
+        r->info[6] = dm[D_BEST_HYP]; r->info[7] = dm[D_N_INL];    r->info[8] = dm[D_N_OUT];
+        r->info[9] = dm[D_N_RESC];   r->info[10] = dm[D_STATUS];  r->info[11] = 0;
+    }
+}
+
+}  // namespace ekf

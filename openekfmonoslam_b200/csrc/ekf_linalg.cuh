@@ -1,0 +1,465 @@
+// ekf_linalg.cuh -- the dense part of the EKF update on sm_100a (E/Update.cpp:92-109,116-218,282-319).
+//
+// The reference forms K = P H^T (H P H^T + R)^-1 with a dense >99%-zero H and then P = (I - K H) P
+// (2 n^3 flop).  Here the update is the partial Cholesky of the augmented matrix
+//
+//        [ S   B  nu ]         S = H P H^T + sigma I   (k x k)
+//        [ B^T P     ]         B = (P H^T)^T           (k x n, rows gathered from 7+d rows of P)
+//
+// in upper/row form:  S = U^T U,  W^T = U^-T B,  y = U^-T nu,  then  x += W y  and  P -= W W^T.
+// All operands are stored K-major (row r of B / W^T is one measurement row, contiguous over the
+// state index), so every kernel streams rows and the two big contractions are the same "TN" GEMM
+//        C[m][n] -= sum_r A[r][m] * B[r][n]
+// executed on the FP64 tensor pipe (mma.sync.m8n8k4.f64 = DMMA.8x8x4 on sm_100a) from a
+// cp.async-fed shared-memory ring.
+#pragma once
+
+#include "ekf_kernels.cuh"
+
+namespace ekf {
+
+constexpr int kNB = 64;  // Cholesky block
+constexpr int kCholDiagSmem = 2 * kNB * (kNB + 1) * (int)sizeof(double);
+constexpr int kCholPanelSmem = (kNB * 128 + kNB * kNB) * (int)sizeof(double);
+
+struct UpdSrc {  // which prediction arrays feed the update (all-features pass or the rescue re-prediction)
+    const double* h; const double* Hx; const double* Hf;
+};
+
+__device__ __forceinline__ UpdSrc upd_src(const DevView& v, int which)
+{
+    UpdSrc s;
+    s.h = which ? v.h2 : v.h;
+    s.Hx = which ? v.Hx2 : v.Hx;
+    s.Hf = which ? v.Hf2 : v.Hf;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// U1 front: B = (P H^T)^T for the update list.  H_a touches camera columns 0..6 and the d columns
+// of its own feature, so row pair a of B is a combination of 7 + d ROWS of P (P symmetric) --
+// 13 coalesced row reads instead of the reference's dense n x n x k product (E/Update.cpp:105).
+// Column n of B carries the dead-banded innovation nu (E/Update.cpp:133-134); padding columns are 0.
+// grid (ceil(ld/256), ku_max, F)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gain_rows(DevView v, int which)
+{
+    const int f = blockIdx.z, a = blockIdx.y;
+    const int* dm = fdims(v, f);
+    if (a >= dm[D_ULIST]) return;
+    const int n = dm[D_N_STATE];
+    const size_t fo = (size_t)f * v.Nmax;
+    const int j = v.ulist[fo + a];
+    const UpdSrc s = upd_src(v, which);
+    __shared__ double sHx[14], sHf[12];
+    if (threadIdx.x < 14) sHx[threadIdx.x] = s.Hx[(fo + j) * 14 + threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 44) sHf[threadIdx.x - 32] = s.Hf[(fo + j) * 12 + threadIdx.x - 32];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.ld) return;
+    const int off = v.foff[fo + j];
+    const int d = v.ftype[fo + j] == kTypeInvDepth ? 6 : 3;
+    const double* P = v.P + (size_t)f * v.nmax * v.ld;
+    double* B0 = v.Bu + ((size_t)f * v.kmax + 2 * a) * v.ld;
+    double b0 = 0., b1 = 0.;
+    if (i < n) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            const double p = P[(size_t)c * v.ld + i];
+            b0 += sHx[c] * p;
+            b1 += sHx[7 + c] * p;
+        }
+        for (int c = 0; c < d; ++c) {
+            const double p = P[(size_t)(off + c) * v.ld + i];
+            b0 += sHf[c] * p;
+            b1 += sHf[6 + c] * p;
+        }
+    } else if (i == n) {
+        b0 = deadband(v.z[(fo + j) * 2] - s.h[(fo + j) * 2]);
+        b1 = deadband(v.z[(fo + j) * 2 + 1] - s.h[(fo + j) * 2 + 1]);
+    }
+    B0[i] = b0;
+    B0[v.ld + i] = b1;
+}
+
+// S = H B^T + sigma I, sparse in H again (E/Update.cpp:95-107).  grid (ceil(k/16), ceil(k/16), F), block (16,16)
+__global__ void k_build_S(DevView v, int which)
+{
+    const int f = blockIdx.z;
+    const int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST];
+    const int ra = blockIdx.y * 16 + threadIdx.y, rb = blockIdx.x * 16 + threadIdx.x;
+    if (ra >= k || rb >= k) return;
+    const size_t fo = (size_t)f * v.Nmax;
+    const int a = ra >> 1, r = ra & 1;
+    const int j = v.ulist[fo + a];
+    const UpdSrc s = upd_src(v, which);
+    const double* Hx = s.Hx + (fo + j) * 14 + 7 * r;
+    const double* Hf = s.Hf + (fo + j) * 12 + 6 * r;
+    const int off = v.foff[fo + j];
+    const int d = v.ftype[fo + j] == kTypeInvDepth ? 6 : 3;
+    const double* Brow = v.Bu + ((size_t)f * v.kmax + rb) * v.ld;
+    double acc = 0.;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) acc += Hx[c] * Brow[c];
+    for (int c = 0; c < d; ++c) acc += Hf[c] * Brow[off + c];
+    if (ra == rb) acc += v.sigma_px;
+    v.S[((size_t)f * v.kmax + ra) * v.ldS + rb] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cholesky step J, part 1: factor the 64x64 diagonal block S_JJ = U^T U in shared memory and invert
+// U (upper triangular).  Rows beyond k are treated as identity.  One CTA per filter,
+// dynamic smem = 2 * 64 * 65 doubles.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chol_diag(DevView v, int J)
+{
+    const int f = blockIdx.x;
+    int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST];
+    const int J0 = J * kNB;
+    if (J0 >= k) return;
+    const int kb = min(kNB, k - J0);
+    extern __shared__ __align__(16) double dsm[];
+    double (*A)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm);
+    double (*Ui)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm + kNB * (kNB + 1));
+    double* S = v.S + ((size_t)f * v.kmax + J0) * v.ldS + J0;
+    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+        const int i = e / kNB, j = e % kNB;
+        double val = (i == j) ? 1.0 : 0.0;
+        if (i < kb && j < kb && j >= i) val = S[(size_t)i * v.ldS + j];
+        A[i][j] = val;
+        Ui[i][j] = 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < kNB; ++c) {
+        if (threadIdx.x == 0) {
+            double dg = A[c][c];
+            if (!(dg > 0.0)) {
+                dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
+                dg = 1.0;
+            }
+            A[c][c] = sqrt(dg);
+        }
+        __syncthreads();
+        const double dg = A[c][c];
+        for (int j = c + 1 + threadIdx.x; j < kNB; j += blockDim.x) A[c][j] /= dg;
+        __syncthreads();
+        const int rem = kNB - 1 - c;
+        for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+            const int i = c + 1 + e / rem, j = c + 1 + e % rem;
+            if (j >= i) A[i][j] -= A[c][i] * A[c][j];
+        }
+        __syncthreads();
+    }
+    // inverse of the upper-triangular U by back substitution, one column per thread
+    if (threadIdx.x < kNB) {
+        const int t = threadIdx.x;
+        Ui[t][t] = 1.0 / A[t][t];
+        for (int i = t - 1; i >= 0; --i) {
+            double s = 0.;
+            for (int q = i + 1; q <= t; ++q) s += A[i][q] * Ui[q][t];
+            Ui[i][t] = -s / A[i][i];
+        }
+    }
+    __syncthreads();
+    double* Di = v.Dinv + (size_t)f * kNB * kNB;
+    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+        const int i = e / kNB, j = e % kNB;
+        Di[e] = Ui[i][j];
+        if (i < kb && j < kb) S[(size_t)i * v.ldS + j] = (j >= i) ? A[i][j] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cholesky step J, part 2: row panel  X = U_JJ^-T [ S(J, >J) | B(J, :) ]  in place.
+// Column tiles of 128 over the virtual concatenation of S's columns right of the block and B's
+// n+1 columns.  grid (tiles, F), dynamic smem = (64*128 + 64*64) doubles.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chol_panel(DevView v, int J)
+{
+    extern __shared__ __align__(16) double psm[];
+    double* At = psm;                 // [64][128]
+    double* Ui = psm + kNB * 128;     // [64][64]
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST], n = dm[D_N_STATE];
+    const int J0 = J * kNB, J1 = J0 + kNB;
+    if (J0 >= k) return;
+    const int kb = min(kNB, k - J0);
+    const int nS = (k > J1) ? (k - J1 + 127) / 128 : 0;
+    const int nB = (n + 1 + 127) / 128;
+    int t = blockIdx.x;
+    double* base;
+    int ldx, c0, cEnd;
+    if (t < nS) {
+        base = v.S + ((size_t)f * v.kmax + J0) * v.ldS;
+        ldx = v.ldS; c0 = J1 + t * 128; cEnd = k;
+    } else {
+        t -= nS;
+        if (t >= nB) return;
+        base = v.Bu + ((size_t)f * v.kmax + J0) * v.ld;
+        ldx = v.ld; c0 = t * 128; cEnd = n + 1;
+    }
+    const double* Di = v.Dinv + (size_t)f * kNB * kNB;
+    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) Ui[e] = Di[e];
+    for (int e = threadIdx.x; e < kNB * 128; e += blockDim.x) {
+        const int r = e / 128, c = c0 + (e % 128);
+        At[e] = (r < kb && c < cEnd) ? base[(size_t)r * ldx + c] : 0.0;
+    }
+    __syncthreads();
+    const int c = threadIdx.x & 127, rh = threadIdx.x >> 7;  // two threads per column, 32 rows each
+    if (c0 + c < cEnd) {
+        for (int r = rh * 32; r < rh * 32 + 32 && r < kb; ++r) {
+            double s = 0.;
+            for (int q = 0; q <= r; ++q) s += Ui[q * kNB + r] * At[q * 128 + c];
+            base[(size_t)r * ldx + c0 + c] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The TN contraction on the FP64 tensor pipe:   C[m][n] -= sum_{r<K} A[r][m] * B[r][n]
+//   KIND 0: trailing update of S at Cholesky step J   (A = B = X rows in S, upper tiles only)
+//   KIND 1: trailing update of B at step J            (A = X rows in S, B = X rows in B)
+//   KIND 2: covariance downdate P -= W W^T            (A = B = W^T, K = k, lower tiles, mirrored
+//           store so P stays exactly symmetric: replaces 0.5 P + 0.5 P^T of E/Update.cpp:307)
+// CTA tile 128 x 128, 8 warps as 2 (m) x 4 (n), warp tile 64 x 32 = 8 x 4 DMMA m8n8k4 tiles.
+// K is consumed in chunks of 16 rows through a 3-stage cp.async ring; the row pitch of 132 doubles
+// makes both fragment loads bank-conflict free (lane -> (k = lane%4, m = lane/4) hits 16 distinct
+// 8-byte banks per half warp).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTM = 128, kTN = 128, kKC = 16, kLDS = 132, kStages = 3;
+constexpr int kGemmSmemBytes = kStages * 2 * kKC * kLDS * (int)sizeof(double);
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// load a kKC x 128 slab (rows k0.., columns col0..) of a K-major operand into shared memory
+__device__ __forceinline__ void load_slab(double* dst, const double* src, int ldsrc, int k0, int K, int col0,
+                                          int colLimit, int tid)
+{
+#pragma unroll
+    for (int it = 0; it < (kKC * 128 / 2) / 256; ++it) {
+        const int c = tid + it * 256;
+        const int r = c >> 6, c2 = (c & 63) * 2;
+        double* d = dst + r * kLDS + c2;
+        if (k0 + r < K && col0 + c2 < colLimit) {
+            cp_async16(d, src + (size_t)(k0 + r) * ldsrc + col0 + c2);
+        } else {
+            d[0] = 0.0;
+            d[1] = 0.0;
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
+{
+    extern __shared__ __align__(16) double gsm[];
+    const int f = blockIdx.z;
+    const int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST], n = dm[D_N_STATE];
+    const double *A, *B;
+    double* C;
+    int lda, ldb, ldc, mBeg, mEnd, nBeg, nEnd, K, aLim, bLim;
+    if (KIND == 2) {
+        A = B = v.Bu + (size_t)f * v.kmax * v.ld;
+        C = v.P + (size_t)f * v.nmax * v.ld;
+        lda = ldb = ldc = v.ld;
+        mBeg = nBeg = 0; mEnd = nEnd = n; K = k; aLim = bLim = v.ld;
+    } else {
+        const int J0 = J * kNB, J1 = J0 + kNB;
+        if (J1 >= k) return;
+        A = v.S + ((size_t)f * v.kmax + J0) * v.ldS;
+        lda = v.ldS; aLim = v.ldS;
+        K = kNB;  // J1 < k, so the panel block is full
+        mBeg = J1; mEnd = k;
+        if (KIND == 0) {
+            B = A; ldb = lda; bLim = aLim;
+            C = v.S + (size_t)f * v.kmax * v.ldS; ldc = v.ldS;
+            nBeg = J1; nEnd = k;
+        } else {
+            B = v.Bu + ((size_t)f * v.kmax + J0) * v.ld; ldb = v.ld; bLim = v.ld;
+            C = v.Bu + (size_t)f * v.kmax * v.ld; ldc = v.ld;
+            nBeg = 0; nEnd = n + 1;
+        }
+    }
+    const int tm0 = mBeg + blockIdx.y * kTM, tn0 = nBeg + blockIdx.x * kTN;
+    if (tm0 >= mEnd || tn0 >= nEnd) return;
+    if (KIND == 0 && tn0 + kTN <= tm0) return;  // tile strictly below the diagonal
+    if (KIND == 2 && tn0 > tm0) return;         // lower tiles only
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    const int nk = (K + kKC - 1) / kKC;
+    auto stageA = [&](int s) { return gsm + (size_t)s * 2 * kKC * kLDS; };
+    auto stageB = [&](int s) { return gsm + (size_t)s * 2 * kKC * kLDS + kKC * kLDS; };
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if (s < nk) {
+            load_slab(stageA(s), A, lda, s * kKC, K, tm0, aLim, tid);
+            load_slab(stageB(s), B, ldb, s * kKC, K, tn0, bLim, tid);
+        }
+        cp_async_commit();
+    }
+    const int kq = lane & 3, mq = lane >> 2;
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        {   // prefetch chunk kt + kStages - 1 into the slot freed at iteration kt - 1
+            const int nx = kt + kStages - 1;
+            if (nx < nk) {
+                load_slab(stageA(nx % kStages), A, lda, nx * kKC, K, tm0, aLim, tid);
+                load_slab(stageB(nx % kStages), B, ldb, nx * kKC, K, tn0, bLim, tid);
+            }
+            cp_async_commit();
+        }
+        const double* As = stageA(kt % kStages) + wm * 64 + mq;
+        const double* Bs = stageB(kt % kStages) + wn * 32 + mq;
+#pragma unroll
+        for (int k4 = 0; k4 < kKC; k4 += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) af[a] = As[(k4 + kq) * kLDS + a * 8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = Bs[(k4 + kq) * kLDS + b * 8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+    }
+    cp_async_wait<0>();
+    // epilogue: C -= acc
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int gm = tm0 + wm * 64 + a * 8 + mq;
+        if (gm >= mEnd) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int gn = tn0 + wn * 32 + b * 8 + 2 * kq;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int g = gn + e;
+                if (g >= nEnd) continue;
+                if (KIND == 2) {
+                    if (g > gm) continue;
+                    const double val = C[(size_t)gm * ldc + g] - acc[a][b][e];
+                    C[(size_t)gm * ldc + g] = val;
+                    if (g != gm) C[(size_t)g * ldc + gm] = val;
+                } else {
+                    C[(size_t)gm * ldc + g] -= acc[a][b][e];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// U2: x += deadband(W y) (E/Update.cpp:136-204), y = column n of the factored B.  grid (ceil(n/256), F)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_state_update(DevView v)
+{
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST], n = dm[D_N_STATE];
+    if (k == 0) return;
+    __shared__ double ys[256];
+    const double* Wt = v.Bu + (size_t)f * v.kmax * v.ld;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.;
+    for (int r0 = 0; r0 < k; r0 += 256) {
+        __syncthreads();
+        if (r0 + threadIdx.x < k) ys[threadIdx.x] = Wt[(size_t)(r0 + threadIdx.x) * v.ld + n];
+        __syncthreads();
+        const int rl = min(256, k - r0);
+        if (i < n)
+            for (int r = 0; r < rl; ++r) acc += Wt[(size_t)(r0 + r) * v.ld + i] * ys[r];
+    }
+    if (i < n) {
+        double* x = v.x + (size_t)f * v.ld;
+        if (fabs(acc) > kDelta) x[i] += acc;
+    }
+}
+
+// U4 (a): J = d(q/|q|)/dq at the un-normalised q, then q <- q/|q| (E/Update.cpp:45-60,309-317)
+__global__ void k_quat_norm(DevView v)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= v.F) return;
+    if (fdims(v, f)[D_ULIST] == 0) return;
+    double* x = v.x + (size_t)f * v.ld;
+    const double r = x[3], a = x[4], b = x[5], c = x[6];
+    const double nrm = sqrt(r * r + a * a + b * b + c * c);
+    const double s = 1.0 / (nrm * nrm * nrm);
+    const double M[16] = {a * a + b * b + c * c, -r * a, -r * b, -r * c, -a * r, r * r + b * b + c * c, -a * b, -a * c,
+                          -b * r, -b * a, r * r + a * a + c * c, -b * c, -c * r, -c * a, -c * b, r * r + a * a + b * b};
+    double* Jq = v.Jq + (size_t)f * 16;
+    for (int e = 0; e < 16; ++e) Jq[e] = M[e] * s;
+    x[3] = r / nrm; x[4] = a / nrm; x[5] = b / nrm; x[6] = c / nrm;
+}
+
+// U4 (b): P <- T P T^T with T = diag(I3, J, I) (normalizeCovariance, E/Update.cpp:64-85): only rows
+// and columns 3..6 change.  grid (ceil(n/256), F)
+__global__ void __launch_bounds__(256) k_quat_cov(DevView v)
+{
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    if (dm[D_ULIST] == 0) return;
+    const int n = dm[D_N_STATE];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double* P = v.P + (size_t)f * v.nmax * v.ld;
+    double Jm[16];
+    for (int e = 0; e < 16; ++e) Jm[e] = v.Jq[(size_t)f * 16 + e];
+    if (j >= 3 && j < 7) {
+        if (j != 3) return;
+        double B4[16], T4[16];
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b) B4[a * 4 + b] = P[(size_t)(3 + a) * v.ld + 3 + b];
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b) {
+                double s = 0.;
+                for (int c = 0; c < 4; ++c) s += Jm[a * 4 + c] * B4[c * 4 + b];
+                T4[a * 4 + b] = s;
+            }
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b <= a; ++b) {
+                double s = 0.;
+                for (int c = 0; c < 4; ++c) s += T4[a * 4 + c] * Jm[b * 4 + c];
+                P[(size_t)(3 + a) * v.ld + 3 + b] = s;
+                P[(size_t)(3 + b) * v.ld + 3 + a] = s;
+            }
+        return;
+    }
+    double col[4];
+    for (int a = 0; a < 4; ++a) col[a] = P[(size_t)(3 + a) * v.ld + j];
+    for (int a = 0; a < 4; ++a) {
+        double s = 0.;
+        for (int c = 0; c < 4; ++c) s += Jm[a * 4 + c] * col[c];
+        P[(size_t)(3 + a) * v.ld + j] = s;
+        P[(size_t)j * v.ld + 3 + a] = s;
+    }
+}
+
+}  // namespace ekf
