@@ -273,6 +273,9 @@ extern "C" int ekfb_set_state(ekfb_handle c, int f, int n, int N, const double* 
     hd[D_N_FEAT] = N;
     hd[D_N_KP] = c->hKp[f];
     CK(cudaMemcpyAsync(v.dims + (size_t)f * D_STRIDE, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    k_symmetrize<<<dim3(cdiv(n, 16), cdiv(n, 16)), dim3(16, 16), 0, c->stream>>>(v, f);
+    count_launch(c);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));  // caller buffers may be pageable
     c->hn[f] = n;
     c->hN[f] = N;

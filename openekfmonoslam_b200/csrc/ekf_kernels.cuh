@@ -99,6 +99,19 @@ __global__ void __launch_bounds__(256) k_predict_cov(DevView v)
     }
 }
 
+// Establishes the device invariant "P is exactly symmetric" at upload: P <- 0.5 P + 0.5 P^T, which is
+// what the reference applies at every update (E/Update.cpp:307).  grid (ceil(n/16), ceil(n/16), F), block (16,16)
+__global__ void k_symmetrize(DevView v, int f)
+{
+    const int n = fdims(v, f)[D_N_STATE];
+    const int i = blockIdx.y * 16 + threadIdx.y, j = blockIdx.x * 16 + threadIdx.x;
+    if (i >= n || j > i) return;
+    double* P = v.P + (size_t)f * v.nmax * v.ld;
+    const double a = 0.5 * P[(size_t)i * v.ld + j] + 0.5 * P[(size_t)j * v.ld + i];
+    P[(size_t)i * v.ld + j] = a;
+    P[(size_t)j * v.ld + i] = a;
+}
+
 // P2: x <- f(x), after P1 (E/StateAndCovariancePrediction.cpp:43-65,252)
 __global__ void k_predict_state(DevView v)
 {

@@ -23,6 +23,9 @@ print("setup s", round(time.time() - t0, 1))
 warm = T // 2
 for t in range(warm):
     gpu.select_frame(t); gpu.step()
+    if len(sys.argv) > 6:
+        i = gpu.frame_info(0)
+        print(t, {k: i[k] for k in ("n_predicted", "n_matches", "n_hypotheses", "n_inliers", "n_rescued", "status")})
 gpu.sync()
 gpu.timer_record(0)
 l0 = gpu.kernel_launches()
