@@ -178,7 +178,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     ALLOC(v.inl, F * N); ALLOC(v.outl, F * N); ALLOC(v.resc, F * N); ALLOC(v.ulist, F * N);
     ALLOC(v.kpok, F * c->Kpmax); ALLOC(v.mask, F * (size_t)v.W * v.H);
     ALLOC(v.hypcount, F * N); ALLOC(v.hypsup, F * N * c->supWords);
-    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.Dinv, F * kNB * kNB); ALLOC(v.Jq, F * 16);
+    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.dx, F * c->ld); ALLOC(v.Jq, F * 16);
     ALLOC(c->d_kpxy, F * c->Kpmax * 2); ALLOC(c->d_kpdesc, F * c->Kpmax * 32);
     ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F);
     ALLOC(c->d_rec, F);
@@ -201,10 +201,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     c->seq.resize(c->F);
 
     CK(cudaFuncSetAttribute(k_gemm_tn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-    CK(cudaFuncSetAttribute(k_gemm_tn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_gemm_tn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
-    CK(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholDiagSmem));
-    CK(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholPanelSmem));
     CK(cudaFuncSetAttribute(k_ransac_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             std::min<int>(227 * 1024 - 2048, c->ld * (int)sizeof(double))));
     const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
@@ -511,19 +508,17 @@ static int run_update(ekfb_ctx* c, int which)
         const int steps = cdiv(k, kNB);
         for (int J = 0; J < steps; ++J) {
             const int J1 = (J + 1) * kNB;
-            k_chol_diag<<<c->F, 256, kCholDiagSmem, c->stream>>>(v, J);
-            const int nS = k > J1 ? cdiv(k - J1, 128) : 0;
-            const int nB = cdiv(n + 1, 128);
-            k_chol_panel<<<dim3(nS + nB, c->F), 256, kCholPanelSmem, c->stream>>>(v, J);
-            count_launch(c, 2);
+            const int nS = k > J1 ? cdiv(k - J1, kPanelCols) : 0;
+            const int nB = cdiv(n + 1, kPanelCols);
+            k_chol_panel<<<dim3(nS + nB, c->F), 128, 0, c->stream>>>(v, J);
+            count_launch(c);
             if (k > J1) {
                 const int mt = cdiv(k - J1, kTM);
-                k_gemm_tn<0><<<dim3(mt, mt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, J);
-                k_gemm_tn<1><<<dim3(cdiv(n + 1, kTN), mt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, J);
-                count_launch(c, 2);
+                k_gemm_tn<0><<<dim3(cdiv(k - J1, kTN) + cdiv(n + 1, kTN), mt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, J);
+                count_launch(c);
             }
         }
-        k_state_update<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
+        k_state_apply<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
         k_quat_norm<<<cdiv(c->F, 128), 128, 0, c->stream>>>(v);
         count_launch(c, 2);
     }

@@ -19,8 +19,6 @@
 namespace ekf {
 
 constexpr int kNB = 64;  // Cholesky block
-constexpr int kCholDiagSmem = 2 * kNB * (kNB + 1) * (int)sizeof(double);
-constexpr int kCholPanelSmem = (kNB * 128 + kNB * kNB) * (int)sizeof(double);
 
 struct UpdSrc {  // which prediction arrays feed the update (all-features pass or the rescue re-prediction)
     const double* h; const double* Hx; const double* Hf;
@@ -80,6 +78,7 @@ __global__ void __launch_bounds__(256) k_gain_rows(DevView v, int which)
     }
     B0[i] = b0;
     B0[v.ld + i] = b1;
+    if (a == 0) v.dx[(size_t)f * v.ld + i] = 0.0;  // reset the state-correction accumulator
 }
 
 // S = H B^T + sigma I, sparse in H again (E/Update.cpp:95-107).  grid (ceil(k/16), ceil(k/16), F), block (16,16)
@@ -108,120 +107,133 @@ __global__ void k_build_S(DevView v, int which)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cholesky step J, part 1: factor the 64x64 diagonal block S_JJ = U^T U in shared memory and invert
-// U (upper triangular).  Rows beyond k are treated as identity.  One CTA per filter,
-// dynamic smem = 2 * 64 * 65 doubles.
+// Cholesky step J, panel kernel: the 64-row block J of the augmented matrix [S | B | nu] becomes
+// [U_JJ | X_J | y_J] with X_J = U_JJ^-T A_J.  Every CTA owns 128 columns (one per thread) and
+//   (1) redundantly eliminates the 64x64 diagonal tile (plus the nu column) with one column per
+//       thread in registers -- one barrier per pivot, reciprocal instead of division -- leaving the
+//       multipliers M[c][i] = A(c)[c][i] / A(c)[c][c] and 1/sqrt(pivot) in shared memory;
+//   (2) applies the same row operations to its own columns: 64 values per thread in registers,
+//       2016 FMAs, no barrier (forward substitution without forming an inverse);
+//   (3) accumulates its share of the state correction dx[col] += sum_r X[r][col] * y[r]
+//       (E/Update.cpp:136-141: K nu = W y), own columns only, so no atomics and a fixed order.
+// Column tiles run over the virtual concatenation of S's columns right of the block and B's n+1
+// columns.  grid (tiles, F), 128 threads.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_chol_diag(DevView v, int J)
+// forward substitution of one column of the row block (64 values in registers), separate function so
+// that its register allocation is independent of the diagonal-tile phase
+__device__ __noinline__ double panel_substitute(double* colp, int ldx, int kb, const double* Msm, const double* dinvs,
+                                                const double* ysm)
 {
-    const int f = blockIdx.x;
-    int* dm = fdims(v, f);
-    const int k = 2 * dm[D_ULIST];
-    const int J0 = J * kNB;
-    if (J0 >= k) return;
-    const int kb = min(kNB, k - J0);
-    extern __shared__ __align__(16) double dsm[];
-    double (*A)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm);
-    double (*Ui)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(dsm + kNB * (kNB + 1));
-    double* S = v.S + ((size_t)f * v.kmax + J0) * v.ldS + J0;
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-        const int i = e / kNB, j = e % kNB;
-        double val = (i == j) ? 1.0 : 0.0;
-        if (i < kb && j < kb && j >= i) val = S[(size_t)i * v.ldS + j];
-        A[i][j] = val;
-        Ui[i][j] = 0.0;
+    double x[kNB];
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) x[i] = (i < kb) ? colp[(size_t)i * ldx] : 0.0;
+#pragma unroll
+    for (int c = 0; c < kNB - 1; ++c) {
+        const double xc = x[c];
+#pragma unroll
+        for (int i = c + 1; i < kNB; ++i) x[i] -= Msm[c * kNB + i] * xc;
     }
-    __syncthreads();
-    for (int c = 0; c < kNB; ++c) {
-        if (threadIdx.x == 0) {
-            double dg = A[c][c];
-            if (!(dg > 0.0)) {
-                dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
-                dg = 1.0;
-            }
-            A[c][c] = sqrt(dg);
-        }
-        __syncthreads();
-        const double dg = A[c][c];
-        for (int j = c + 1 + threadIdx.x; j < kNB; j += blockDim.x) A[c][j] /= dg;
-        __syncthreads();
-        const int rem = kNB - 1 - c;
-        for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-            const int i = c + 1 + e / rem, j = c + 1 + e % rem;
-            if (j >= i) A[i][j] -= A[c][i] * A[c][j];
-        }
-        __syncthreads();
+    double part = 0.0;
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) {
+        x[i] *= dinvs[i];
+        part += x[i] * ysm[i];
+        if (i < kb) colp[(size_t)i * ldx] = x[i];
     }
-    // inverse of the upper-triangular U by back substitution, one column per thread
-    if (threadIdx.x < kNB) {
-        const int t = threadIdx.x;
-        Ui[t][t] = 1.0 / A[t][t];
-        for (int i = t - 1; i >= 0; --i) {
-            double s = 0.;
-            for (int q = i + 1; q <= t; ++q) s += A[i][q] * Ui[q][t];
-            Ui[i][t] = -s / A[i][i];
-        }
-    }
-    __syncthreads();
-    double* Di = v.Dinv + (size_t)f * kNB * kNB;
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-        const int i = e / kNB, j = e % kNB;
-        Di[e] = Ui[i][j];
-        if (i < kb && j < kb) S[(size_t)i * v.ldS + j] = (j >= i) ? A[i][j] : 0.0;
-    }
+    return part;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Cholesky step J, part 2: row panel  X = U_JJ^-T [ S(J, >J) | B(J, :) ]  in place.
-// Column tiles of 128 over the virtual concatenation of S's columns right of the block and B's
-// n+1 columns.  grid (tiles, F), dynamic smem = (64*128 + 64*64) doubles.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_chol_panel(DevView v, int J)
+constexpr int kPanelCols = 128;
+
+__global__ void __launch_bounds__(128) k_chol_panel(DevView v, int J)
 {
-    extern __shared__ __align__(16) double psm[];
-    double* At = psm;                 // [64][128]
-    double* Ui = psm + kNB * 128;     // [64][64]
+    __shared__ double rowbuf[2][72];
+    __shared__ __align__(16) double Msm[kNB * kNB];
+    __shared__ double dinvs[kNB], ysm[kNB];
     const int f = blockIdx.y;
-    const int* dm = fdims(v, f);
+    int* dm = fdims(v, f);
     const int k = 2 * dm[D_ULIST], n = dm[D_N_STATE];
     const int J0 = J * kNB, J1 = J0 + kNB;
     if (J0 >= k) return;
     const int kb = min(kNB, k - J0);
-    const int nS = (k > J1) ? (k - J1 + 127) / 128 : 0;
-    const int nB = (n + 1 + 127) / 128;
+    const int nS = (k > J1) ? (k - J1 + kPanelCols - 1) / kPanelCols : 0;
+    const int nB = (n + 1 + kPanelCols - 1) / kPanelCols;
     int t = blockIdx.x;
     double* base;
     int ldx, c0, cEnd;
-    if (t < nS) {
+    const bool isB = t >= nS;
+    if (!isB) {
         base = v.S + ((size_t)f * v.kmax + J0) * v.ldS;
-        ldx = v.ldS; c0 = J1 + t * 128; cEnd = k;
+        ldx = v.ldS; c0 = J1 + t * kPanelCols; cEnd = k;
     } else {
         t -= nS;
         if (t >= nB) return;
         base = v.Bu + ((size_t)f * v.kmax + J0) * v.ld;
-        ldx = v.ld; c0 = t * 128; cEnd = n + 1;
+        ldx = v.ld; c0 = t * kPanelCols; cEnd = n + 1;
     }
-    const double* Di = v.Dinv + (size_t)f * kNB * kNB;
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) Ui[e] = Di[e];
-    for (int e = threadIdx.x; e < kNB * 128; e += blockDim.x) {
-        const int r = e / 128, c = c0 + (e % 128);
-        At[e] = (r < kb && c < cEnd) ? base[(size_t)r * ldx + c] : 0.0;
+    const int tid = threadIdx.x;
+    double* Sd = v.S + ((size_t)f * v.kmax + J0) * v.ldS + J0;
+    const double* nuCol = v.Bu + ((size_t)f * v.kmax + J0) * v.ld + n;
+    for (int e = tid; e < kNB * kNB; e += blockDim.x) Msm[e] = 0.0;
+
+    // ---- (1) diagonal tile elimination, thread j <-> column j (j = 64: the nu column) ----
+    double a[kNB];
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) {
+        double val = 0.0;
+        if (tid < kNB) {
+            if (i < kb && tid < kb) { if (i <= tid) val = Sd[(size_t)i * v.ldS + tid]; }
+            else if (i == tid) val = 1.0;  // identity padding of a partial last block
+        } else if (tid == kNB) {
+            if (i < kb) val = nuCol[(size_t)i * v.ld];
+        }
+        a[i] = val;
     }
     __syncthreads();
-    const int c = threadIdx.x & 127, rh = threadIdx.x >> 7;  // two threads per column, 32 rows each
-    if (c0 + c < cEnd) {
-        for (int r = rh * 32; r < rh * 32 + 32 && r < kb; ++r) {
-            double s = 0.;
-            for (int q = 0; q <= r; ++q) s += Ui[q * kNB + r] * At[q * 128 + c];
-            base[(size_t)r * ldx + c0 + c] = s;
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) {
+        double* buf = rowbuf[c & 1];
+        if (tid >= c && tid <= kNB) buf[tid] = a[c];
+        __syncthreads();
+        const double piv = buf[c];
+        const double pinv = 1.0 / piv;
+        if (tid == c) {
+            if (!(piv > 0.0)) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
+            dinvs[c] = rsqrt(piv);
+        }
+        if (tid > c && tid <= kNB) {
+            const double mj = buf[tid] * pinv;
+            if (tid < kNB) Msm[c * kNB + tid] = mj;
+#pragma unroll
+            for (int i = c + 1; i < kNB; ++i)
+                if (i <= tid) a[i] -= buf[i] * mj;
         }
     }
+    __syncthreads();
+    if (tid == kNB) {
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) ysm[c] = a[c] * dinvs[c];
+    }
+    if (blockIdx.x == 0 && tid < kNB && tid < kb) {  // U_JJ back to S (upper), zeros below
+#pragma unroll
+        for (int i = 0; i < kNB; ++i)
+            if (i < kb) Sd[(size_t)i * v.ldS + tid] = (i <= tid) ? a[i] * dinvs[i] : 0.0;
+    }
+    __syncthreads();
+
+    // ---- (2) forward substitution on this CTA's columns ----
+    const int col = c0 + tid;
+    if (col >= cEnd) return;
+    const double part = panel_substitute(base + col, ldx, kb, Msm, dinvs, ysm);
+    // ---- (3) state correction share ----
+    if (isB && col < n) v.dx[(size_t)f * v.ld + col] += part;
 }
 
 // ---------------------------------------------------------------------------------------------
 // The TN contraction on the FP64 tensor pipe:   C[m][n] -= sum_{r<K} A[r][m] * B[r][n]
-//   KIND 0: trailing update of S at Cholesky step J   (A = B = X rows in S, upper tiles only)
-//   KIND 1: trailing update of B at step J            (A = X rows in S, B = X rows in B)
+//   KIND 0: trailing update at Cholesky step J of S (A = B = X rows in S, upper tiles only) and of
+//           B (A = X rows in S, B = X rows in B) in one launch: blockIdx.x runs over the virtual
+//           concatenation of S's and B's column tiles
 //   KIND 2: covariance downdate P -= W W^T            (A = B = W^T, K = k, lower tiles, mirrored
 //           store so P stays exactly symmetric: replaces 0.5 P + 0.5 P^T of E/Update.cpp:307)
 // CTA tile 128 x 128, 8 warps as 2 (m) x 4 (n), warp tile 64 x 32 = 8 x 4 DMMA m8n8k4 tiles.
@@ -276,6 +288,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
     const double *A, *B;
     double* C;
     int lda, ldb, ldc, mBeg, mEnd, nBeg, nEnd, K, aLim, bLim;
+    int tileN = blockIdx.x;
+    bool sPart = false;
     if (KIND == 2) {
         A = B = v.Bu + (size_t)f * v.kmax * v.ld;
         C = v.P + (size_t)f * v.nmax * v.ld;
@@ -288,19 +302,20 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
         lda = v.ldS; aLim = v.ldS;
         K = kNB;  // J1 < k, so the panel block is full
         mBeg = J1; mEnd = k;
-        if (KIND == 0) {
+        const int nS = (k - J1 + kTN - 1) / kTN;
+        if ((int)blockIdx.x < nS) {
             B = A; ldb = lda; bLim = aLim;
             C = v.S + (size_t)f * v.kmax * v.ldS; ldc = v.ldS;
-            nBeg = J1; nEnd = k;
+            nBeg = J1; nEnd = k; tileN = blockIdx.x; sPart = true;
         } else {
             B = v.Bu + ((size_t)f * v.kmax + J0) * v.ld; ldb = v.ld; bLim = v.ld;
             C = v.Bu + (size_t)f * v.kmax * v.ld; ldc = v.ld;
-            nBeg = 0; nEnd = n + 1;
+            nBeg = 0; nEnd = n + 1; tileN = blockIdx.x - nS;
         }
     }
-    const int tm0 = mBeg + blockIdx.y * kTM, tn0 = nBeg + blockIdx.x * kTN;
+    const int tm0 = mBeg + blockIdx.y * kTM, tn0 = nBeg + tileN * kTN;
     if (tm0 >= mEnd || tn0 >= nEnd) return;
-    if (KIND == 0 && tn0 + kTN <= tm0) return;  // tile strictly below the diagonal
+    if (sPart && tn0 + kTN <= tm0) return;      // S tile strictly below the diagonal
     if (KIND == 2 && tn0 > tm0) return;         // lower tiles only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -376,30 +391,19 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
 }
 
 // ---------------------------------------------------------------------------------------------
-// U2: x += deadband(W y) (E/Update.cpp:136-204), y = column n of the factored B.  grid (ceil(n/256), F)
+// U2: x += deadband(dx) (E/Update.cpp:143-204); dx = W y was accumulated by the panel kernels.
+// grid (ceil(n/256), F)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_state_update(DevView v)
+__global__ void __launch_bounds__(256) k_state_apply(DevView v)
 {
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
-    const int k = 2 * dm[D_ULIST], n = dm[D_N_STATE];
-    if (k == 0) return;
-    __shared__ double ys[256];
-    const double* Wt = v.Bu + (size_t)f * v.kmax * v.ld;
+    if (dm[D_ULIST] == 0) return;
+    const int n = dm[D_N_STATE];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double acc = 0.;
-    for (int r0 = 0; r0 < k; r0 += 256) {
-        __syncthreads();
-        if (r0 + threadIdx.x < k) ys[threadIdx.x] = Wt[(size_t)(r0 + threadIdx.x) * v.ld + n];
-        __syncthreads();
-        const int rl = min(256, k - r0);
-        if (i < n)
-            for (int r = 0; r < rl; ++r) acc += Wt[(size_t)(r0 + r) * v.ld + i] * ys[r];
-    }
-    if (i < n) {
-        double* x = v.x + (size_t)f * v.ld;
-        if (fabs(acc) > kDelta) x[i] += acc;
-    }
+    if (i >= n) return;
+    const double d = v.dx[(size_t)f * v.ld + i];
+    if (fabs(d) > kDelta) v.x[(size_t)f * v.ld + i] += d;
 }
 
 // U4 (a): J = d(q/|q|)/dq at the un-normalised q, then q <- q/|q| (E/Update.cpp:45-60,309-317)
