@@ -151,6 +151,15 @@ int ekfb_profile_enable(ekfb_handle h, int on);
  * rescue, misc (9 floats), plus launch counts (9 ints) */
 int ekfb_profile_read(ekfb_handle h, float* ms9, int32_t* launches9);
 int64_t ekfb_kernel_launches(ekfb_handle h);     /* kernels launched by this handle so far */
+/* write a scratch buffer larger than L2 on the handle's stream (timing hygiene between iterations) */
+int ekfb_flush_l2(ekfb_handle h);
+/* Per-launch timing of the covariance downdate kernel (the roofline kernel).  enable != 0 starts
+ * recording one CUDA-event pair around every downdate launch (no host sync in the stream);
+ * ekfb_downdate_stats synchronises and returns the summed kernel time, the number of launches and
+ * the algorithmic flops n(n+1)k summed over those launches, then clears the pool. */
+int ekfb_downdate_timing(ekfb_handle h, int enable);
+int ekfb_downdate_stats(ekfb_handle h, double* ms_total, int64_t* launches, double* flops_total,
+                        double* bytes_min_total);
 
 #ifdef __cplusplus
 }

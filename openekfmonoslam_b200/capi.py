@@ -212,3 +212,13 @@ class EkfBatch:
 
     def kernel_launches(self):
         return int(self.L.ekfb_kernel_launches(self.h))
+
+    def flush_l2(self): self._ck(self.L.ekfb_flush_l2(self.h))
+
+    def downdate_timing(self, on=True): self._ck(self.L.ekfb_downdate_timing(self.h, ctypes.c_int(1 if on else 0)))
+
+    def downdate_stats(self):
+        ms, fl, by = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        ln = ctypes.c_int64()
+        self._ck(self.L.ekfb_downdate_stats(self.h, ctypes.byref(ms), ctypes.byref(ln), ctypes.byref(fl), ctypes.byref(by)))
+        return dict(ms=ms.value, launches=ln.value, flops=fl.value, bytes_min=by.value)

@@ -70,6 +70,13 @@ struct ekfb_ctx {
     int cur_group = G_MISC;
     int64_t launches = 0;
     float last_downdate_ms = 0.f;
+    // L2 flush scratch and the per-launch event pool of the downdate kernel
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    bool dd_timing = false;
+    std::vector<cudaEvent_t> dd_ev;   // pairs
+    size_t dd_used = 0;               // events used
+    double dd_flops = 0., dd_bytes = 0.;
 };
 
 template <typename T>
@@ -221,6 +228,8 @@ extern "C" int ekfb_destroy(ekfb_handle c)
         if (s.xy) cudaFree(s.xy);
         if (s.desc) cudaFree(s.desc);
     }
+    if (c->flush_buf) cudaFree(c->flush_buf);
+    for (cudaEvent_t e : c->dd_ev) cudaEventDestroy(e);
     cudaFreeHost(c->h_dims);
     cudaFreeHost(c->h_kpxy_ptr);
     cudaFreeHost(c->h_kpdesc_ptr);
@@ -525,7 +534,20 @@ static int run_update(ekfb_ctx* c, int which)
     {
         GroupScope gs(c, G_DOWNDATE);
         const int nt = cdiv(n, kTM);
+        const bool timeIt = c->dd_timing && c->dd_used + 2 <= c->dd_ev.size();
+        if (timeIt) cudaEventRecord(c->dd_ev[c->dd_used], c->stream);
         k_gemm_tn<2><<<dim3(nt, nt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, 0);
+        if (timeIt) {
+            cudaEventRecord(c->dd_ev[c->dd_used + 1], c->stream);
+            c->dd_used += 2;
+            for (int f = 0; f < c->F; ++f) {
+                const double nf = c->hn[f], kf = 2.0 * c->h_dims[(size_t)f * D_STRIDE + D_ULIST];
+                if (kf > 0) {
+                    c->dd_flops += nf * (nf + 1.0) * kf;   // symmetric rank-k form
+                    c->dd_bytes += 16.0 * nf * nf;         // read + write P once
+                }
+            }
+        }
         k_quat_cov<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
         count_launch(c, 2);
     }
@@ -767,3 +789,50 @@ extern "C" int ekfb_profile_read(ekfb_handle c, float* ms9, int32_t* launches9)
 }
 
 extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches : 0; }
+
+extern "C" int ekfb_flush_l2(ekfb_handle c)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    if (!c->flush_buf) {
+        c->flush_bytes = (size_t)256 << 20;  // > 126 MB L2
+        CK(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    CK(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_downdate_timing(ekfb_handle c, int enable)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    if (enable && c->dd_ev.empty()) {
+        c->dd_ev.resize(8192);
+        for (cudaEvent_t& e : c->dd_ev) CK(cudaEventCreate(&e));
+    }
+    c->dd_timing = enable != 0;
+    c->dd_used = 0;
+    c->dd_flops = c->dd_bytes = 0.;
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_downdate_stats(ekfb_handle c, double* ms_total, int64_t* launches, double* flops_total,
+                                   double* bytes_min_total)
+{
+    REQUIRE(c, "null handle");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    double ms = 0.;
+    for (size_t i = 0; i + 1 < c->dd_used; i += 2) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, c->dd_ev[i], c->dd_ev[i + 1]));
+        ms += t;
+    }
+    if (ms_total) *ms_total = ms;
+    if (launches) *launches = (int64_t)(c->dd_used / 2);
+    if (flops_total) *flops_total = c->dd_flops;
+    if (bytes_min_total) *bytes_min_total = c->dd_bytes;
+    c->dd_used = 0;
+    c->dd_flops = c->dd_bytes = 0.;
+    return EKFB_OK;
+}

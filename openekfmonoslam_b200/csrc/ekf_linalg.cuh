@@ -119,19 +119,24 @@ __global__ void k_build_S(DevView v, int which)
 // Column tiles run over the virtual concatenation of S's columns right of the block and B's n+1
 // columns.  grid (tiles, F), 128 threads.
 // ---------------------------------------------------------------------------------------------
-// forward substitution of one column of the row block (64 values in registers), separate function so
-// that its register allocation is independent of the diagonal-tile phase
+// forward substitution of one column of the row block (64 values in registers, multipliers read as
+// double2 broadcasts); a separate function so that its register allocation is its own
 __device__ __noinline__ double panel_substitute(double* colp, int ldx, int kb, const double* Msm, const double* dinvs,
                                                 const double* ysm)
 {
     double x[kNB];
 #pragma unroll
     for (int i = 0; i < kNB; ++i) x[i] = (i < kb) ? colp[(size_t)i * ldx] : 0.0;
+    const double2* M2 = reinterpret_cast<const double2*>(Msm);
 #pragma unroll
     for (int c = 0; c < kNB - 1; ++c) {
         const double xc = x[c];
 #pragma unroll
-        for (int i = c + 1; i < kNB; ++i) x[i] -= Msm[c * kNB + i] * xc;
+        for (int p = c / 2; p < kNB / 2; ++p) {  // M[c][i] is zero for i <= c, so whole pairs are safe
+            const double2 m = M2[c * (kNB / 2) + p];
+            if (2 * p > c) x[2 * p] -= m.x * xc;
+            x[2 * p + 1] -= m.y * xc;
+        }
     }
     double part = 0.0;
 #pragma unroll
@@ -145,9 +150,23 @@ __device__ __noinline__ double panel_substitute(double* colp, int ldx, int kb, c
 
 constexpr int kPanelCols = 128;
 
+// ---------------------------------------------------------------------------------------------
+// Cholesky step J, panel kernel: the 64-row block J of the augmented matrix [S | B | nu] becomes
+// [U_JJ | X_J | y_J] with X_J = U_JJ^-T A_J.  Every CTA owns 128 columns (one per thread) and
+//   (1) redundantly eliminates the 64x64 diagonal tile plus the nu column: thread (i, h) keeps the
+//       entries of row i in columns j = h (mod 2) in registers, the pivot row is broadcast through
+//       a double-buffered shared row (one barrier per pivot, reciprocal instead of division),
+//       leaving the multipliers M[c][i] = A(c)[c][i] / A(c)[c][c], 1/sqrt(pivot) and y_J in smem;
+//   (2) applies the same row operations to its own columns: 64 values per thread in registers,
+//       2016 FMAs, no barrier (forward substitution without forming an inverse);
+//   (3) accumulates its share of the state correction dx[col] += sum_r X[r][col] * y[r]
+//       (E/Update.cpp:136-141: K nu = W y), own columns only, so no atomics and a fixed order.
+// Column tiles run over the virtual concatenation of S's columns right of the block and B's n+1
+// columns.  grid (tiles, F), 128 threads.
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_chol_panel(DevView v, int J)
 {
-    __shared__ double rowbuf[2][72];
+    __shared__ __align__(16) double rowbuf[2][66];
     __shared__ __align__(16) double Msm[kNB * kNB];
     __shared__ double dinvs[kNB], ysm[kNB];
     const int f = blockIdx.y;
@@ -176,50 +195,57 @@ __global__ void __launch_bounds__(128) k_chol_panel(DevView v, int J)
     const double* nuCol = v.Bu + ((size_t)f * v.kmax + J0) * v.ld + n;
     for (int e = tid; e < kNB * kNB; e += blockDim.x) Msm[e] = 0.0;
 
-    // ---- (1) diagonal tile elimination, thread j <-> column j (j = 64: the nu column) ----
-    double a[kNB];
+    // ---- (1) diagonal tile elimination: thread (i, h) owns row i, columns j = 2 q + h, q = 0..32 ----
+    {
+        const int i = tid >> 1, h = tid & 1;
+        double a[33];
 #pragma unroll
-    for (int i = 0; i < kNB; ++i) {
-        double val = 0.0;
-        if (tid < kNB) {
-            if (i < kb && tid < kb) { if (i <= tid) val = Sd[(size_t)i * v.ldS + tid]; }
-            else if (i == tid) val = 1.0;  // identity padding of a partial last block
-        } else if (tid == kNB) {
-            if (i < kb) val = nuCol[(size_t)i * v.ld];
+        for (int q = 0; q < 33; ++q) {
+            const int j = 2 * q + h;
+            double val = 0.0;
+            if (j < kNB) {
+                if (i < kb && j < kb) { if (j >= i) val = Sd[(size_t)i * v.ldS + j]; }
+                else if (i == j) val = 1.0;  // identity padding of a partial last block
+            } else if (j == kNB) {
+                if (i < kb) val = nuCol[(size_t)i * v.ld];
+            }
+            a[q] = val;
         }
-        a[i] = val;
-    }
-    __syncthreads();
+        if (i == 0) {
 #pragma unroll
-    for (int c = 0; c < kNB; ++c) {
-        double* buf = rowbuf[c & 1];
-        if (tid >= c && tid <= kNB) buf[tid] = a[c];
+            for (int q = 0; q < 33; ++q) rowbuf[0][2 * q + h] = a[q];
+        }
+        for (int c = 0; c < kNB; ++c) {
+            __syncthreads();
+            const double* rb = rowbuf[c & 1];
+            const double piv = rb[c];
+            const double pinv = 1.0 / piv;
+            const double dinv = rsqrt(piv);
+            if (tid == 0) {
+                if (!(piv > 0.0)) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
+                dinvs[c] = dinv;
+                ysm[c] = rb[kNB] * dinv;
+            }
+            if (blockIdx.x == 0 && tid < kNB && c < kb && tid < kb)  // U_JJ row c back to S (zeros left of the diagonal)
+                Sd[(size_t)c * v.ldS + tid] = (tid >= c) ? rb[tid] * dinv : 0.0;
+            if (i > c) {
+                const double m = rb[i] * pinv;
+                if (h == 0) Msm[c * kNB + i] = m;
+                const double2* rb2 = reinterpret_cast<const double2*>(rb);
+#pragma unroll
+                for (int q = 0; q < 33; ++q) {
+                    const double2 r2 = rb2[q];
+                    a[q] -= m * (h ? r2.y : r2.x);
+                }
+                if (i == c + 1) {
+                    double* nb = rowbuf[(c + 1) & 1];
+#pragma unroll
+                    for (int q = 0; q < 33; ++q) nb[2 * q + h] = a[q];
+                }
+            }
+        }
         __syncthreads();
-        const double piv = buf[c];
-        const double pinv = 1.0 / piv;
-        if (tid == c) {
-            if (!(piv > 0.0)) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
-            dinvs[c] = rsqrt(piv);
-        }
-        if (tid > c && tid <= kNB) {
-            const double mj = buf[tid] * pinv;
-            if (tid < kNB) Msm[c * kNB + tid] = mj;
-#pragma unroll
-            for (int i = c + 1; i < kNB; ++i)
-                if (i <= tid) a[i] -= buf[i] * mj;
-        }
     }
-    __syncthreads();
-    if (tid == kNB) {
-#pragma unroll
-        for (int c = 0; c < kNB; ++c) ysm[c] = a[c] * dinvs[c];
-    }
-    if (blockIdx.x == 0 && tid < kNB && tid < kb) {  // U_JJ back to S (upper), zeros below
-#pragma unroll
-        for (int i = 0; i < kNB; ++i)
-            if (i < kb) Sd[(size_t)i * v.ldS + tid] = (i <= tid) ? a[i] * dinvs[i] : 0.0;
-    }
-    __syncthreads();
 
     // ---- (2) forward substitution on this CTA's columns ----
     const int col = c0 + tid;

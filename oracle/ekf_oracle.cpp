@@ -61,19 +61,52 @@ Mat eye(int n)
     return m;
 }
 
-// C = A * B, plain i-k-j product (what cv::gemm computes; summation order is not part of parity)
+// C += A * B (row-major).  Same dense product cv::gemm computes (summation order is not part of
+// parity), cache-blocked over k and j with 4 rows of A per pass so that timing the oracle is a fair
+// stand-in for OpenCV 2.4's blocked SSE2 gemm; target_clones picks AVX2+FMA at run time when present.
+__attribute__((target_clones("avx2,fma", "default")))
+void gemmAcc(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int K, int N)
+{
+    const int KB = 128, JB = 1024;
+    for (int jb = 0; jb < N; jb += JB) {
+        const int je = std::min(N, jb + JB);
+        for (int kb = 0; kb < K; kb += KB) {
+            const int ke = std::min(K, kb + KB);
+            int i = 0;
+            for (; i + 4 <= M; i += 4) {
+                double* c0 = C + (size_t)i * ldc;
+                double* c1 = c0 + ldc;
+                double* c2 = c1 + ldc;
+                double* c3 = c2 + ldc;
+                for (int k = kb; k < ke; ++k) {
+                    const double a0 = A[(size_t)i * lda + k], a1 = A[(size_t)(i + 1) * lda + k];
+                    const double a2 = A[(size_t)(i + 2) * lda + k], a3 = A[(size_t)(i + 3) * lda + k];
+                    const double* b = B + (size_t)k * ldb;
+                    for (int j = jb; j < je; ++j) {
+                        const double bv = b[j];
+                        c0[j] += a0 * bv;
+                        c1[j] += a1 * bv;
+                        c2[j] += a2 * bv;
+                        c3[j] += a3 * bv;
+                    }
+                }
+            }
+            for (; i < M; ++i) {
+                double* c0 = C + (size_t)i * ldc;
+                for (int k = kb; k < ke; ++k) {
+                    const double a0 = A[(size_t)i * lda + k];
+                    const double* b = B + (size_t)k * ldb;
+                    for (int j = jb; j < je; ++j) c0[j] += a0 * b[j];
+                }
+            }
+        }
+    }
+}
+
 Mat mul(const Mat& A, const Mat& B)
 {
     Mat C(A.r, B.c);
-    for (int i = 0; i < A.r; ++i) {
-        double* ci = C.row(i);
-        const double* ai = A.row(i);
-        for (int k = 0; k < A.c; ++k) {
-            const double a = ai[k];
-            const double* bk = B.row(k);
-            for (int j = 0; j < B.c; ++j) ci[j] += a * bk[j];
-        }
-    }
+    gemmAcc(A.d.data(), A.c, B.d.data(), B.c, C.d.data(), C.c, A.r, A.c, B.c);
     return C;
 }
 
