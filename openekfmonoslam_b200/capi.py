@@ -213,6 +213,8 @@ class EkfBatch:
     def kernel_launches(self):
         return int(self.L.ekfb_kernel_launches(self.h))
 
+    def set_option(self, option, value): self._ck(self.L.ekfb_set_option(self.h, ctypes.c_int(option), ctypes.c_int(value)))
+
     def flush_l2(self): self._ck(self.L.ekfb_flush_l2(self.h))
 
     def downdate_timing(self, on=True): self._ck(self.L.ekfb_downdate_timing(self.h, ctypes.c_int(1 if on else 0)))

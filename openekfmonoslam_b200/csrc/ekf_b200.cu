@@ -73,6 +73,7 @@ struct ekfb_ctx {
     // L2 flush scratch and the per-launch event pool of the downdate kernel
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
+    bool force_generic = false;
     bool dd_timing = false;
     std::vector<cudaEvent_t> dd_ev;   // pairs
     size_t dd_used = 0;               // events used
@@ -152,7 +153,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     c->ld = rup(c->nmax + 1, 16);
     c->Kpmax = max_keypoints;
     c->kmax = rup(2 * max_features, kNB);
-    c->ldS = rup(c->kmax, 16);
+    c->ldS = rup(c->kmax + 1, 16);
     c->supWords = cdiv(max_features, 32);
     std::memset(c->prof_ms, 0, sizeof(c->prof_ms));
     std::memset(c->prof_launch, 0, sizeof(c->prof_launch));
@@ -185,7 +186,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     ALLOC(v.inl, F * N); ALLOC(v.outl, F * N); ALLOC(v.resc, F * N); ALLOC(v.ulist, F * N);
     ALLOC(v.kpok, F * c->Kpmax); ALLOC(v.mask, F * (size_t)v.W * v.H);
     ALLOC(v.hypcount, F * N); ALLOC(v.hypsup, F * N * c->supWords);
-    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.dx, F * c->ld); ALLOC(v.Jq, F * 16);
+    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.dx, F * c->ld); ALLOC(v.Uinv, F * (c->kmax / kNB) * kNB * kNB); ALLOC(v.Jq, F * 16);
     ALLOC(c->d_kpxy, F * c->Kpmax * 2); ALLOC(c->d_kpdesc, F * c->Kpmax * 32);
     ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F);
     ALLOC(c->d_rec, F);
@@ -209,6 +210,10 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
 
     CK(cudaFuncSetAttribute(k_gemm_tn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_gemm_tn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_schain_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, kSTrailSmem));
+    CK(cudaFuncSetAttribute(k_invert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kInvSmem));
+    CK(cudaFuncSetAttribute(k_trsm_slab<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_trsm_slab<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_ransac_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             std::min<int>(227 * 1024 - 2048, c->ld * (int)sizeof(double))));
     const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
@@ -515,16 +520,39 @@ static int run_update(ekfb_ctx* c, int which)
     {
         GroupScope gs(c, G_CHOL);
         const int steps = cdiv(k, kNB);
-        for (int J = 0; J < steps; ++J) {
-            const int J1 = (J + 1) * kNB;
-            const int nS = k > J1 ? cdiv(k - J1, kPanelCols) : 0;
-            const int nB = cdiv(n + 1, kPanelCols);
-            k_chol_panel<<<dim3(nS + nB, c->F), 128, 0, c->stream>>>(v, J);
-            count_launch(c);
-            if (k > J1) {
-                const int mt = cdiv(k - J1, kTM);
-                k_gemm_tn<0><<<dim3(cdiv(k - J1, kTN) + cdiv(n + 1, kTN), mt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, J);
+        const size_t smem24 = trsm_smem_bytes(k, 24), smem16 = trsm_smem_bytes(k, 16);
+        const size_t smemMax = 227 * 1024;
+        if (smem16 <= smemMax && !c->force_generic) {
+            // fast path: S-only chain, diagonal-block inverses, slab TRSM
+            for (int J = 0; J < steps; ++J) {
+                const int J0 = J * kNB, J1 = J0 + kNB;
+                const int Jr = std::min(J1, k);
+                k_schain_panel<<<dim3(cdiv(k + 1 - Jr, 256), c->F), 256, 0, c->stream>>>(v, J);
                 count_launch(c);
+                if (k > J1) {
+                    k_schain_trail<<<dim3(cdiv(k + 1 - J1, 64), cdiv(k - J1, 64), c->F), 128, kSTrailSmem, c->stream>>>(v, J);
+                    count_launch(c);
+                }
+            }
+            k_invert_diag<<<dim3(steps, c->F), 256, kInvSmem, c->stream>>>(v);
+            if (smem24 <= smemMax)
+                k_trsm_slab<24><<<dim3(cdiv(n, 24), c->F), 256, smem24, c->stream>>>(v);
+            else
+                k_trsm_slab<16><<<dim3(cdiv(n, 16), c->F), 256, smem16, c->stream>>>(v);
+            count_launch(c, 2);
+        } else {
+            // generic path (very large k): right-looking over the whole augmented matrix
+            for (int J = 0; J < steps; ++J) {
+                const int J1 = (J + 1) * kNB;
+                const int nS = k > J1 ? cdiv(k - J1, kPanelCols) : 0;
+                const int nB = cdiv(n + 1, kPanelCols);
+                k_chol_panel<<<dim3(nS + nB, c->F), 128, 0, c->stream>>>(v, J);
+                count_launch(c);
+                if (k > J1) {
+                    const int mt = cdiv(k - J1, kTM);
+                    k_gemm_tn<0><<<dim3(cdiv(k - J1, kTN) + cdiv(n + 1, kTN), mt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, J);
+                    count_launch(c);
+                }
             }
         }
         k_state_apply<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
@@ -789,6 +817,14 @@ extern "C" int ekfb_profile_read(ekfb_handle c, float* ms9, int32_t* launches9)
 }
 
 extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches : 0; }
+
+extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(option == EKFB_OPT_FORCE_GENERIC_FACTOR, "unknown option");
+    c->force_generic = value != 0;
+    return EKFB_OK;
+}
 
 extern "C" int ekfb_flush_l2(ekfb_handle c)
 {

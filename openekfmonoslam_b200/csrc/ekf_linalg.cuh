@@ -104,6 +104,8 @@ __global__ void k_build_S(DevView v, int which)
     for (int c = 0; c < d; ++c) acc += Hf[c] * Brow[off + c];
     if (ra == rb) acc += v.sigma_px;
     v.S[((size_t)f * v.kmax + ra) * v.ldS + rb] = acc;
+    if (rb == 0)  // column k of S carries the dead-banded innovation nu (it becomes y = U^-T nu)
+        v.S[((size_t)f * v.kmax + ra) * v.ldS + k] = deadband(v.z[(fo + j) * 2 + r] - s.h[(fo + j) * 2 + r]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -226,8 +228,6 @@ __global__ void __launch_bounds__(128) k_chol_panel(DevView v, int J)
                 dinvs[c] = dinv;
                 ysm[c] = rb[kNB] * dinv;
             }
-            if (blockIdx.x == 0 && tid < kNB && c < kb && tid < kb)  // U_JJ row c back to S (zeros left of the diagonal)
-                Sd[(size_t)c * v.ldS + tid] = (tid >= c) ? rb[tid] * dinv : 0.0;
             if (i > c) {
                 const double m = rb[i] * pinv;
                 if (h == 0) Msm[c * kNB + i] = m;
@@ -413,6 +413,321 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
                 }
             }
         }
+    }
+}
+
+// =============================================================================================
+// Fast path of the factorisation (k small enough for a shared-memory slab, the normal case):
+//   S-chain : right-looking blocked Cholesky of [S | nu] ONLY (k x (k+1)); small latency-bound kernels
+//   k_invert_diag : inverses of the 64x64 diagonal blocks of U, all blocks in parallel
+//   k_trsm_slab   : W^T = U^-T B, one CTA per slab of SW columns of B held entirely in shared memory,
+//                   left-looking over row blocks, all products on the FP64 tensor pipe; also dx = W y
+// B is read once and W^T written once; no kernel of the chain touches the n-wide part.
+// =============================================================================================
+
+// S-chain panel, step J: 256 threads.  Phase 1: the diagonal tile is eliminated with thread (i, h) owning
+// row i, columns j = h (mod 4); the pivot row goes through a double-buffered shared row, one barrier
+// and one reciprocal per pivot.  Phase 2: one column of [S(J, >J) | nu] per thread, register-resident
+// forward substitution.  grid (ceil((k + 1 - Jr) / 256), F), Jr = min(J1, k).
+__global__ void __launch_bounds__(256) k_schain_panel(DevView v, int J)
+{
+    __shared__ __align__(16) double rowbuf[2][kNB];
+    __shared__ __align__(16) double Msm[kNB * kNB];
+    __shared__ double dinvs[kNB], ysm[kNB];
+    const int f = blockIdx.y;
+    int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST];
+    const int J0 = J * kNB;
+    if (J0 >= k) return;
+    const int kb = min(kNB, k - J0);
+    const int Jr = J0 + kb;
+    const int tid = threadIdx.x;
+    double* Srow = v.S + ((size_t)f * v.kmax + J0) * v.ldS;
+    const double* Sd = Srow + J0;
+    double* Ublk = v.Uinv + ((size_t)f * (v.kmax / kNB) + J) * kNB * kNB;
+    for (int e = tid; e < kNB * kNB; e += blockDim.x) Msm[e] = 0.0;
+    if (tid < kNB) ysm[tid] = 0.0;
+    {
+        const int i = tid >> 2, h = tid & 3;
+        double a[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int j = 4 * q + h;
+            double val = 0.0;
+            if (i < kb && j < kb) { if (j >= i) val = Sd[(size_t)i * v.ldS + j]; }
+            else if (i == j) val = 1.0;
+            a[q] = val;
+        }
+        if (i == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) rowbuf[0][4 * q + h] = a[q];
+        }
+        for (int c = 0; c < kNB; ++c) {
+            __syncthreads();
+            const double* rb = rowbuf[c & 1];
+            const double piv = rb[c];
+            const double pinv = __drcp_rn(piv);
+            if (i > c) {
+                const double m = rb[i] * pinv;
+                if (h == 0) Msm[c * kNB + i] = m;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) a[q] -= m * rb[4 * q + h];
+                if (i == c + 1) {
+                    double* nb = rowbuf[(c + 1) & 1];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) nb[4 * q + h] = a[q];
+                }
+            }
+            // off the critical path: 1/sqrt(pivot) and the U row for the write-back
+            if (tid < kNB) {
+                const double dinv = rsqrt(piv);
+                if (tid == c) {
+                    if (!(piv > 0.0)) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
+                    dinvs[c] = dinv;
+                }
+                // U_JJ row c goes to the Uinv slot of this block (NOT in place: the other CTAs of this launch
+                // are still reading the original tile); k_invert_diag inverts it there
+                if (blockIdx.x == 0) Ublk[c * kNB + tid] = (tid >= c) ? rb[tid] * dinv : 0.0;
+            }
+        }
+        __syncthreads();
+    }
+    const int col = Jr + blockIdx.x * blockDim.x + tid;
+    if (col > k) return;  // columns Jr .. k (column k = nu)
+    panel_substitute(Srow + col, v.ldS, kb, Msm, dinvs, ysm);
+}
+
+// S-chain trailing update, step J (J1 < k):  S[I, c] -= X_J[:, I]^T X_J[:, c] for rows I >= J1 and columns
+// c in [I, k] (column k = nu).  64x64 tiles, 4 warps of 32x32, K = 64 loaded in one shot.
+// grid (ceil((k + 1 - J1) / 64), ceil((k - J1) / 64), F), dynamic smem 2 * 64 * 68 doubles.
+constexpr int kSTrailSmem = 2 * kNB * 68 * (int)sizeof(double);
+
+__global__ void __launch_bounds__(128) k_schain_trail(DevView v, int J)
+{
+    extern __shared__ __align__(16) double ssm[];
+    double* As = ssm;
+    double* Bs = ssm + kNB * 68;
+    const int f = blockIdx.z;
+    const int k = 2 * fdims(v, f)[D_ULIST];
+    const int J0 = J * kNB, J1 = J0 + kNB;
+    if (J1 >= k) return;
+    const int tm0 = J1 + blockIdx.y * 64, tn0 = J1 + blockIdx.x * 64;
+    if (tm0 >= k || tn0 > k) return;
+    if (tn0 + 64 <= tm0) return;  // strictly below the diagonal
+    const double* X = v.S + ((size_t)f * v.kmax + J0) * v.ldS;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool same = (tm0 == tn0);
+    for (int e = tid; e < kNB * 32; e += blockDim.x) {  // 64 rows x 32 double2 per operand
+        const int r = e >> 5, c2 = (e & 31) * 2;
+        if (tm0 + c2 < v.ldS) cp_async16(As + r * 68 + c2, X + (size_t)r * v.ldS + tm0 + c2);
+        else { As[r * 68 + c2] = 0.0; As[r * 68 + c2 + 1] = 0.0; }
+        if (!same) {
+            if (tn0 + c2 < v.ldS) cp_async16(Bs + r * 68 + c2, X + (size_t)r * v.ldS + tn0 + c2);
+            else { Bs[r * 68 + c2] = 0.0; Bs[r * 68 + c2 + 1] = 0.0; }
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const double* Bsrc = same ? As : Bs;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = w >> 1, wn = w & 1;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll 4
+    for (int k4 = 0; k4 < kNB; k4 += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = As[(k4 + q) * 68 + wm * 32 + a * 8 + g];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = Bsrc[(k4 + q) * 68 + wn * 32 + b * 8 + g];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    double* C = v.S + (size_t)f * v.kmax * v.ldS;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int gm = tm0 + wm * 32 + a * 8 + g;
+        if (gm >= k) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gn = tn0 + wn * 32 + b * 8 + 2 * q + e;
+                if (gn <= k) C[(size_t)gm * v.ldS + gn] -= acc[a][b][e];
+            }
+    }
+}
+
+// Inverse of every 64x64 diagonal block U_JJ (upper triangular; identity padding of a partial last
+// block) into Uinv[f][J][64][64].  4 lanes per column split the dot products.  grid (steps, F), 256 threads.
+constexpr int kInvSmem = 2 * kNB * (kNB + 1) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256) k_invert_diag(DevView v)
+{
+    extern __shared__ __align__(16) double ism[];
+    double (*U)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(ism);
+    double (*Ui)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(ism + kNB * (kNB + 1));
+    const int f = blockIdx.y, J = blockIdx.x;
+    const int k = 2 * fdims(v, f)[D_ULIST];
+    const int J0 = J * kNB;
+    if (J0 >= k) return;
+    const int kb = min(kNB, k - J0);
+    double* blk = v.Uinv + ((size_t)f * (v.kmax / kNB) + J) * kNB * kNB;  // holds U_JJ (identity padded)
+    (void)kb;
+    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
+        const int i = e / kNB, j = e % kNB;
+        U[i][j] = (j >= i) ? blk[e] : 0.0;
+        Ui[i][j] = 0.0;
+    }
+    __syncthreads();
+    const int t = threadIdx.x >> 2, l = threadIdx.x & 3;  // column t, 4 lanes
+    if (l == 0) Ui[t][t] = 1.0 / U[t][t];
+    __syncwarp();
+    for (int i = kNB - 2; i >= 0; --i) {  // warp-uniform trip count: the shuffles need every lane
+        double s = 0.;
+        if (i < t)
+            for (int qq = i + 1 + l; qq <= t; qq += 4) s += U[i][qq] * Ui[qq][t];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (l == 0 && i < t) Ui[i][t] = -s / U[i][i];
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) blk[e] = Ui[e / kNB][e % kNB];
+}
+
+// W^T = U^-T B on the tensor pipe.  CTA = slab of SW columns of B kept in shared memory (K-major,
+// pitch SW + 4).  For row block J (left-looking):
+//     T   = B_J - sum_{r < J0} U[r][J0 + m] * X[r][c]        (A chunks: 32 rows x 64 cols of U)
+//     X_J = Uinv_J^T T                                       (A chunks: the two halves of Uinv_J)
+// All A chunks of all row blocks form one stream that is double-buffered with cp.async one chunk ahead,
+// so L2 latency is hidden across block boundaries.  8 warps: warp w owns rows 8w..8w+7 of the block.
+// Finally dx[c] = sum_r X[r][c] y[r] (y = column k of the factored S) and W^T goes back to global.
+// grid (ceil(n / SW), F), 256 threads, dynamic smem trsm_smem_bytes(k, SW).
+template <int SW>
+__host__ __device__ constexpr int trsm_pitch() { return SW + 4; }
+
+inline size_t trsm_smem_bytes(int k, int SW)
+{
+    const int kpad = (k + kNB - 1) / kNB * kNB;
+    return sizeof(double) * ((size_t)kpad * (SW + 4) + 2 * 32 * 68 + (size_t)kNB * (SW + 4) + 8 * SW);
+}
+
+template <int SW>
+__global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
+{
+    constexpr int SWP = SW + 4, NT = SW / 8;
+    extern __shared__ __align__(16) double tsm[];
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST], n = dm[D_N_STATE];
+    if (k == 0) return;
+    const int c0 = blockIdx.x * SW;
+    if (c0 >= n) return;
+    const int kpad = (k + kNB - 1) / kNB * kNB, steps = kpad / kNB;
+    double* Xs = tsm;
+    double* Us = Xs + (size_t)kpad * SWP;   // 2 stages x [32][68]
+    double* Ts = Us + 2 * 32 * 68;          // [64][SWP]
+    double* red = Ts + kNB * SWP;           // [8][SW]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* Bg = v.Bu + (size_t)f * v.kmax * v.ld;
+    const double* Sg = v.S + (size_t)f * v.kmax * v.ldS;
+    const double* Uinv = v.Uinv + (size_t)f * (v.kmax / kNB) * kNB * kNB;
+
+    for (int e = tid; e < kpad * SW; e += blockDim.x) {
+        const int r = e / SW, c = e % SW;
+        Xs[(size_t)r * SWP + c] = (r < k && c0 + c < n) ? Bg[(size_t)r * v.ld + c0 + c] : 0.0;
+    }
+    // chunk stream: for block J: J0/32 chunks of U, then 2 chunks of Uinv_J
+    auto issue = [&](int J, int ch, int stage) {
+        const int J0 = J * kNB, nU = J0 / 32;
+        double* dst = Us + stage * 32 * 68;
+        const double* src;
+        int lds;
+        if (ch < nU) { src = Sg + (size_t)(ch * 32) * v.ldS + J0; lds = v.ldS; }
+        else { src = Uinv + (size_t)J * kNB * kNB + (size_t)(ch - nU) * 32 * kNB; lds = kNB; }
+        for (int e = tid; e < 32 * 32; e += blockDim.x) {
+            const int r = e >> 5, c2 = (e & 31) * 2;
+            cp_async16(dst + r * 68 + c2, src + (size_t)r * lds + c2);
+        }
+    };
+    int J = 0, ch = 0, stage = 0;
+    issue(0, 0, 0);
+    cp_async_commit();
+    double acc[NT][2];
+    while (J < steps) {
+        const int J0 = J * kNB, nU = J0 / 32, nCh = nU + 2;
+        const int kb = min(kNB, k - J0);
+        if (ch == 0) {
+#pragma unroll
+            for (int b = 0; b < NT; ++b) acc[b][0] = acc[b][1] = 0.0;
+        }
+        // prefetch the next chunk of the stream
+        int Jn = J, chn = ch + 1;
+        if (chn == nCh) { Jn = J + 1; chn = 0; }
+        if (Jn < steps) issue(Jn, chn, stage ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* Uc = Us + stage * 32 * 68;
+        if (ch == nU) {
+            // T = B_J - acc -> Ts (rows beyond the block are zero), then restart the accumulator
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = 8 * w + g, c = 8 * b + 2 * q + e;
+                    Ts[m * SWP + c] = (m < kb) ? Xs[(size_t)(J0 + m) * SWP + c] - acc[b][e] : 0.0;
+                    acc[b][e] = 0.0;
+                }
+            __syncthreads();
+        }
+        const double* Bsrc = (ch < nU) ? Xs + (size_t)(ch * 32) * SWP : Ts + (size_t)((ch - nU) * 32) * SWP;
+#pragma unroll
+        for (int k4 = 0; k4 < 32; k4 += 4) {
+            const double a = Uc[(k4 + q) * 68 + 8 * w + g];
+#pragma unroll
+            for (int b = 0; b < NT; ++b) dmma8x8x4(acc[b][0], acc[b][1], a, Bsrc[(size_t)(k4 + q) * SWP + 8 * b + g]);
+        }
+        if (ch == nCh - 1) {
+            // X_J complete: store into the slab
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = 8 * w + g, c = 8 * b + 2 * q + e;
+                    Xs[(size_t)(J0 + m) * SWP + c] = (m < kb) ? acc[b][e] : 0.0;
+                }
+        }
+        __syncthreads();  // stage buffer and Ts / Xs hazards before the next chunk
+        stage ^= 1;
+        J = Jn;
+        ch = chn;
+    }
+    cp_async_wait<0>();
+    // W^T back to global, dx = W y
+    for (int e = tid; e < k * SW; e += blockDim.x) {
+        const int r = e / SW, c = e % SW;
+        if (c0 + c < n) Bg[(size_t)r * v.ld + c0 + c] = Xs[(size_t)r * SWP + c];
+    }
+    if (lane < SW) {
+        double s = 0.;
+        for (int r = w; r < k; r += 8) s += Xs[(size_t)r * SWP + lane] * Sg[(size_t)r * v.ldS + k];
+        red[w * SW + lane] = s;
+    }
+    __syncthreads();
+    if (tid < SW && c0 + tid < n) {
+        double s = 0.;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) s += red[ww * SW + tid];
+        v.dx[(size_t)f * v.ld + c0 + tid] = s;
     }
 }
 

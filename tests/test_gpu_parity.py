@@ -103,6 +103,15 @@ def test_phase_by_phase_after_warmup_multi_block_update():
     assert gpu.frame_info(0)["n_inliers"] > 40
 
 
+def test_generic_factorisation_path():
+    """The right-looking factorisation over the whole augmented matrix (used when k is too large for the
+    slab TRSM) must agree with the oracle as well; forced here at a size where k spans several blocks."""
+    sc, orc, gpu = make_pair(640, 480, 100, warm=3)
+    gpu.set_option(1, 1)
+    for t in range(4, 7):
+        phase_by_phase(sc, orc, gpu, t)
+
+
 def test_whole_step_sequence_c2():
     """ekfb_step against orc_step over 40 frames, both free-running from the same initial map."""
     sc, orc, gpu = make_pair(320, 240, 50)
