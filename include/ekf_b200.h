@@ -153,8 +153,10 @@ int ekfb_profile_read(ekfb_handle h, float* ms9, int32_t* launches9);
 int64_t ekfb_kernel_launches(ekfb_handle h);     /* kernels launched by this handle so far */
 /* tuning / test switches.  EKFB_OPT_FORCE_GENERIC_FACTOR = 1 forces the right-looking factorisation over
  * the whole augmented matrix (the path used when k is too large for the shared-memory slab TRSM). */
-enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1 };
+enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* 0: 128x128 tiles (default), 1: 128x64 tiles, 2 CTAs/SM */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
+/* developer aid: 64 device-side cycle counters written by instrumented kernels */
+int ekfb_debug_read(ekfb_handle h, long long* out64);
 /* write a scratch buffer larger than L2 on the handle's stream (timing hygiene between iterations) */
 int ekfb_flush_l2(ekfb_handle h);
 /* Per-launch timing of the covariance downdate kernel (the roofline kernel).  enable != 0 starts

@@ -74,6 +74,7 @@ struct ekfb_ctx {
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     bool force_generic = false;
+    int downdate_variant = 0;
     bool dd_timing = false;
     std::vector<cudaEvent_t> dd_ev;   // pairs
     size_t dd_used = 0;               // events used
@@ -186,7 +187,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     ALLOC(v.inl, F * N); ALLOC(v.outl, F * N); ALLOC(v.resc, F * N); ALLOC(v.ulist, F * N);
     ALLOC(v.kpok, F * c->Kpmax); ALLOC(v.mask, F * (size_t)v.W * v.H);
     ALLOC(v.hypcount, F * N); ALLOC(v.hypsup, F * N * c->supWords);
-    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.dx, F * c->ld); ALLOC(v.Uinv, F * (c->kmax / kNB) * kNB * kNB); ALLOC(v.Jq, F * 16);
+    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.dx, F * c->ld); ALLOC(v.dbg, 64); ALLOC(v.Uinv, F * (c->kmax / kNB) * kNB * kNB); ALLOC(v.Jq, F * 16);
     ALLOC(c->d_kpxy, F * c->Kpmax * 2); ALLOC(c->d_kpdesc, F * c->Kpmax * 32);
     ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F);
     ALLOC(c->d_rec, F);
@@ -210,8 +211,9 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
 
     CK(cudaFuncSetAttribute(k_gemm_tn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_gemm_tn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmemBytes));
     CK(cudaFuncSetAttribute(k_schain_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, kSTrailSmem));
-    CK(cudaFuncSetAttribute(k_invert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, kInvSmem));
+    CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
     CK(cudaFuncSetAttribute(k_trsm_slab<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_ransac_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -527,19 +529,18 @@ static int run_update(ekfb_ctx* c, int which)
             for (int J = 0; J < steps; ++J) {
                 const int J0 = J * kNB, J1 = J0 + kNB;
                 const int Jr = std::min(J1, k);
-                k_schain_panel<<<dim3(cdiv(k + 1 - Jr, 256), c->F), 256, 0, c->stream>>>(v, J);
+                k_schain_panel<<<dim3(cdiv(k + 1 - Jr, kSPanelCols), c->F), 128, kSPanelSmem, c->stream>>>(v, J);
                 count_launch(c);
                 if (k > J1) {
                     k_schain_trail<<<dim3(cdiv(k + 1 - J1, 64), cdiv(k - J1, 64), c->F), 128, kSTrailSmem, c->stream>>>(v, J);
                     count_launch(c);
                 }
             }
-            k_invert_diag<<<dim3(steps, c->F), 256, kInvSmem, c->stream>>>(v);
             if (smem24 <= smemMax)
                 k_trsm_slab<24><<<dim3(cdiv(n, 24), c->F), 256, smem24, c->stream>>>(v);
             else
                 k_trsm_slab<16><<<dim3(cdiv(n, 16), c->F), 256, smem16, c->stream>>>(v);
-            count_launch(c, 2);
+            count_launch(c);
         } else {
             // generic path (very large k): right-looking over the whole augmented matrix
             for (int J = 0; J < steps; ++J) {
@@ -561,10 +562,13 @@ static int run_update(ekfb_ctx* c, int which)
     }
     {
         GroupScope gs(c, G_DOWNDATE);
-        const int nt = cdiv(n, kTM);
+        const int nI = cdiv(n, kDTM);
         const bool timeIt = c->dd_timing && c->dd_used + 2 <= c->dd_ev.size();
         if (timeIt) cudaEventRecord(c->dd_ev[c->dd_used], c->stream);
-        k_gemm_tn<2><<<dim3(nt, nt, c->F), 256, kGemmSmemBytes, c->stream>>>(v, 0);
+        if (c->downdate_variant == 1)
+            k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
+        else
+            k_gemm_tn<2><<<dim3(nI, nI, c->F), 256, kGemmSmemBytes, c->stream>>>(v, 0);
         if (timeIt) {
             cudaEventRecord(c->dd_ev[c->dd_used + 1], c->stream);
             c->dd_used += 2;
@@ -734,9 +738,9 @@ extern "C" int ekfb_test_downdate(ekfb_handle c, int n, int k, const double* P_i
     hd[D_N_STATE] = n;
     hd[D_ULIST] = k / 2;
     CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
-    const int nt = cdiv(n, kTM);
+    const int nI = cdiv(n, kDTM);
     CK(cudaEventRecord(c->pe[0], c->stream));
-    k_gemm_tn<2><<<dim3(nt, nt, 1), 256, kGemmSmemBytes, c->stream>>>(v, 0);
+    k_downdate<<<dim3(nI * (nI + 1), 1), 128, kDownSmemBytes, c->stream>>>(v);
     CK(cudaEventRecord(c->pe[1], c->stream));
     count_launch(c);
     CK(cudaGetLastError());
@@ -766,9 +770,9 @@ extern "C" int ekfb_time_update(ekfb_handle c, int which, int reps, float* ms_to
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, c->timers[62], c->timers[63]));
     if (ms_total) *ms_total = ms / reps;
-    const int n = max_of(c->hn), nt = cdiv(n, kTM);
+    const int n = max_of(c->hn), nI = cdiv(n, kDTM);
     CK(cudaEventRecord(c->timers[62], c->stream));
-    for (int r = 0; r < reps; ++r) k_gemm_tn<2><<<dim3(nt, nt, c->F), 256, kGemmSmemBytes, c->stream>>>(c->v, 0);
+    for (int r = 0; r < reps; ++r) k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(c->v);
     CK(cudaEventRecord(c->timers[63], c->stream));
     count_launch(c, reps);
     CK(cudaStreamSynchronize(c->stream));
@@ -821,8 +825,18 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option == EKFB_OPT_FORCE_GENERIC_FACTOR, "unknown option");
-    c->force_generic = value != 0;
+    REQUIRE(option == EKFB_OPT_FORCE_GENERIC_FACTOR || option == EKFB_OPT_DOWNDATE_VARIANT, "unknown option");
+    if (option == EKFB_OPT_FORCE_GENERIC_FACTOR) c->force_generic = value != 0;
+    else c->downdate_variant = value;
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_debug_read(ekfb_handle c, long long* out64)
+{
+    REQUIRE(c && out64, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(out64, c->v.dbg, sizeof(long long) * 64, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return EKFB_OK;
 }
 

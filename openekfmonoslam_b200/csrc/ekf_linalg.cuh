@@ -425,15 +425,50 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
 // B is read once and W^T written once; no kernel of the chain touches the n-wide part.
 // =============================================================================================
 
-// S-chain panel, step J: 256 threads.  Phase 1: the diagonal tile is eliminated with thread (i, h) owning
-// row i, columns j = h (mod 4); the pivot row goes through a double-buffered shared row, one barrier
-// and one reciprocal per pivot.  Phase 2: one column of [S(J, >J) | nu] per thread, register-resident
-// forward substitution.  grid (ceil((k + 1 - Jr) / 256), F), Jr = min(J1, k).
-__global__ void __launch_bounds__(256) k_schain_panel(DevView v, int J)
+// Register-resident forward substitution of one column against the pivot rows kept in shared memory:
+//   x[i] -= U(c)[c][i] * (x[c] / piv_c)  for i > c,  then  x[c] *= 1/sqrt(piv_c).
+__device__ __noinline__ void schain_substitute(double* colp, int ldx, int kb, const double* Urows, const double* pinvs,
+                                               const double* dinvs)
 {
-    __shared__ __align__(16) double rowbuf[2][kNB];
-    __shared__ __align__(16) double Msm[kNB * kNB];
-    __shared__ double dinvs[kNB], ysm[kNB];
+    double x[kNB];
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) x[i] = (i < kb) ? colp[(size_t)i * ldx] : 0.0;
+    const double2* U2 = reinterpret_cast<const double2*>(Urows);
+#pragma unroll
+    for (int c = 0; c < kNB - 1; ++c) {
+        const double xs = x[c] * pinvs[c];
+#pragma unroll
+        for (int p = c / 2; p < kNB / 2; ++p) {
+            const double2 u = U2[c * (kNB / 2) + p];
+            if (2 * p > c) x[2 * p] -= u.x * xs;
+            if (2 * p + 1 > c) x[2 * p + 1] -= u.y * xs;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kNB; ++i)
+        if (i < kb) colp[(size_t)i * ldx] = x[i] * dinvs[i];
+}
+
+// S-chain panel, step J: 128 threads.  Phase 1 eliminates the diagonal tile with a 2-D register blocking:
+// thread (ri, cj) owns rows 4ri..4ri+3 x columns 8cj..8cj+7 (32 values).  Measured on B200 the earlier
+// one-row-per-thread variants were bound by shared-memory wavefronts (every FMA fetched its pivot-row operand
+// from smem: an LDS.128 always costs 4 wavefronts, broadcast or not); the 4x8 patch needs 12 loaded doubles for
+// 32 FMAs.  Every pivot row is published once into its own shared-memory row (no reuse hazards): one barrier,
+// one reciprocal per pivot; 1/sqrt and write-backs happen after the loop.  CTA 0 also carries an identity block
+// through the same row operations (columns <= c only, complementary to the U part), which yields L^-1 and hence
+// Uinv_J = U_JJ^-1 for the slab TRSM.  Phase 2: 32 threads own one column of [S(J, >J) | nu] each,
+// register-resident forward substitution.  grid (ceil((k + 1 - Jr) / 32), F); dynamic smem kSPanelSmem.
+constexpr int kSPanelSmem = (2 * kNB * kNB + 3 * kNB) * (int)sizeof(double);
+constexpr int kSPanelCols = 32;
+
+__global__ void __launch_bounds__(128) k_schain_panel(DevView v, int J)
+{
+    extern __shared__ __align__(16) double psm[];
+    double* Urows = psm;                   // [64][64] pivot rows (row c valid for j >= c)
+    double* Erows = psm + kNB * kNB;       // [64][64] identity part (CTA 0 only)
+    double* pinvs = Erows + kNB * kNB;
+    double* pivs = pinvs + kNB;
+    double* dinvs = pivs + kNB;
     const int f = blockIdx.y;
     int* dm = fdims(v, f);
     const int k = 2 * dm[D_ULIST];
@@ -442,59 +477,113 @@ __global__ void __launch_bounds__(256) k_schain_panel(DevView v, int J)
     const int kb = min(kNB, k - J0);
     const int Jr = J0 + kb;
     const int tid = threadIdx.x;
+    const bool lead = (blockIdx.x == 0);
     double* Srow = v.S + ((size_t)f * v.kmax + J0) * v.ldS;
     const double* Sd = Srow + J0;
-    double* Ublk = v.Uinv + ((size_t)f * (v.kmax / kNB) + J) * kNB * kNB;
-    for (int e = tid; e < kNB * kNB; e += blockDim.x) Msm[e] = 0.0;
-    if (tid < kNB) ysm[tid] = 0.0;
+    const bool dbgT = (v.dbg != nullptr) && lead && tid == 0 && f == 0 && J == 0;
+    if (dbgT) v.dbg[0] = clock64();
     {
-        const int i = tid >> 2, h = tid & 3;
-        double a[16];
+        const int ri = tid >> 3, cj = tid & 7;
+        const int r0 = 4 * ri, c0 = 8 * cj;
+        double a[4][8], e[4][8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int j = 4 * q + h;
-            double val = 0.0;
-            if (i < kb && j < kb) { if (j >= i) val = Sd[(size_t)i * v.ldS + j]; }
-            else if (i == j) val = 1.0;
-            a[q] = val;
-        }
-        if (i == 0) {
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) rowbuf[0][4 * q + h] = a[q];
+            for (int q = 0; q < 8; ++q) {
+                const int i = r0 + r, j = c0 + q;
+                double val = 0.0;
+                if (i < kb && j < kb) { if (j >= i) val = Sd[(size_t)i * v.ldS + j]; }
+                else if (i == j) val = 1.0;
+                a[r][q] = val;
+                e[r][q] = (i == j) ? 1.0 : 0.0;
+            }
+        if (ri == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                Urows[c0 + q] = a[0][q];
+                if (lead) Erows[c0 + q] = e[0][q];
+            }
         }
+        if (dbgT) v.dbg[1] = clock64();
         for (int c = 0; c < kNB; ++c) {
             __syncthreads();
-            const double* rb = rowbuf[c & 1];
+            const double* rb = Urows + c * kNB;
             const double piv = rb[c];
             const double pinv = __drcp_rn(piv);
-            if (i > c) {
-                const double m = rb[i] * pinv;
-                if (h == 0) Msm[c * kNB + i] = m;
-#pragma unroll
-                for (int q = 0; q < 16; ++q) a[q] -= m * rb[4 * q + h];
-                if (i == c + 1) {
-                    double* nb = rowbuf[(c + 1) & 1];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) nb[4 * q + h] = a[q];
+            if (tid == 0) { pinvs[c] = pinv; pivs[c] = piv; }
+            if (r0 + 3 > c) {
+                double m[4];
+                {
+                    const double2 m01 = *reinterpret_cast<const double2*>(rb + r0);
+                    const double2 m23 = *reinterpret_cast<const double2*>(rb + r0 + 2);
+                    m[0] = (r0 > c) ? m01.x * pinv : 0.0;
+                    m[1] = (r0 + 1 > c) ? m01.y * pinv : 0.0;
+                    m[2] = (r0 + 2 > c) ? m23.x * pinv : 0.0;
+                    m[3] = m23.y * pinv;
                 }
-            }
-            // off the critical path: 1/sqrt(pivot) and the U row for the write-back
-            if (tid < kNB) {
-                const double dinv = rsqrt(piv);
-                if (tid == c) {
-                    if (!(piv > 0.0)) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
-                    dinvs[c] = dinv;
+                if (c0 + 7 >= c) {  // U part: columns >= c matter
+                    double rv[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double2 t2 = *reinterpret_cast<const double2*>(rb + c0 + 2 * q);
+                        rv[2 * q] = t2.x; rv[2 * q + 1] = t2.y;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) a[r][q] -= m[r] * rv[q];
                 }
-                // U_JJ row c goes to the Uinv slot of this block (NOT in place: the other CTAs of this launch
-                // are still reading the original tile); k_invert_diag inverts it there
-                if (blockIdx.x == 0) Ublk[c * kNB + tid] = (tid >= c) ? rb[tid] * dinv : 0.0;
+                if (lead && c0 <= c) {  // identity part: row c is non-zero in columns <= c only
+                    const double* eb = Erows + c * kNB;
+                    double ev[8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double2 t2 = *reinterpret_cast<const double2*>(eb + c0 + 2 * q);
+                        ev[2 * q] = t2.x; ev[2 * q + 1] = t2.y;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) e[r][q] -= m[r] * ev[q];
+                }
+                if (ri == (c + 1) >> 2) {  // this thread row-block holds row c + 1: publish it
+                    const int rr = (c + 1) & 3;
+                    double* nb = Urows + (c + 1) * kNB + c0;
+                    double* ne = Erows + (c + 1) * kNB + c0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (r == rr) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                nb[q] = a[r][q];
+                                if (lead) ne[q] = e[r][q];
+                            }
+                        }
+                }
             }
         }
         __syncthreads();
+        if (dbgT) v.dbg[2] = clock64();
+        if (tid < kNB) {
+            const double piv = pivs[tid];
+            if (!(piv > 0.0)) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
+            dinvs[tid] = rsqrt(piv);
+        }
+        __syncthreads();
+        if (lead) {  // Uinv[s][m] = Linv[m][s] / sqrt(piv_m)  (upper triangular)
+            double* Ublk = v.Uinv + ((size_t)f * (v.kmax / kNB) + J) * kNB * kNB;
+            for (int idx = tid; idx < kNB * kNB; idx += blockDim.x) {
+                const int sI = idx / kNB, m = idx % kNB;
+                Ublk[idx] = (sI <= m) ? Erows[m * kNB + sI] * dinvs[m] : 0.0;
+            }
+        }
     }
-    const int col = Jr + blockIdx.x * blockDim.x + tid;
+    if (dbgT) v.dbg[3] = clock64();
+    if (tid >= kSPanelCols) return;
+    const int col = Jr + blockIdx.x * kSPanelCols + tid;
     if (col > k) return;  // columns Jr .. k (column k = nu)
-    panel_substitute(Srow + col, v.ldS, kb, Msm, dinvs, ysm);
+    schain_substitute(Srow + col, v.ldS, kb, Urows, pinvs, dinvs);
+    if (dbgT) v.dbg[4] = clock64();
 }
 
 // S-chain trailing update, step J (J1 < k):  S[I, c] -= X_J[:, I]^T X_J[:, c] for rows I >= J1 and columns
@@ -562,44 +651,6 @@ __global__ void __launch_bounds__(128) k_schain_trail(DevView v, int J)
                 if (gn <= k) C[(size_t)gm * v.ldS + gn] -= acc[a][b][e];
             }
     }
-}
-
-// Inverse of every 64x64 diagonal block U_JJ (upper triangular; identity padding of a partial last
-// block) into Uinv[f][J][64][64].  4 lanes per column split the dot products.  grid (steps, F), 256 threads.
-constexpr int kInvSmem = 2 * kNB * (kNB + 1) * (int)sizeof(double);
-
-__global__ void __launch_bounds__(256) k_invert_diag(DevView v)
-{
-    extern __shared__ __align__(16) double ism[];
-    double (*U)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(ism);
-    double (*Ui)[kNB + 1] = reinterpret_cast<double (*)[kNB + 1]>(ism + kNB * (kNB + 1));
-    const int f = blockIdx.y, J = blockIdx.x;
-    const int k = 2 * fdims(v, f)[D_ULIST];
-    const int J0 = J * kNB;
-    if (J0 >= k) return;
-    const int kb = min(kNB, k - J0);
-    double* blk = v.Uinv + ((size_t)f * (v.kmax / kNB) + J) * kNB * kNB;  // holds U_JJ (identity padded)
-    (void)kb;
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) {
-        const int i = e / kNB, j = e % kNB;
-        U[i][j] = (j >= i) ? blk[e] : 0.0;
-        Ui[i][j] = 0.0;
-    }
-    __syncthreads();
-    const int t = threadIdx.x >> 2, l = threadIdx.x & 3;  // column t, 4 lanes
-    if (l == 0) Ui[t][t] = 1.0 / U[t][t];
-    __syncwarp();
-    for (int i = kNB - 2; i >= 0; --i) {  // warp-uniform trip count: the shuffles need every lane
-        double s = 0.;
-        if (i < t)
-            for (int qq = i + 1 + l; qq <= t; qq += 4) s += U[i][qq] * Ui[qq][t];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (l == 0 && i < t) Ui[i][t] = -s / U[i][i];
-        __syncwarp();
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < kNB * kNB; e += blockDim.x) blk[e] = Ui[e / kNB][e % kNB];
 }
 
 // W^T = U^-T B on the tensor pipe.  CTA = slab of SW columns of B kept in shared memory (K-major,
@@ -728,6 +779,168 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
 #pragma unroll
         for (int ww = 0; ww < 8; ++ww) s += red[ww * SW + tid];
         v.dx[(size_t)f * v.ld + c0 + tid] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// U3 (+ symmetrise of U4): the covariance downdate  P -= W W^T  on the FP64 tensor pipe, version 2.
+//   * work items are the 128 x 64 tiles of the LOWER triangle only, in a 1-D grid (row block I has 2I+2
+//     column tiles), 4 warps (2 x 2, warp tile 64 x 32 = 8 x 4 DMMA m8n8k4), two CTAs per SM so that the
+//     hardware scheduler balances the 600 tiles of n = 3013 over 296 slots;
+//   * K-major operands through a 3-stage cp.async ring (16 rows per stage), pitch 132 / 68 doubles;
+//   * m- and n-tiles beyond the matrix edge are skipped (the ragged last block row);
+//   * epilogue: lower elements are read-modified-written in place; the mirrored (upper) elements get the
+//     SAME values through a shared-memory transpose so that they are stored as contiguous rows (the direct
+//     scattered mirror store of version 1 cost 4x write amplification) -- P stays exactly symmetric.
+// Algorithmic work per launch: n (n + 1) k flop; minimum traffic 16 n^2 bytes.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDTM = 128, kDTN = 64, kDLA = 132, kDLB = 68, kDTP = 130;
+constexpr int kDownSmemBytes = kStages * kKC * (kDLA + kDLB) * (int)sizeof(double);  // 76.8 KB >= 64 * 130 * 8
+
+template <int PITCH, int WIDTH, int NTHREADS>
+__device__ __forceinline__ void load_slab_w(double* dst, const double* src, int ldsrc, int k0, int K, int col0,
+                                            int colLimit, int tid)
+{
+    constexpr int CPR = WIDTH / 2;  // 16-byte chunks per row
+#pragma unroll
+    for (int it = 0; it < (kKC * CPR) / NTHREADS; ++it) {
+        const int c = tid + it * NTHREADS;
+        const int r = c / CPR, c2 = (c % CPR) * 2;
+        double* d = dst + r * PITCH + c2;
+        if (k0 + r < K && col0 + c2 < colLimit) cp_async16(d, src + (size_t)(k0 + r) * ldsrc + col0 + c2);
+        else { d[0] = 0.0; d[1] = 0.0; }
+    }
+}
+
+__global__ void __launch_bounds__(128, 2) k_downdate(DevView v)
+{
+    extern __shared__ __align__(16) double dsm2[];
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    const int K = 2 * dm[D_ULIST], n = dm[D_N_STATE];
+    if (K == 0) return;
+    // linear tile index -> (row block I, column tile j), j in [0, 2I+1]
+    const int idx = blockIdx.x;
+    int I = (int)((sqrtf(4.0f * idx + 1.0f) - 1.0f) * 0.5f);
+    while (I * (I + 1) > idx) --I;
+    while ((I + 1) * (I + 2) <= idx) ++I;
+    const int j = idx - I * (I + 1);
+    const int tm0 = I * kDTM, tn0 = j * kDTN;
+    if (tm0 >= n || tn0 >= n) return;
+    const bool dbgT = (v.dbg != nullptr) && idx == 40 && f == 0 && threadIdx.x == 0 && K > 128;
+    if (dbgT) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        v.dbg[8] = clock64();
+        v.dbg[9] = (long long)gt;
+    }
+    const double* W = v.Bu + (size_t)f * v.kmax * v.ld;
+    double* P = v.P + (size_t)f * v.nmax * v.ld;
+    const int ld = v.ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int g = lane >> 2, q = lane & 3;
+    // number of valid 8-row / 8-column sub-tiles of this warp (ragged edge)
+    const int aMax = min(8, max(0, (n - (tm0 + wm * 64) + 7) / 8));
+    const int bMax = min(4, max(0, (n - (tn0 + wn * 32) + 7) / 8));
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int nk = (K + kKC - 1) / kKC;
+    auto stA = [&](int st) { return dsm2 + (size_t)st * kKC * (kDLA + kDLB); };
+    auto stB = [&](int st) { return dsm2 + (size_t)st * kKC * (kDLA + kDLB) + kKC * kDLA; };
+#pragma unroll
+    for (int st = 0; st < kStages - 1; ++st) {
+        if (st < nk) {
+            load_slab_w<kDLA, kDTM, 128>(stA(st), W, ld, st * kKC, K, tm0, ld, tid);
+            load_slab_w<kDLB, kDTN, 128>(stB(st), W, ld, st * kKC, K, tn0, ld, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        {
+            const int nx = kt + kStages - 1;
+            if (nx < nk) {
+                load_slab_w<kDLA, kDTM, 128>(stA(nx % kStages), W, ld, nx * kKC, K, tm0, ld, tid);
+                load_slab_w<kDLB, kDTN, 128>(stB(nx % kStages), W, ld, nx * kKC, K, tn0, ld, tid);
+            }
+            cp_async_commit();
+        }
+        const double* As = stA(kt % kStages) + wm * 64 + g;
+        const double* Bs = stB(kt % kStages) + wn * 32 + g;
+#pragma unroll
+        for (int k4 = 0; k4 < kKC; k4 += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) af[a] = As[(k4 + q) * kDLA + a * 8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = Bs[(k4 + q) * kDLB + b * 8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                if (a < aMax) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (b < bMax) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    if (dbgT) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        v.dbg[10] = clock64();
+        v.dbg[11] = (long long)gt;
+        v.dbg[12] = K;
+    }
+    __syncthreads();  // pipeline buffers are free: reuse them as the transpose tile T[n][m], pitch 130
+    double* T = dsm2;
+    const bool needMirror = true;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int ml = wm * 64 + a * 8 + g, gm = tm0 + ml;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int nl = wn * 32 + b * 8 + 2 * q, gn = tn0 + nl;
+            double v0 = 0.0, v1 = 0.0;
+            if (gm < n && gn <= gm) {  // lower (incl. diagonal): read-modify-write in place
+                if (gn + 1 <= gm && gn + 1 < n) {
+                    double2 c2 = *reinterpret_cast<double2*>(P + (size_t)gm * ld + gn);
+                    v0 = c2.x - acc[a][b][0];
+                    v1 = c2.y - acc[a][b][1];
+                    *reinterpret_cast<double2*>(P + (size_t)gm * ld + gn) = make_double2(v0, v1);
+                } else {
+                    v0 = P[(size_t)gm * ld + gn] - acc[a][b][0];
+                    P[(size_t)gm * ld + gn] = v0;
+                }
+            }
+            if (needMirror) {
+                T[(size_t)nl * kDTP + ml] = v0;
+                T[(size_t)(nl + 1) * kDTP + ml] = v1;
+            }
+        }
+    }
+    __syncthreads();
+    // mirrored rows: P[gn][gm] = T[nl][ml] for gm > gn, contiguous in gm
+    for (int nl = warp; nl < kDTN; nl += 4) {
+        const int gn = tn0 + nl;
+        if (gn >= n) break;
+        double* Prow = P + (size_t)gn * ld + tm0;
+        const double* Trow = T + (size_t)nl * kDTP;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int ml = h * 64 + 2 * lane, gm = tm0 + ml;
+            const double2 t2 = *reinterpret_cast<const double2*>(Trow + ml);
+            if (gm > gn && gm + 1 < n) {
+                *reinterpret_cast<double2*>(Prow + ml) = t2;
+            } else {
+                if (gm > gn && gm < n) Prow[ml] = t2.x;
+                if (gm + 1 > gn && gm + 1 < n) Prow[ml + 1] = t2.y;
+            }
+        }
     }
 }
 

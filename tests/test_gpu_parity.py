@@ -112,6 +112,14 @@ def test_generic_factorisation_path():
         phase_by_phase(sc, orc, gpu, t)
 
 
+def test_downdate_variant_128x64():
+    """The alternative downdate kernel (128x64 tiles, transposed mirror store) against the oracle."""
+    sc, orc, gpu = make_pair(640, 480, 100, warm=3)
+    gpu.set_option(2, 1)
+    for t in range(4, 6):
+        phase_by_phase(sc, orc, gpu, t)
+
+
 def test_whole_step_sequence_c2():
     """ekfb_step against orc_step over 40 frames, both free-running from the same initial map."""
     sc, orc, gpu = make_pair(320, 240, 50)

@@ -1,0 +1,17 @@
+import ctypes, sys
+sys.path.insert(0, ".")
+import numpy as np
+from openekfmonoslam_b200.capi import EkfBatch
+from openekfmonoslam_b200.scenario import Scenario
+sc = Scenario(640, 480, 500)
+gpu = EkfBatch(sc.params, 1, 500, 1300)
+x, P, ft, fo, desc, _ = sc.init_map()
+gpu.set_state(0, x, P, ft, fo, desc)
+for t in range(1, 12):
+    kp, ds = sc.frame(t); gpu.set_keypoints(0, kp, ds); gpu.step()
+out = np.zeros(64, np.int64)
+gpu.L.ekfb_debug_read(gpu.h, out.ctypes.data_as(ctypes.c_void_p))
+print("cycles: load %d loop %d post %d phase2 %d total %d" % (out[1]-out[0], out[2]-out[1], out[3]-out[2], out[4]-out[3], out[4]-out[0]))
+dc, dt = out[10] - out[8], out[11] - out[9]
+print("downdate tile 40 main loop: %d cycles, %d ns -> %.0f MHz, K=%d, DMMA-bound cycles %d" % (dc, dt, dc / max(dt, 1) * 1e3, out[12], out[12] // 4 * 128 * 4))
+print(gpu.frame_info(0))
