@@ -449,24 +449,28 @@ __device__ __noinline__ void schain_substitute(double* colp, int ldx, int kb, co
         if (i < kb) colp[(size_t)i * ldx] = x[i] * dinvs[i];
 }
 
-// S-chain panel, step J: 128 threads.  Phase 1 eliminates the diagonal tile with a 2-D register blocking:
-// thread (ri, cj) owns rows 4ri..4ri+3 x columns 8cj..8cj+7 (32 values).  Measured on B200 the earlier
-// one-row-per-thread variants were bound by shared-memory wavefronts (every FMA fetched its pivot-row operand
-// from smem: an LDS.128 always costs 4 wavefronts, broadcast or not); the 4x8 patch needs 12 loaded doubles for
-// 32 FMAs.  Every pivot row is published once into its own shared-memory row (no reuse hazards): one barrier,
-// one reciprocal per pivot; 1/sqrt and write-backs happen after the loop.  CTA 0 also carries an identity block
-// through the same row operations (columns <= c only, complementary to the U part), which yields L^-1 and hence
+// S-chain panel, step J: 128 threads.  Phase 1 eliminates the 64x64 diagonal tile TWO pivots per barrier (the
+// natural 2x2 blocks of the innovation covariance: one feature = two measurement rows).  Thread (ri, cj) owns
+// rows 4ri..4ri+3 x columns 8cj..8cj+7 in registers (2-D blocking: 12 loaded doubles per 32 FMAs -- the
+// one-row-per-thread variants were bound by shared-memory wavefronts).  Per step the two raw pivot rows
+// (eliminated by all earlier pivots, not by each other) are published once into their own shared-memory rows;
+// every thread redoes the 2x2 pivot algebra (two chained reciprocals) and applies a rank-2 update.  Measured on
+// B200 the publish -> barrier -> load round trip costs ~450 cycles, a reciprocal chain ~100: pairing pivots
+// halves the former.  1/sqrt and write-backs happen after the loop.  CTA 0 also carries an identity block through
+// the same row operations (columns <= c only, complementary to the U part), which yields L^-1 and hence
 // Uinv_J = U_JJ^-1 for the slab TRSM.  Phase 2: 32 threads own one column of [S(J, >J) | nu] each,
 // register-resident forward substitution.  grid (ceil((k + 1 - Jr) / 32), F); dynamic smem kSPanelSmem.
-constexpr int kSPanelSmem = (2 * kNB * kNB + 3 * kNB) * (int)sizeof(double);
+constexpr int kSPanelSmem = (4 * kNB * kNB + 3 * kNB) * (int)sizeof(double);
 constexpr int kSPanelCols = 32;
 
 __global__ void __launch_bounds__(128) k_schain_panel(DevView v, int J)
 {
     extern __shared__ __align__(16) double psm[];
-    double* Urows = psm;                   // [64][64] pivot rows (row c valid for j >= c)
-    double* Erows = psm + kNB * kNB;       // [64][64] identity part (CTA 0 only)
-    double* pinvs = Erows + kNB * kNB;
+    double* Rraw = psm;                    // [64][64] published raw pivot rows
+    double* Ufin = psm + kNB * kNB;        // [64][64] final pivot rows (row c valid for j >= c)
+    double* Eraw = Ufin + kNB * kNB;       // identity part, raw / final (CTA 0 only)
+    double* Efin = Eraw + kNB * kNB;
+    double* pinvs = Efin + kNB * kNB;
     double* pivs = pinvs + kNB;
     double* dinvs = pivs + kNB;
     const int f = blockIdx.y;
@@ -500,63 +504,90 @@ __global__ void __launch_bounds__(128) k_schain_panel(DevView v, int J)
         if (ri == 0) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                Urows[c0 + q] = a[0][q];
-                if (lead) Erows[c0 + q] = e[0][q];
+                Rraw[c0 + q] = a[0][q];
+                Rraw[kNB + c0 + q] = a[1][q];
+                if (lead) { Eraw[c0 + q] = e[0][q]; Eraw[kNB + c0 + q] = e[1][q]; }
             }
         }
         if (dbgT) v.dbg[1] = clock64();
-        for (int c = 0; c < kNB; ++c) {
+        for (int c = 0; c < kNB; c += 2) {
             __syncthreads();
-            const double* rb = Urows + c * kNB;
-            const double piv = rb[c];
-            const double pinv = __drcp_rn(piv);
-            if (tid == 0) { pinvs[c] = pinv; pivs[c] = piv; }
-            if (r0 + 3 > c) {
-                double m[4];
+            const double* R0 = Rraw + c * kNB;
+            const double* R1 = R0 + kNB;
+            const double2 d0 = *reinterpret_cast<const double2*>(R0 + c);   // A[c][c], A[c][c+1]
+            const double d11 = R1[c + 1];
+            const double pinv0 = __drcp_rn(d0.x);
+            const double l = d0.y * pinv0;
+            const double piv1 = d11 - l * d0.y;
+            const double pinv1 = __drcp_rn(piv1);
+            if (tid == 0) { pinvs[c] = pinv0; pivs[c] = d0.x; pinvs[c + 1] = pinv1; pivs[c + 1] = piv1; }
+            if (r0 + 3 > c + 1 || ri == 15) {
+                // multipliers of this thread's rows (rows <= c+1 get zero)
+                double m0[4], m1[4];
                 {
-                    const double2 m01 = *reinterpret_cast<const double2*>(rb + r0);
-                    const double2 m23 = *reinterpret_cast<const double2*>(rb + r0 + 2);
-                    m[0] = (r0 > c) ? m01.x * pinv : 0.0;
-                    m[1] = (r0 + 1 > c) ? m01.y * pinv : 0.0;
-                    m[2] = (r0 + 2 > c) ? m23.x * pinv : 0.0;
-                    m[3] = m23.y * pinv;
+                    const double2 g01 = *reinterpret_cast<const double2*>(R0 + r0);
+                    const double2 g23 = *reinterpret_cast<const double2*>(R0 + r0 + 2);
+                    const double2 h01 = *reinterpret_cast<const double2*>(R1 + r0);
+                    const double2 h23 = *reinterpret_cast<const double2*>(R1 + r0 + 2);
+                    m0[0] = g01.x * pinv0; m1[0] = (h01.x - m0[0] * d0.y) * pinv1;
+                    m0[1] = g01.y * pinv0; m1[1] = (h01.y - m0[1] * d0.y) * pinv1;
+                    m0[2] = g23.x * pinv0; m1[2] = (h23.x - m0[2] * d0.y) * pinv1;
+                    m0[3] = g23.y * pinv0; m1[3] = (h23.y - m0[3] * d0.y) * pinv1;
+                    if (!(r0 > c + 1)) { m0[0] = 0.0; m1[0] = 0.0; }
+                    if (!(r0 + 1 > c + 1)) { m0[1] = 0.0; m1[1] = 0.0; }
+                    if (!(r0 + 2 > c + 1)) { m0[2] = 0.0; m1[2] = 0.0; }
+                    if (!(r0 + 3 > c + 1)) { m0[3] = 0.0; m1[3] = 0.0; }
                 }
-                if (c0 + 7 >= c) {  // U part: columns >= c matter
-                    double rv[8];
+                if (c0 + 7 >= c) {  // U part
+                    double u0[8], u1[8];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const double2 t2 = *reinterpret_cast<const double2*>(rb + c0 + 2 * q);
-                        rv[2 * q] = t2.x; rv[2 * q + 1] = t2.y;
+                        const double2 t0 = *reinterpret_cast<const double2*>(R0 + c0 + 2 * q);
+                        const double2 t1 = *reinterpret_cast<const double2*>(R1 + c0 + 2 * q);
+                        u0[2 * q] = t0.x; u0[2 * q + 1] = t0.y;
+                        u1[2 * q] = t1.x - l * t0.x; u1[2 * q + 1] = t1.y - l * t0.y;   // row c+1 eliminated by c
                     }
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) a[r][q] -= m[r] * rv[q];
+                        for (int q = 0; q < 8; ++q) a[r][q] -= m0[r] * u0[q] + m1[r] * u1[q];
+                    if (ri == 15) {  // rows 60..63 are active for every pivot: they record the final pivot rows
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { Ufin[c * kNB + c0 + q] = u0[q]; Ufin[(c + 1) * kNB + c0 + q] = u1[q]; }
+                    }
                 }
-                if (lead && c0 <= c) {  // identity part: row c is non-zero in columns <= c only
-                    const double* eb = Erows + c * kNB;
-                    double ev[8];
+                if (lead && c0 <= c + 1) {  // identity part: rows c, c+1 are non-zero in columns <= c+1 only
+                    const double* E0 = Eraw + c * kNB;
+                    const double* E1 = E0 + kNB;
+                    double v0[8], v1[8];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const double2 t2 = *reinterpret_cast<const double2*>(eb + c0 + 2 * q);
-                        ev[2 * q] = t2.x; ev[2 * q + 1] = t2.y;
+                        const double2 t0 = *reinterpret_cast<const double2*>(E0 + c0 + 2 * q);
+                        const double2 t1 = *reinterpret_cast<const double2*>(E1 + c0 + 2 * q);
+                        v0[2 * q] = t0.x; v0[2 * q + 1] = t0.y;
+                        v1[2 * q] = t1.x - l * t0.x; v1[2 * q + 1] = t1.y - l * t0.y;
                     }
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) e[r][q] -= m[r] * ev[q];
-                }
-                if (ri == (c + 1) >> 2) {  // this thread row-block holds row c + 1: publish it
-                    const int rr = (c + 1) & 3;
-                    double* nb = Urows + (c + 1) * kNB + c0;
-                    double* ne = Erows + (c + 1) * kNB + c0;
+                        for (int q = 0; q < 8; ++q) e[r][q] -= m0[r] * v0[q] + m1[r] * v1[q];
+                    if (ri == 15) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
+                        for (int q = 0; q < 8; ++q) { Efin[c * kNB + c0 + q] = v0[q]; Efin[(c + 1) * kNB + c0 + q] = v1[q]; }
+                    }
+                }
+                if (c + 2 < kNB && ri == (c + 2) >> 2) {  // this row block holds rows c+2, c+3: publish them
+                    const int rr = (c + 2) & 3;           // 0 or 2
+                    double* n0 = Rraw + (c + 2) * kNB + c0;
+                    double* q0 = Eraw + (c + 2) * kNB + c0;
+#pragma unroll
+                    for (int r = 0; r < 4; r += 2)
                         if (r == rr) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                nb[q] = a[r][q];
-                                if (lead) ne[q] = e[r][q];
+                                n0[q] = a[r][q];
+                                n0[kNB + q] = a[r + 1][q];
+                                if (lead) { q0[q] = e[r][q]; q0[kNB + q] = e[r + 1][q]; }
                             }
                         }
                 }
@@ -574,7 +605,7 @@ __global__ void __launch_bounds__(128) k_schain_panel(DevView v, int J)
             double* Ublk = v.Uinv + ((size_t)f * (v.kmax / kNB) + J) * kNB * kNB;
             for (int idx = tid; idx < kNB * kNB; idx += blockDim.x) {
                 const int sI = idx / kNB, m = idx % kNB;
-                Ublk[idx] = (sI <= m) ? Erows[m * kNB + sI] * dinvs[m] : 0.0;
+                Ublk[idx] = (sI <= m) ? Efin[m * kNB + sI] * dinvs[m] : 0.0;
             }
         }
     }
@@ -582,7 +613,7 @@ __global__ void __launch_bounds__(128) k_schain_panel(DevView v, int J)
     if (tid >= kSPanelCols) return;
     const int col = Jr + blockIdx.x * kSPanelCols + tid;
     if (col > k) return;  // columns Jr .. k (column k = nu)
-    schain_substitute(Srow + col, v.ldS, kb, Urows, pinvs, dinvs);
+    schain_substitute(Srow + col, v.ldS, kb, Ufin, pinvs, dinvs);
     if (dbgT) v.dbg[4] = clock64();
 }
 
