@@ -184,7 +184,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     total_filters = wl["filters"] if wl["filters"] > 1 else world   # c4: fixed total; others: one per GPU
-    my_filters = [f for f in range(total_filters) if f % world == rank]
+    from openekfmonoslam_b200.sharding import assign_filters
+    my_filters = assign_filters(total_filters, world, rank)
     F = len(my_filters)
     scenes, N = make_scenarios(wl, my_filters, args.features)
     T0, W_, K = args.filter_warm, args.warmup, args.steps
