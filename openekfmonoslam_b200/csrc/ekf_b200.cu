@@ -47,7 +47,9 @@ struct SeqDev {
 struct ekfb_ctx {
     ekfb_params prm;
     int device = 0, F = 0, Nmax = 0, nmax = 0, ld = 0, Kpmax = 0, kmax = 0, ldS = 0, supWords = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    int smCount = 148;
     DevView v;
     std::vector<void*> allocs;
     std::vector<int> hn, hN, hKp;  // host copies of per-filter sizes
@@ -159,6 +161,10 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     std::memset(c->prof_ms, 0, sizeof(c->prof_ms));
     std::memset(c->prof_launch, 0, sizeof(c->prof_launch));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+    c->smCount = prop.multiProcessorCount;
     for (int i = 0; i < 64; ++i) CK(cudaEventCreate(&c->timers[i]));
     CK(cudaEventCreate(&c->pe[0]));
     CK(cudaEventCreate(&c->pe[1]));
@@ -212,6 +218,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     CK(cudaFuncSetAttribute(k_gemm_tn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_gemm_tn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmemBytes));
+    CK(cudaFuncSetAttribute(k_downdate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
     CK(cudaFuncSetAttribute(k_schain_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, kSTrailSmem));
     CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
     CK(cudaFuncSetAttribute(k_trsm_slab<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -245,6 +252,9 @@ extern "C" int ekfb_destroy(ekfb_handle c)
     cudaEventDestroy(c->pe[0]);
     cudaEventDestroy(c->pe[1]);
     cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
     delete c;
     return EKFB_OK;
 }
@@ -505,6 +515,47 @@ extern "C" int ekfb_ransac(ekfb_handle c)
     return EKFB_OK;
 }
 
+// P -= W W^T for all filters of the handle (W^T = rows of Bu, K = 2 * ulist count per filter)
+static int launch_downdate(ekfb_ctx* c, int n)
+{
+    DevView& v = c->v;
+    const int nI = cdiv(n, kDTM);
+    const bool timeIt = c->dd_timing && c->dd_used + 2 <= c->dd_ev.size();
+    if (timeIt) cudaEventRecord(c->dd_ev[c->dd_used], c->stream);
+    if (c->downdate_variant == 1)
+        k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
+    else {
+        // 1-D grid over the T lower 128x128 tiles.  Single filter: if T is just above a multiple of the SM
+        // count, the remainder would cost a whole extra wave; it runs as 64x64 tiles on a second stream,
+        // co-resident with the big CTAs (register / smem budgets of the two kernels are sized for that).
+        const int T = nI * (nI + 1) / 2;
+        int rem = (c->F == 1 && T > c->smCount) ? T % c->smCount : 0;
+        if (rem > c->smCount / 4) rem = 0;
+        const int nBig = T - rem;
+        if (rem > 0) {
+            CK(cudaEventRecord(c->evFork, c->stream));
+            CK(cudaStreamWaitEvent(c->stream2, c->evFork, 0));
+            k_downdate_small<<<dim3(rem * 4, c->F), 128, kSmallSmemBytes, c->stream2>>>(v, nBig);
+            CK(cudaEventRecord(c->evJoin, c->stream2));
+            count_launch(c);
+        }
+        k_gemm_tn<2><<<dim3(nBig, 1, c->F), 256, kGemmSmemBytes, c->stream>>>(v, nBig);
+        if (rem > 0) CK(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
+    }
+    if (timeIt) {
+        cudaEventRecord(c->dd_ev[c->dd_used + 1], c->stream);
+        c->dd_used += 2;
+        for (int f = 0; f < c->F; ++f) {
+            const double nf = c->hn[f], kf = 2.0 * c->h_dims[(size_t)f * D_STRIDE + D_ULIST];
+            if (kf > 0) {
+                c->dd_flops += nf * (nf + 1.0) * kf;   // symmetric rank-k form
+                c->dd_bytes += 16.0 * nf * nf;         // read + write P once
+            }
+        }
+    }
+    return EKFB_OK;
+}
+
 // update() for the list currently in ulist (host mirror of the counts must be fresh)
 static int run_update(ekfb_ctx* c, int which)
 {
@@ -562,24 +613,8 @@ static int run_update(ekfb_ctx* c, int which)
     }
     {
         GroupScope gs(c, G_DOWNDATE);
-        const int nI = cdiv(n, kDTM);
-        const bool timeIt = c->dd_timing && c->dd_used + 2 <= c->dd_ev.size();
-        if (timeIt) cudaEventRecord(c->dd_ev[c->dd_used], c->stream);
-        if (c->downdate_variant == 1)
-            k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
-        else
-            k_gemm_tn<2><<<dim3(nI, nI, c->F), 256, kGemmSmemBytes, c->stream>>>(v, 0);
-        if (timeIt) {
-            cudaEventRecord(c->dd_ev[c->dd_used + 1], c->stream);
-            c->dd_used += 2;
-            for (int f = 0; f < c->F; ++f) {
-                const double nf = c->hn[f], kf = 2.0 * c->h_dims[(size_t)f * D_STRIDE + D_ULIST];
-                if (kf > 0) {
-                    c->dd_flops += nf * (nf + 1.0) * kf;   // symmetric rank-k form
-                    c->dd_bytes += 16.0 * nf * nf;         // read + write P once
-                }
-            }
-        }
+        int rcD = launch_downdate(c, n);
+        if (rcD != EKFB_OK) return rcD;
         k_quat_cov<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
         count_launch(c, 2);
     }
@@ -738,11 +773,15 @@ extern "C" int ekfb_test_downdate(ekfb_handle c, int n, int k, const double* P_i
     hd[D_N_STATE] = n;
     hd[D_ULIST] = k / 2;
     CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
-    const int nI = cdiv(n, kDTM);
     CK(cudaEventRecord(c->pe[0], c->stream));
-    k_downdate<<<dim3(nI * (nI + 1), 1), 128, kDownSmemBytes, c->stream>>>(v);
+    {
+        const int saveN = c->hn[0];
+        c->hn[0] = n;
+        int rcD = launch_downdate(c, n);
+        c->hn[0] = saveN;
+        if (rcD != EKFB_OK) return rcD;
+    }
     CK(cudaEventRecord(c->pe[1], c->stream));
-    count_launch(c);
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(P_out, sizeof(double) * n, v.P, sizeof(double) * c->ld, sizeof(double) * n, n,
                          cudaMemcpyDeviceToHost, c->stream));

@@ -305,7 +305,7 @@ __device__ __forceinline__ void load_slab(double* dst, const double* src, int ld
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
+__global__ void __maxnreg__(200) k_gemm_tn(DevView v, int J)
 {
     extern __shared__ __align__(16) double gsm[];
     const int f = blockIdx.z;
@@ -339,7 +339,19 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
             nBeg = 0; nEnd = n + 1; tileN = blockIdx.x - nS;
         }
     }
-    const int tm0 = mBeg + blockIdx.y * kTM, tn0 = nBeg + tileN * kTN;
+    int tileM = blockIdx.y;
+    if (KIND == 2) {
+        // 1-D grid over the lower-triangular 128x128 tiles, row block by row block; tiles with index >= J are
+        // left to k_downdate_small (wave-quantisation remainder, see run_update)
+        const int idx = blockIdx.x;
+        if (idx >= J) return;
+        int I = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+        while (I * (I + 1) / 2 > idx) --I;
+        while ((I + 1) * (I + 2) / 2 <= idx) ++I;
+        tileM = I;
+        tileN = idx - I * (I + 1) / 2;
+    }
+    const int tm0 = mBeg + tileM * kTM, tn0 = nBeg + tileN * kTN;
     if (tm0 >= mEnd || tn0 >= nEnd) return;
     if (sPart && tn0 + kTN <= tm0) return;      // S tile strictly below the diagonal
     if (KIND == 2 && tn0 > tm0) return;         // lower tiles only
@@ -413,6 +425,96 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tn(DevView v, int J)
                 }
             }
         }
+    }
+}
+
+// The wave-quantisation remainder of the covariance downdate: when the number T of 128x128 lower tiles is
+// slightly above a multiple of the SM count (n = 3013: T = 300 = 2 * 148 + 4), the last T mod 148 tiles would
+// cost a whole extra wave.  They are cut into 64x64 tiles and run by this small-footprint kernel (<= 112
+// registers, 52 KB smem) on a second stream, co-resident with the big CTAs.  Big tile `idx` -> 4 small tiles.
+constexpr int kSmallSmemBytes = kStages * kKC * (68 + 68) * (int)sizeof(double);
+
+__global__ void __maxnreg__(112) k_downdate_small(DevView v, int firstBig)
+{
+    extern __shared__ __align__(16) double ssm2[];
+    const int f = blockIdx.y;
+    const int* dm = fdims(v, f);
+    const int K = 2 * dm[D_ULIST], n = dm[D_N_STATE];
+    if (K == 0) return;
+    const int idx = firstBig + (blockIdx.x >> 2), sub = blockIdx.x & 3;
+    int I = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+    while (I * (I + 1) / 2 > idx) --I;
+    while ((I + 1) * (I + 2) / 2 <= idx) ++I;
+    const int Jt = idx - I * (I + 1) / 2;
+    const int tm0 = I * kTM + (sub >> 1) * 64, tn0 = Jt * kTN + (sub & 1) * 64;
+    if (tm0 >= n || tn0 >= n || tn0 > tm0) return;
+    const double* W = v.Bu + (size_t)f * v.kmax * v.ld;
+    double* P = v.P + (size_t)f * v.nmax * v.ld;
+    const int ld = v.ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int nk = (K + kKC - 1) / kKC;
+    auto stA = [&](int st) { return ssm2 + (size_t)st * kKC * 136; };
+    auto stB = [&](int st) { return ssm2 + (size_t)st * kKC * 136 + kKC * 68; };
+    auto load = [&](int st, int kc) {
+#pragma unroll
+        for (int it = 0; it < (kKC * 32) / 128; ++it) {
+            const int c = tid + it * 128;
+            const int r = c >> 5, c2 = (c & 31) * 2;
+            const bool rowOk = kc * kKC + r < K;
+            double* da = stA(st) + r * 68 + c2;
+            double* db = stB(st) + r * 68 + c2;
+            if (rowOk && tm0 + c2 < ld) cp_async16(da, W + (size_t)(kc * kKC + r) * ld + tm0 + c2);
+            else { da[0] = 0.0; da[1] = 0.0; }
+            if (rowOk && tn0 + c2 < ld) cp_async16(db, W + (size_t)(kc * kKC + r) * ld + tn0 + c2);
+            else { db[0] = 0.0; db[1] = 0.0; }
+        }
+    };
+#pragma unroll
+    for (int st = 0; st < kStages - 1; ++st) {
+        if (st < nk) load(st, st);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        if (kt + kStages - 1 < nk) load((kt + kStages - 1) % kStages, kt + kStages - 1);
+        cp_async_commit();
+        const double* As = stA(kt % kStages) + wm * 32 + g;
+        const double* Bs = stB(kt % kStages) + wn * 32 + g;
+#pragma unroll
+        for (int k4 = 0; k4 < kKC; k4 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = As[(k4 + q) * 68 + a * 8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = Bs[(k4 + q) * 68 + b * 8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int gm = tm0 + wm * 32 + a * 8 + g;
+        if (gm >= n) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gn = tn0 + wn * 32 + b * 8 + 2 * q + e;
+                if (gn > gm || gn >= n) continue;
+                const double val = P[(size_t)gm * ld + gn] - acc[a][b][e];
+                P[(size_t)gm * ld + gn] = val;
+                if (gn != gm) P[(size_t)gn * ld + gm] = val;
+            }
     }
 }
 

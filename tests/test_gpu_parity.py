@@ -219,14 +219,17 @@ def test_device_resident_sequence_equals_host_fed():
         compare_state(orc, gpu, f"seq frame {t}")
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("n,k", [(313, 2), (313, 100), (613, 40), (1213, 120), (3013, 200)])
-def test_covariance_downdate_kernel(n, k):
-    """P - W W^T on the FP64 tensor pipe vs numpy, sizes of SURVEY 7.1 step 4; exactly symmetric output."""
+def test_covariance_downdate_kernel(n, k, variant):
+    """P - W W^T on the FP64 tensor pipe vs numpy, sizes of SURVEY 7.1 step 4; exactly symmetric output.
+    variant 0 = default (128x128 tiles + co-resident 64x64 remainder kernel at n = 3013), 1 = 128x64 tiles."""
     rng = np.random.default_rng(n + k)
     A = rng.normal(size=(n, 64))
     P = A @ A.T / 64 + np.eye(n)
     Wt = rng.normal(size=(k, n)) * 0.05
     gpu = EkfBatch(Scenario(320, 240, 4).params, 1, (n - 13 + 5) // 6, 64)
+    gpu.set_option(2, variant)
     out = gpu.test_downdate(P, Wt)
     ref = P - Wt.T @ Wt
     assert rel_err(out, ref) < 1e-13
