@@ -217,6 +217,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
 
     CK(cudaFuncSetAttribute(k_gemm_tn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_gemm_tn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(k_gemm_tn<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmemBytes));
     CK(cudaFuncSetAttribute(k_downdate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
     CK(cudaFuncSetAttribute(k_schain_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, kSTrailSmem));
@@ -539,7 +540,10 @@ static int launch_downdate(ekfb_ctx* c, int n)
             CK(cudaEventRecord(c->evJoin, c->stream2));
             count_launch(c);
         }
-        k_gemm_tn<2><<<dim3(nBig, 1, c->F), 256, kGemmSmemBytes, c->stream>>>(v, nBig);
+        if (c->F == 1)
+            k_gemm_tn<2><<<dim3(nBig, 1, c->F), 256, kGemmSmemBytes, c->stream>>>(v, nBig);
+        else
+            k_gemm_tn<3><<<dim3(nBig, 1, c->F), 256, kGemmSmemBytes, c->stream>>>(v, nBig);
         if (rem > 0) CK(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
     }
     if (timeIt) {
@@ -580,7 +584,8 @@ static int run_update(ekfb_ctx* c, int which)
             for (int J = 0; J < steps; ++J) {
                 const int J0 = J * kNB, J1 = J0 + kNB;
                 const int Jr = std::min(J1, k);
-                k_schain_panel<<<dim3(cdiv(k + 1 - Jr, kSPanelCols), c->F), 128, kSPanelSmem, c->stream>>>(v, J);
+                const int pcols = (c->F >= 8) ? 128 : kSPanelCols;
+                k_schain_panel<<<dim3(cdiv(k + 1 - Jr, pcols), c->F), 128, kSPanelSmem, c->stream>>>(v, J, pcols);
                 count_launch(c);
                 if (k > J1) {
                     k_schain_trail<<<dim3(cdiv(k + 1 - J1, 64), cdiv(k - J1, 64), c->F), 128, kSTrailSmem, c->stream>>>(v, J);

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(128) k_chol_panel(DevView v, int J)
 //   KIND 0: trailing update at Cholesky step J of S (A = B = X rows in S, upper tiles only) and of
 //           B (A = X rows in S, B = X rows in B) in one launch: blockIdx.x runs over the virtual
 //           concatenation of S's and B's column tiles
+//   KIND 3: same as KIND 2 without the register cap (batched filters: no co-resident remainder kernel)
 //   KIND 2: covariance downdate P -= W W^T            (A = B = W^T, K = k, lower tiles, mirrored
 //           store so P stays exactly symmetric: replaces 0.5 P + 0.5 P^T of E/Update.cpp:307)
 // CTA tile 128 x 128, 8 warps as 2 (m) x 4 (n), warp tile 64 x 32 = 8 x 4 DMMA m8n8k4 tiles.
@@ -305,7 +306,7 @@ __device__ __forceinline__ void load_slab(double* dst, const double* src, int ld
 }
 
 template <int KIND>
-__global__ void __maxnreg__(200) k_gemm_tn(DevView v, int J)
+__global__ void __maxnreg__(KIND == 2 ? 200 : 255) k_gemm_tn(DevView v, int J)
 {
     extern __shared__ __align__(16) double gsm[];
     const int f = blockIdx.z;
@@ -316,7 +317,7 @@ __global__ void __maxnreg__(200) k_gemm_tn(DevView v, int J)
     int lda, ldb, ldc, mBeg, mEnd, nBeg, nEnd, K, aLim, bLim;
     int tileN = blockIdx.x;
     bool sPart = false;
-    if (KIND == 2) {
+    if ((KIND >= 2)) {
         A = B = v.Bu + (size_t)f * v.kmax * v.ld;
         C = v.P + (size_t)f * v.nmax * v.ld;
         lda = ldb = ldc = v.ld;
@@ -340,7 +341,7 @@ __global__ void __maxnreg__(200) k_gemm_tn(DevView v, int J)
         }
     }
     int tileM = blockIdx.y;
-    if (KIND == 2) {
+    if ((KIND >= 2)) {
         // 1-D grid over the lower-triangular 128x128 tiles, row block by row block; tiles with index >= J are
         // left to k_downdate_small (wave-quantisation remainder, see run_update)
         const int idx = blockIdx.x;
@@ -354,7 +355,7 @@ __global__ void __maxnreg__(200) k_gemm_tn(DevView v, int J)
     const int tm0 = mBeg + tileM * kTM, tn0 = nBeg + tileN * kTN;
     if (tm0 >= mEnd || tn0 >= nEnd) return;
     if (sPart && tn0 + kTN <= tm0) return;      // S tile strictly below the diagonal
-    if (KIND == 2 && tn0 > tm0) return;         // lower tiles only
+    if ((KIND >= 2) && tn0 > tm0) return;         // lower tiles only
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
@@ -415,7 +416,7 @@ __global__ void __maxnreg__(200) k_gemm_tn(DevView v, int J)
             for (int e = 0; e < 2; ++e) {
                 const int g = gn + e;
                 if (g >= nEnd) continue;
-                if (KIND == 2) {
+                if ((KIND >= 2)) {
                     if (g > gm) continue;
                     const double val = C[(size_t)gm * ldc + g] - acc[a][b][e];
                     C[(size_t)gm * ldc + g] = val;
@@ -565,7 +566,7 @@ __device__ __noinline__ void schain_substitute(double* colp, int ldx, int kb, co
 constexpr int kSPanelSmem = (4 * kNB * kNB + 3 * kNB) * (int)sizeof(double);
 constexpr int kSPanelCols = 32;
 
-__global__ void __launch_bounds__(128) k_schain_panel(DevView v, int J)
+__global__ void __launch_bounds__(128) k_schain_panel(DevView v, int J, int colsPerCta)
 {
     extern __shared__ __align__(16) double psm[];
     double* Rraw = psm;                    // [64][64] published raw pivot rows
@@ -712,8 +713,10 @@ __global__ void __launch_bounds__(128) k_schain_panel(DevView v, int J)
         }
     }
     if (dbgT) v.dbg[3] = clock64();
-    if (tid >= kSPanelCols) return;
-    const int col = Jr + blockIdx.x * kSPanelCols + tid;
+    // colsPerCta = 32 for a single filter (latency: spread the columns over many SMs), 128 for batched filters
+    // (throughput: fewer redundant eliminations of the diagonal tile)
+    if (tid >= colsPerCta) return;
+    const int col = Jr + blockIdx.x * colsPerCta + tid;
     if (col > k) return;  // columns Jr .. k (column k = nu)
     schain_substitute(Srow + col, v.ldS, kb, Ufin, pinvs, dinvs);
     if (dbgT) v.dbg[4] = clock64();
