@@ -101,13 +101,21 @@ def make_scenarios(wl, my_filters, features):
 
 
 def cpu_oracle_sample(wl, N, budget_s=25.0, max_frames=20):
-    """Times the CPU oracle (the reference's literal algorithm, 1 thread) on the first frames of the same
-    workload until ~budget_s of CPU time is spent; returns frames/s and the sample description."""
-    from oracle.oracle_lib import OracleFilter
+    """Times the reference's CPU path (1 thread -- the reference is single-threaded) on the first frames of the same
+    workload until ~budget_s of CPU time is spent; returns frames/s and the sample description.
+    kind "reference": oracle/_ref/libref.so, the reference's own sources (EKF::step and everything below it)
+    compiled against oracle/cvshim -- used when it was built (needs /root/reference at build time; the .so travels to
+    the GPU box).  kind "port": the oracle restatement otherwise."""
     from openekfmonoslam_b200.scenario import Scenario
+    from oracle import ref_lib
     sc = Scenario(wl["W"], wl["H"], N)
     x, P, ft, fo, desc, _ = sc.init_map()
-    f = OracleFilter(sc.params)
+    use_ref = ref_lib.available(build=False)
+    if use_ref:
+        f = ref_lib.ReferenceFilter(sc.params)
+    else:
+        from oracle.oracle_lib import OracleFilter
+        f = OracleFilter(sc.params)
     f.set_state(x, P, ft, fo, desc)
     frames, spent, phases = 0, 0.0, {}
     while frames < max_frames and (frames == 0 or spent < budget_s):
@@ -116,13 +124,17 @@ def cpu_oracle_sample(wl, N, budget_s=25.0, max_frames=20):
         info = f.step(kp, ds)
         spent += time.perf_counter() - t0
         frames += 1
-        for k, v in info.items():
+        for k, v in (info or {}).items():
             if k.startswith("us_"):
                 phases[k[3:]] = phases.get(k[3:], 0.0) + v
-    return dict(value=frames / spent, unit=UNIT, cores=1, kind="port",
-                sample=f"oracle (literal reference algorithm, g++ -O2, 1 thread) on frames 1..{frames} of the workload "
-                       f"({spent:.1f} s CPU); k differs slightly from the steady-state frames timed on the GPU",
-                us_per_phase={k: v / frames for k, v in phases.items()})
+    what = ("reference sources (EKF::step) compiled against oracle/cvshim, g++ -O2" if use_ref
+            else "oracle (literal restatement of the reference algorithm, g++ -O2)")
+    out = dict(value=frames / spent, unit=UNIT, cores=1, kind="reference" if use_ref else "port",
+               sample=f"{what}, 1 thread, frames 1..{frames} of the workload ({spent:.1f} s CPU); "
+                      f"k differs slightly from the steady-state frames timed on the GPU")
+    if phases:
+        out["us_per_phase"] = {k: v / frames for k, v in phases.items()}
+    return out
 
 
 def measure_fp64_peak(device):
@@ -143,8 +155,8 @@ def measure_fp64_peak(device):
 
 
 def run_reference(args, wl, rank, world):
-    """--impl reference: the reference's CPU path (oracle port; the reference itself needs OpenCV 2.4.3 C++
-    and cannot be built here) on this workload; rank 0 only."""
+    """--impl reference: the reference's CPU path on this workload, rank 0 only: oracle/_ref/libref.so (the reference's
+    own sources compiled against oracle/cvshim) when it was built, else the oracle port."""
     if rank != 0:
         return
     N = args.features or wl["N"]

@@ -18,6 +18,10 @@
  * cv::ellipse filled (ellipse2Poly on the 1-degree float sine table + FillConvexPoly with its
  * fixed-point edge walk and Line2 outline).  These are pinned against cv2 4.13 fixtures in
  * tests/golden/ (tests/test_oracle_golden.py).
+ *
+ * PARITY STATUS: pinned.  tests/test_reference_pin.py compares every phase, the add-feature path and whole
+ * EKF::step frames of this restatement with oracle/_ref/libref.so, the reference's own sources compiled
+ * unmodified against oracle/cvshim (oracle/ref/Makefile): discrete results identical, FP64 to <= 1e-12.
  */
 #include "ekf_oracle.h"
 
@@ -1867,6 +1871,10 @@ void orc_get_mask(const orc_filter* f, uint8_t* mask, uint8_t* kpok)
 }
 
 void orc_eigen2x2(const double* A, double* ev, double* V) { eigen2x2(A, ev, V); }
+void orc_gemm_acc(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int K, int N)
+{
+    gemmAcc(A, lda, B, ldb, C, ldc, M, K, N);
+}
 int orc_invert(const double* A, int32_t n, double* out) { return invertLU(A, n, out) ? 1 : 0; }
 void orc_ellipse_params(const double* S, double* o)
 {

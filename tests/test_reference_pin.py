@@ -1,0 +1,126 @@
+"""Pins the oracle against the REFERENCE's own code: oracle/_ref/libref.so is built from the unmodified sources
+under /root/reference (kalmanFilter/modules/{Core,1PointRansacEKF,Gui}) against oracle/cvshim (oracle/ref/Makefile).
+Every phase of EKF::step, the add-feature path and whole frames through the reference's own EKF::step must agree
+with the oracle: sets exactly, floating point to 1e-12 (both are CPU FP64; only summation order differs).
+Skipped when the reference tree (and a prebuilt libref.so) is not available."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from openekfmonoslam_b200.scenario import Scenario
+from oracle import ref_lib
+from oracle.oracle_lib import OracleFilter
+
+pytestmark = pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref/libref.so not built (needs /root/reference)")
+TOL = 1e-12
+
+
+def pair(N, W=320, H=240, seed_offset=0):
+    sc = Scenario(W, H, N, seed_offset=seed_offset)
+    x, P, ft, fo, desc, uv0 = sc.init_map()
+    o = OracleFilter(sc.params)
+    r = ref_lib.ReferenceFilter(sc.params)
+    o.set_state(x, P, ft, fo, desc)
+    r.set_state(x, P, ft, fo, desc)
+    return sc, o, r, (x, P, ft, fo, desc, uv0)
+
+
+def same_state(o, r, what, tol=TOL):
+    xo, Po = o.get_state()
+    xr, Pr = r.get_state()
+    assert rel_err(xo, xr) < tol and rel_err(Po, Pr) < tol, what
+
+
+def phase_by_phase(sc, o, r, t, tol=TOL):
+    kp, ds = sc.frame(t)
+    o.predict(); r.predict()
+    same_state(o, r, f"predict {t}", tol)
+    o.measure(); r.measure()
+    mo, mr = o.get_measure(), r.get_measure()
+    assert np.array_equal(mo["vis"], mr["vis"])
+    v = mo["vis"].astype(bool)
+    assert np.abs(mo["h"][v] - mr["h"][v]).max() < 1e-10
+    for k in ("S", "Hx", "Hf"):
+        assert rel_err(mo[k][v], mr[k][v]) < tol, k
+    o.match(kp, ds); r.match(kp, ds)
+    ao, ar = o.get_match(), r.get_match()
+    assert np.array_equal(ao["matched"], ar["matched"])
+    m = ao["matched"].astype(bool)
+    assert np.array_equal(ao["z"][m], ar["z"][m]) and np.array_equal(ao["dist"][m], ar["dist"][m])
+    o.ransac(); r.ransac()
+    so, sr = o.get_ransac(), r.get_sets()
+    assert np.array_equal(so["inlier"], sr["inlier"]) and np.array_equal(so["outlier"], sr["outlier"])
+    o.update_li(); r.update_li()
+    same_state(o, r, f"update LI {t}", tol)
+    o.rescue(); r.rescue()
+    assert np.array_equal(o.get_rescue(), r.get_sets()["rescued"])
+    o.update_hi(); r.update_hi()
+    same_state(o, r, f"update HI {t}", tol)
+    o.update_map_features(); r.update_map_features()
+    fo_, fr_ = o.get_features(), r.get_features()
+    assert np.array_equal(fo_["desc"], fr_["desc"]) and np.array_equal(fo_["times_predicted"], fr_["times_predicted"])
+    assert np.array_equal(fo_["times_matched"], fr_["times_matched"])
+
+
+def test_add_feature_path():
+    sc, o, r, (x, P, ft, fo, desc, uv0) = pair(10)
+    o.init(); r.init()
+    for i in range(10):
+        o.add_feature(uv0[i], desc[i]); r.add_feature(uv0[i], desc[i])
+    same_state(o, r, "add feature")
+    r.close()
+
+
+def test_every_phase_inverse_depth():
+    sc, o, r, _ = pair(40)
+    for t in range(1, 11):
+        phase_by_phase(sc, o, r, t)
+    r.close()
+
+
+def test_whole_frames_through_the_references_own_step():
+    """EKF::step (the reference's orchestrator, EKF.cpp:242-666) vs orc_step, 25 free-running frames."""
+    sc, o, r, _ = pair(30, seed_offset=2)
+    for t in range(1, 26):
+        kp, ds = sc.frame(t)
+        o.step(kp, ds); r.step(kp, ds)
+        same_state(o, r, f"frame {t}")
+        fo_, fr_ = o.get_features(), r.get_features()
+        assert np.array_equal(fo_["desc"], fr_["desc"]) and np.array_equal(fo_["times_matched"], fr_["times_matched"])
+    r.close()
+
+
+def test_every_phase_mixed_xyz_features():
+    sc, o, r, (x, P, ft, fo, desc, _) = pair(18)
+    for t in range(1, 4):
+        o.step(*sc.frame(t))
+    x, P = o.get_state()
+    xs, types, offs, blocks, n_new = [x[:13]], [], [], [], 13
+    for j in range(sc.N):
+        oj = 13 + 6 * j
+        y = x[oj:oj + 6]
+        if j % 2 == 0:
+            th, ph, rho = y[3], y[4], y[5]
+            m = np.array([np.cos(ph) * np.sin(th), -np.sin(ph), np.cos(ph) * np.cos(th)])
+            dth = np.array([np.cos(ph) * np.cos(th), 0.0, -np.cos(ph) * np.sin(th)])
+            dph = np.array([-np.sin(ph) * np.sin(th), -np.cos(ph), -np.sin(ph) * np.cos(th)])
+            J = np.hstack([np.eye(3), (dth / rho)[:, None], (dph / rho)[:, None], (-m / rho ** 2)[:, None]])
+            xs.append(y[:3] + m / rho); blocks.append((oj, J)); types.append(1); offs.append(n_new); n_new += 3
+        else:
+            xs.append(y); blocks.append((oj, np.eye(6))); types.append(2); offs.append(n_new); n_new += 6
+    T = np.zeros((n_new, x.shape[0]))
+    T[:13, :13] = np.eye(13)
+    for (oj, J), off in zip(blocks, offs):
+        T[off:off + J.shape[0], oj:oj + 6] = J
+    P2 = T @ P @ T.T
+    P2 = 0.5 * (P2 + P2.T)
+    x2 = np.concatenate(xs)
+    types = np.array(types, np.int32); offs = np.array(offs, np.int32)
+    d = o.get_features()["desc"]
+    o.set_state(x2, P2, types, offs, d)
+    r.set_state(x2, P2, types, offs, d)
+    # the hand-converted XYZ covariance has a wide dynamic range (1/rho^2 factors): S_i = H P H^T cancels, so the two
+    # CPU summation orders differ at ~1e-11; everything discrete must still be identical
+    for t in range(4, 9):
+        phase_by_phase(sc, o, r, t, tol=1e-9)
+    r.close()
