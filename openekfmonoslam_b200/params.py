@@ -99,3 +99,31 @@ def load_config(path):
         "descriptor_extractor": run.get("DescriptorExtractor"),
     }
     return p, extras
+
+
+_CAM_KEYS = (("PixelsX", "pixels_x"), ("PixelsY", "pixels_y"), ("FX", "fx"), ("FY", "fy"), ("K1", "k1"), ("K2", "k2"),
+             ("CX", "cx"), ("CY", "cy"), ("DX", "dx"), ("DY", "dy"), ("PixelErrorX", "pixel_error_x"),
+             ("PixelErrorY", "pixel_error_y"), ("AngularVisionX", "angular_vision_x"), ("AngularVisionY", "angular_vision_y"))
+_EKF_KEYS = (("InitInvDepthRho", "init_inv_depth_rho"), ("InitLinearAccelSD", "init_linear_accel_sd"),
+             ("InitAngularAccelSD", "init_angular_accel_sd"), ("LinearAccelSD", "linear_accel_sd"),
+             ("AngularAccelSD", "angular_accel_sd"), ("InverseDepthRhoSD", "inverse_depth_rho_sd"),
+             ("MatchingCompCoefSecondBestVSFirst", "matching_coef"), ("RansacThresholdPredictDistance", "ransac_threshold"),
+             ("RansacAllInliersProbability", "ransac_all_inliers_prob"), ("RansacChi2Threshold", "ransac_chi2"))
+
+
+def write_config(path, p, min_matches_per_image, max_map_size=0):
+    """Write params in the reference's config.yml layout (samples/EKF/config.yml): a RunConfiguration block naming one
+    entry per section, every value a quoted string."""
+    lines = ["%YAML:1.0", "", "RunConfiguration:", '  ExtendedKalmanFilter: "EKF"', '  FeatureDetector: "STAR"',
+             '  DescriptorExtractor: "BRIEF"', '  CameraCalibration: "CAM"', "", "ExtendedKalmanFilter:", "  EKF:"]
+    for key, attr in _EKF_KEYS:
+        lines.append(f'    {key}: "{getattr(p, attr)!r}"')
+    lines.append(f'    MinMatchesPerImage: "{int(min_matches_per_image)}"')
+    if max_map_size:
+        lines.append(f'    MaxMapSize: "{int(max_map_size)}"')
+    lines += ["FeatureDetector:", "  STAR:", '    Type: "STAR"', "DescriptorExtractor:", "  BRIEF:", '    Type: "BRIEF"',
+              "CameraCalibration:", "  CAM:"]
+    for key, attr in _CAM_KEYS:
+        lines.append(f'    {key}: "{getattr(p, attr)!r}"')
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
