@@ -138,6 +138,11 @@ int ekfb_get_mask(ekfb_handle h, int filter, uint8_t* mask, uint8_t* kp_ok);
 /* ---- isolated kernels for the stress sweep (BASELINE.json config 5) and for tests ---------------- */
 /* Covariance downdate alone on filter 0: P <- P - W W^T with W^T given as k x n row-major (host). */
 int ekfb_test_downdate(ekfb_handle h, int n, int k, const double* P_in, const double* Wt, double* P_out);
+/* Test hook for the factorisation of the innovation covariance alone (U2, Update.cpp:92-99 forms S and inverts it): S_in is
+ * k x (k+1) row-major, [S | nu] with S symmetric positive definite.  U_out (k x (k+1)) receives the upper Cholesky factor
+ * (S = U^T U; entries below the diagonal are not written) and, in column k, y = U^-T nu.  Uinv_out receives the inverses of
+ * the ceil(k/64) diagonal 64x64 blocks of U (row-major, identity-padded). */
+int ekfb_test_factor(ekfb_handle h, int k, const double* S_in, double* U_out, double* Uinv_out);
 /* Full gain + update on filter 0 from caller Jacobians: for a = 0..m-1 feature index feat[a] with
  * z (2m), using the handle's current state / P / last ekfb_measure.  Returns timings in ms. */
 int ekfb_time_update(ekfb_handle h, int which, int reps, float* ms_total, float* ms_downdate);
@@ -153,7 +158,8 @@ int ekfb_profile_read(ekfb_handle h, float* ms9, int32_t* launches9);
 int64_t ekfb_kernel_launches(ekfb_handle h);     /* kernels launched by this handle so far */
 /* tuning / test switches.  EKFB_OPT_FORCE_GENERIC_FACTOR = 1 forces the right-looking factorisation over
  * the whole augmented matrix (the path used when k is too large for the shared-memory slab TRSM). */
-enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* 0: 128x128 tiles (default), 1: 128x64 tiles, 2 CTAs/SM */ };
+enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* 0: 128x128 tiles (default), 1: 128x64 tiles, 2 CTAs/SM */,
+       EKFB_OPT_SCHAIN_VARIANT = 3 /* factorisation of S: 0 = one fused launch per 64-row step (default), 1 = panel + trail launches */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

@@ -191,6 +191,14 @@ class EkfBatch:
                                            _ptr(out)))
         return out
 
+    def test_factor(self, S_aug):
+        """[S | nu] (k x (k+1)) -> (U with y in column k, inverses of the diagonal 64x64 blocks)"""
+        S_aug = np.ascontiguousarray(S_aug, np.float64)
+        k = S_aug.shape[0]
+        U = np.zeros_like(S_aug); Ui = np.zeros(((k + 63) // 64, 64, 64))
+        self._ck(self.L.ekfb_test_factor(self.h, ctypes.c_int(k), _ptr(S_aug), _ptr(U), _ptr(Ui)))
+        return U, Ui
+
     def time_update(self, which, reps):
         a, b = ctypes.c_float(), ctypes.c_float()
         self._ck(self.L.ekfb_time_update(self.h, ctypes.c_int(which), ctypes.c_int(reps), ctypes.byref(a), ctypes.byref(b)))

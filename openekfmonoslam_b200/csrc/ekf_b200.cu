@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "ekf_linalg.cuh"
+#include "ekf_schain.cuh"
 
 using namespace ekf;
 
@@ -77,6 +78,7 @@ struct ekfb_ctx {
     size_t flush_bytes = 0;
     bool force_generic = false;
     int downdate_variant = 0;
+    int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches
     bool dd_timing = false;
     std::vector<cudaEvent_t> dd_ev;   // pairs
     size_t dd_used = 0;               // events used
@@ -193,7 +195,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     ALLOC(v.inl, F * N); ALLOC(v.outl, F * N); ALLOC(v.resc, F * N); ALLOC(v.ulist, F * N);
     ALLOC(v.kpok, F * c->Kpmax); ALLOC(v.mask, F * (size_t)v.W * v.H);
     ALLOC(v.hypcount, F * N); ALLOC(v.hypsup, F * N * c->supWords);
-    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.dx, F * c->ld); ALLOC(v.dbg, 64); ALLOC(v.Uinv, F * (c->kmax / kNB) * kNB * kNB); ALLOC(v.Jq, F * 16);
+    ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.Sf, F * c->kmax * c->ldS); ALLOC(v.dx, F * c->ld); ALLOC(v.dbg, 64); ALLOC(v.Uinv, F * (c->kmax / kNB) * kNB * kNB); ALLOC(v.Jq, F * 16);
     ALLOC(c->d_kpxy, F * c->Kpmax * 2); ALLOC(c->d_kpdesc, F * c->Kpmax * 32);
     ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F);
     ALLOC(c->d_rec, F);
@@ -222,6 +224,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     CK(cudaFuncSetAttribute(k_downdate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
     CK(cudaFuncSetAttribute(k_schain_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, kSTrailSmem));
     CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
+    CK(cudaFuncSetAttribute(k_schain_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem));
     CK(cudaFuncSetAttribute(k_trsm_slab<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_ransac_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -560,6 +563,37 @@ static int launch_downdate(ekfb_ctx* c, int n)
     return EKFB_OK;
 }
 
+// Cholesky of [S | nu] for all filters of the handle (k = the largest 2 * ulist count): factor rows into Sf, inverses of
+// the diagonal blocks into Uinv
+static int launch_schain(ekfb_ctx* c, int k)
+{
+    DevView& v = c->v;
+    const int steps = cdiv(k, kNB);
+    if (c->schain_variant == 1) {
+        for (int J = 0; J < steps; ++J) {
+            const int J0 = J * kNB, J1 = J0 + kNB;
+            const int Jr = std::min(J1, k);
+            const int pcols = (c->F >= 8) ? 128 : kSPanelCols;
+            k_schain_panel<<<dim3(cdiv(k + 1 - Jr, pcols), c->F), 128, kSPanelSmem, c->stream>>>(v, J, pcols);
+            count_launch(c);
+            if (k > J1) {
+                k_schain_trail<<<dim3(cdiv(k + 1 - J1, 64), cdiv(k - J1, 64), c->F), 128, kSTrailSmem, c->stream>>>(v, J);
+                count_launch(c);
+            }
+        }
+        CK(cudaMemcpyAsync(v.Sf, v.S, sizeof(double) * (size_t)c->F * c->kmax * c->ldS, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        // one launch per block step; step J needs a launch while a tile row J+1 (or the lone nu column tile) exists
+        const int nbR = steps, nbC = (k + kNB) / kNB;
+        for (int J = -1; J + 1 < nbC && J + 1 <= nbR; ++J) {
+            if (J + 1 == nbR && nbC == nbR) break;
+            k_schain_step<<<dim3(J < 0 ? 1 : nbC - (J + 1), J < 0 ? 1 : std::max(nbR - (J + 1), 1), c->F), 128, kStepSmem, c->stream>>>(v, J);
+            count_launch(c);
+        }
+    }
+    return EKFB_OK;
+}
+
 // update() for the list currently in ulist (host mirror of the counts must be fresh)
 static int run_update(ekfb_ctx* c, int which)
 {
@@ -581,17 +615,7 @@ static int run_update(ekfb_ctx* c, int which)
         const size_t smemMax = 227 * 1024;
         if (smem16 <= smemMax && !c->force_generic) {
             // fast path: S-only chain, diagonal-block inverses, slab TRSM
-            for (int J = 0; J < steps; ++J) {
-                const int J0 = J * kNB, J1 = J0 + kNB;
-                const int Jr = std::min(J1, k);
-                const int pcols = (c->F >= 8) ? 128 : kSPanelCols;
-                k_schain_panel<<<dim3(cdiv(k + 1 - Jr, pcols), c->F), 128, kSPanelSmem, c->stream>>>(v, J, pcols);
-                count_launch(c);
-                if (k > J1) {
-                    k_schain_trail<<<dim3(cdiv(k + 1 - J1, 64), cdiv(k - J1, 64), c->F), 128, kSTrailSmem, c->stream>>>(v, J);
-                    count_launch(c);
-                }
-            }
+            { int rcC = launch_schain(c, k); if (rcC != EKFB_OK) return rcC; }
             if (smem24 <= smemMax)
                 k_trsm_slab<24><<<dim3(cdiv(n, 24), c->F), 256, smem24, c->stream>>>(v);
             else
@@ -799,6 +823,37 @@ extern "C" int ekfb_test_downdate(ekfb_handle c, int n, int k, const double* P_i
     return EKFB_OK;
 }
 
+extern "C" int ekfb_test_factor(ekfb_handle c, int k, const double* S_in, double* U_out, double* Uinv_out)
+{
+    REQUIRE(c && S_in && U_out && Uinv_out, "null argument");
+    REQUIRE(k > 0 && k <= c->kmax && (k % 2) == 0, "k out of range (k must be even)");
+    CK(cudaSetDevice(c->device));
+    DevView& v = c->v;
+    const int nb = cdiv(k, kNB);
+    CK(cudaMemcpy2DAsync(v.S, sizeof(double) * c->ldS, S_in, sizeof(double) * (k + 1), sizeof(double) * (k + 1), k,
+                         cudaMemcpyHostToDevice, c->stream));
+    int* hd = c->h_dims;
+    const int save_u = hd[D_ULIST];
+    hd[D_ULIST] = k / 2;
+    hd[D_STATUS] = 0;
+    CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_schain(c, k);
+    if (rc != EKFB_OK) return rc;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(U_out, sizeof(double) * (k + 1), v.Sf, sizeof(double) * c->ldS, sizeof(double) * (k + 1), k,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(Uinv_out, v.Uinv, sizeof(double) * (size_t)nb * kNB * kNB, cudaMemcpyDeviceToHost, c->stream));
+    int status = 0;
+    CK(cudaMemcpyAsync(&status, v.dims + D_STATUS, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    hd[D_ULIST] = save_u;
+    hd[D_STATUS] = 0;
+    CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    REQUIRE(status == 0, "innovation covariance is not positive definite");
+    return EKFB_OK;
+}
+
 extern "C" int ekfb_time_update(ekfb_handle c, int which, int reps, float* ms_total, float* ms_downdate)
 {
     REQUIRE(c && reps > 0, "bad argument");
@@ -869,8 +924,10 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option == EKFB_OPT_FORCE_GENERIC_FACTOR || option == EKFB_OPT_DOWNDATE_VARIANT, "unknown option");
+    REQUIRE(option == EKFB_OPT_FORCE_GENERIC_FACTOR || option == EKFB_OPT_DOWNDATE_VARIANT || option == EKFB_OPT_SCHAIN_VARIANT,
+            "unknown option");
     if (option == EKFB_OPT_FORCE_GENERIC_FACTOR) c->force_generic = value != 0;
+    else if (option == EKFB_OPT_SCHAIN_VARIANT) c->schain_variant = value;
     else c->downdate_variant = value;
     return EKFB_OK;
 }

@@ -38,7 +38,7 @@ struct DevView {
     uint8_t* inl; uint8_t* outl; uint8_t* resc; int* ulist;
     const float* const* kpxy; const uint8_t* const* kpdesc; uint8_t* kpok; uint8_t* mask;
     int* hypcount; uint32_t* hypsup;
-    double* Bu; double* S; double* dx; double* Jq; double* Uinv; long long* dbg;
+    double* Bu; double* S; double* Sf; double* dx; double* Jq; double* Uinv; long long* dbg;
 };
 
 __device__ __forceinline__ int* fdims(const DevView& v, int f) { return v.dims + (size_t)f * D_STRIDE; }

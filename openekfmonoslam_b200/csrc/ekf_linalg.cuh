@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     double* Bg = v.Bu + (size_t)f * v.kmax * v.ld;
-    const double* Sg = v.S + (size_t)f * v.kmax * v.ldS;
+    const double* Sg = v.Sf + (size_t)f * v.kmax * v.ldS;   // the factor buffer of the S-chain
     const double* Uinv = v.Uinv + (size_t)f * (v.kmax / kNB) * kNB * kNB;
 
     for (int e = tid; e < kpad * SW; e += blockDim.x) {

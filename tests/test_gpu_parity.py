@@ -236,6 +236,46 @@ def test_covariance_downdate_kernel(n, k, variant):
     assert np.array_equal(out, out.T)
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("k", [2, 8, 62, 64, 66, 126, 128, 130, 200, 384, 600, 640])
+def test_innovation_covariance_factorisation(k, variant):
+    """The S-chain alone: S = U^T U, y = U^-T nu and the inverses of the diagonal 64x64 blocks, against numpy.  k covers
+    a single ragged block, exact multiples of 64 (nu alone in the last column tile) and the C3 size.  variant 0 = one
+    fused launch per block step (default), 1 = the panel + trail launch pairs."""
+    rng = np.random.default_rng(1000 + k)
+    A = rng.normal(size=(k, k + 8))
+    S = A @ A.T / k + 0.5 * np.eye(k)
+    d = np.exp(rng.uniform(-2, 2, size=k))          # rows of very different scale, as pixel / depth innovations have
+    S = d[:, None] * S * d[None, :]
+    nu = rng.normal(size=k) * d
+    gpu = EkfBatch(Scenario(320, 240, 4).params, 1, max(k // 2, 4), 64)
+    gpu.set_option(3, variant)
+    U, Ui = gpu.test_factor(np.hstack([S, nu[:, None]]))
+    L = np.linalg.cholesky(S)
+    Uu, Lt = np.triu(U[:, :k]), L.T.copy()
+    if variant == 1:  # the launch-pair variant keeps U_JJ only as its inverse
+        for J in range((k + 63) // 64):
+            Uu[64 * J:64 * J + 64, 64 * J:64 * J + 64] = 0.0
+            Lt[64 * J:64 * J + 64, 64 * J:64 * J + 64] = 0.0
+    if k > 64 or variant == 0:
+        assert rel_err(Uu, Lt) < 1e-12
+    y = np.linalg.solve(L, nu)
+    assert rel_err(U[:, k], y) < 1e-11
+    for J in range((k + 63) // 64):
+        kb = min(64, k - 64 * J)
+        blk = L.T[64 * J:64 * J + kb, 64 * J:64 * J + kb]
+        assert rel_err(Ui[J, :kb, :kb], np.linalg.inv(blk)) < 1e-11, J
+        assert np.array_equal(np.tril(Ui[J, :kb, :kb], -1), np.zeros((kb, kb)))
+
+
+def test_legacy_schain_variant_whole_update():
+    """The panel + trail launch pairs (option 3 = 1) through the whole update, against the oracle."""
+    sc, orc, gpu = make_pair(640, 480, 100, warm=3)
+    gpu.set_option(3, 1)
+    for t in range(4, 6):
+        phase_by_phase(sc, orc, gpu, t)
+
+
 def test_full_size_properties_c3():
     """BASELINE config 3 size (N = 500, n = 3013): the oracle's literal update is too slow to run per
     test, so check size-independent properties of one full GPU frame: P stays exactly symmetric and
