@@ -587,7 +587,7 @@ static int launch_schain(ekfb_ctx* c, int k)
         const int nbR = steps, nbC = (k + kNB) / kNB;
         for (int J = -1; J + 1 < nbC && J + 1 <= nbR; ++J) {
             if (J + 1 == nbR && nbC == nbR) break;
-            k_schain_step<<<dim3(J < 0 ? 1 : nbC - (J + 1), J < 0 ? 1 : std::max(nbR - (J + 1), 1), c->F), 128, kStepSmem, c->stream>>>(v, J);
+            k_schain_step<<<dim3(J < 0 ? 1 : nbC - (J + 1), J < 0 ? 1 : std::max(nbR - (J + 1), 1), c->F), 256, kStepSmem, c->stream>>>(v, J);
             count_launch(c);
         }
     }

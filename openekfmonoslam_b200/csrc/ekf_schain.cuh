@@ -27,59 +27,124 @@ __device__ __forceinline__ double rsqrt_fast(double d)
     return fma(y * e, fma(0.375, e, 0.5), y);     // y (1 + e/2 + 3 e^2 / 8): third-order, ~1 ulp from a 2^-20 seed
 }
 
-// acc[a][b][:] += sum_s A[s][wm*32 + a*8 + ..] * B[s][wn*32 + b*8 + ..]   (A, B: [64][kSS], K-major).  TRI: A is upper
-// triangular (A[s][m] = 0 for s > m), the k-steps that only meet zeros are skipped.
-template <bool TRI>
-__device__ __forceinline__ void tile_gemm64(const double* __restrict__ A, const double* __restrict__ B, int wm, int wn, int g, int q,
-                                            double (&acc)[4][4][2])
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem)
 {
-    const int kEnd = TRI ? wm * 32 + 32 : kNB;
-#pragma unroll 2
-    for (int k4 = 0; k4 < kEnd; k4 += 4) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) af[a] = A[(k4 + q) * kSS + wm * 32 + a * 8 + g];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) bf[b] = B[(k4 + q) * kSS + wn * 32 + b * 8 + g];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            if (TRI && k4 >= wm * 32 + a * 8 + 8) continue;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-        }
-    }
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
 }
+__device__ __forceinline__ void bar_factor() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// 64 x 64 tile of a row-major matrix into shared memory; rows >= rowLimit and columns >= colLimit become zero
+// 64 x 64 tile of a row-major matrix into shared memory (256 threads); rows >= rowLimit and columns >= colLimit become zero
 __device__ __forceinline__ void load_tile64(double* dst, const double* src, int ld, int row0, int rowLimit, int col0, int colLimit, int tid)
 {
-    for (int e = tid; e < kNB * 32; e += 128) {
+#pragma unroll 4
+    for (int e = tid; e < kNB * 32; e += 256) {
         const int r = e >> 5, c2 = (e & 31) * 2;
         double* d = dst + r * kSS + c2;
         const double* s = src + (size_t)(row0 + r) * ld + col0 + c2;
-        if (row0 + r < rowLimit && col0 + c2 + 1 < colLimit) cp_async16(d, s);
-        else {
-            d[0] = (row0 + r < rowLimit && col0 + c2 < colLimit) ? s[0] : 0.0;
-            d[1] = 0.0;
+        const bool rowOk = row0 + r < rowLimit;
+        if (rowOk && col0 + c2 + 1 < colLimit) cp_async16(d, s);
+        else if (rowOk && col0 + c2 < colLimit) { cp_async8(d, s); d[1] = 0.0; }
+        else { d[0] = 0.0; d[1] = 0.0; }
+    }
+}
+
+// X = A^T Sx with A upper triangular (A[s][m] = 0 for s > m), for one or two right-hand tiles that share the A fragments.
+// Warp (p, nh): m-tile rows {p, 7-p} (together 9 k-blocks: balanced), n-tiles 4nh .. 4nh+3.
+template <bool TWO>
+__device__ __forceinline__ void x_gemm(const double* __restrict__ A, const double* __restrict__ S0, const double* __restrict__ S1, int p,
+                                       int nh, int g, int q, double (&x0)[2][4][2], double (&x1)[2][4][2])
+{
+    const int m0 = 8 * p, m1 = 8 * (7 - p), n0 = 32 * nh;
+    int k4 = 0;
+#pragma unroll 2
+    for (; k4 < m0 + 8; k4 += 4) {
+        const double* Ar = A + (k4 + q) * kSS;
+        const double a0 = Ar[m0 + g], a1 = Ar[m1 + g];
+        double b0[4], b1[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            b0[b] = S0[(k4 + q) * kSS + n0 + 8 * b + g];
+            if (TWO) b1[b] = S1[(k4 + q) * kSS + n0 + 8 * b + g];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            dmma8x8x4(x0[0][b][0], x0[0][b][1], a0, b0[b]);
+            dmma8x8x4(x0[1][b][0], x0[1][b][1], a1, b0[b]);
+            if (TWO) {
+                dmma8x8x4(x1[0][b][0], x1[0][b][1], a0, b1[b]);
+                dmma8x8x4(x1[1][b][0], x1[1][b][1], a1, b1[b]);
+            }
+        }
+    }
+#pragma unroll 2
+    for (; k4 < m1 + 8; k4 += 4) {
+        const double a1 = A[(k4 + q) * kSS + m1 + g];
+        double b0[4], b1[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            b0[b] = S0[(k4 + q) * kSS + n0 + 8 * b + g];
+            if (TWO) b1[b] = S1[(k4 + q) * kSS + n0 + 8 * b + g];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            dmma8x8x4(x0[1][b][0], x0[1][b][1], a1, b0[b]);
+            if (TWO) dmma8x8x4(x1[1][b][0], x1[1][b][1], a1, b1[b]);
         }
     }
 }
 
-// In-place factorisation of the SPD tile T (upper triangle read, [64][kSS], valid kb x kb, the rest is replaced by identity):
-// on return T holds U (upper, T = U^T U) and W holds U^-1 (upper, zeros below).  128 threads.  *bad is set if a pivot of the
-// valid part is not positive.
-__device__ void factor_tile64(double* T, double* W, int kb, int tid, int* bad)
+// the 36 upper 8x8 tiles of a 64x64 tile, row-major
+__constant__ unsigned char kUpperTile[36][2] = {
+    {0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {0, 7}, {1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {1, 7}, {2, 2}, {2, 3}, {2, 4},
+    {2, 5}, {2, 6}, {2, 7}, {3, 3}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {4, 4}, {4, 5}, {4, 6}, {4, 7}, {5, 5}, {5, 6}, {5, 7}, {6, 6}, {6, 7}, {7, 7}};
+
+// Left-looking tile updates of factor_tile64 before block step b >= 1, one 8x8 tile per warp:
+//   warps 0 .. 7-b : T(b, c) -= sum_{k < 8b} U[k][8b + .]^T U[k][8c + .],  c = b + w   (block row b brought up to date)
+//   warps 8-b .. 7 : G(a, b)  = sum_{8a <= k < 8b} W[8a + .][k] U[k][8b + .], a = w - (8 - b)  (column block b of U^-1)
+// Two accumulator pairs break the DMMA dependency chain.
+__device__ __forceinline__ void leftlook_tile(double* T, double* W, int b, int w, int g, int q)
 {
-    for (int e = tid; e < kNB * kNB; e += 128) {
-        const int i = e >> 6, j = e & 63;
-        if (i >= kb || j >= kb) T[i * kSS + j] = (i == j) ? 1.0 : 0.0;
-        W[i * kSS + j] = 0.0;
+    const bool inv = w >= 8 - b;
+    const int a8 = inv ? w - (8 - b) : 0, c8 = inv ? b : b + w;
+    const int k0 = inv ? 8 * a8 : 0, k1 = 8 * b;
+    // a-fragment A[k][m]: T[k][8b + m] (trailing) or W[8a + m][k] (inverse); b-fragment B[k][n] = T[k][8 c8 + n]
+    const double* ap = inv ? W + (8 * a8 + g) * kSS + q : T + q * kSS + 8 * b + g;
+    const int astep = inv ? 1 : kSS;
+    const double* bp = T + q * kSS + 8 * c8 + g;
+    double2* dst = reinterpret_cast<double2*>((inv ? W + (8 * a8 + g) * kSS : T + (8 * b + g) * kSS) + 8 * c8 + 2 * q);
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    for (int k = k0; k < k1; k += 8) {
+        const double aa0 = ap[k * astep], aa1 = ap[(k + 4) * astep];
+        const double bb0 = bp[k * kSS], bb1 = bp[(k + 4) * kSS];
+        dmma8x8x4(c0, c1, aa0, bb0);
+        dmma8x8x4(d0, d1, aa1, bb1);
     }
-    __syncthreads();
+    double2 v0 = *dst;
+    if (inv) { v0.x += c0 + d0; v0.y += c1 + d1; }
+    else { v0.x -= c0 + d0; v0.y -= c1 + d1; }
+    *dst = v0;
+}
+
+// In-place factorisation of the SPD tile T (upper triangle read, [64][kSS]; the caller has replaced everything outside the
+// valid part by identity and zeroed W): on return T holds U (upper, T = U^T U) and W holds U^-1 (upper, zeros below).
+// Called by all 256 threads: warps 0-3 do the in-register work, warps 4-7 only join the rank-8 tile updates.  *bad is set if a
+// pivot is not positive.
+__device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int* bad, long long* dbg)
+{
+    long long tA = 0, tB = 0, tC = 0, t0 = 0;
+    const int lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
     for (int b = 0; b < 8; ++b) {
         const int o = 8 * b;
-        // ---- every thread: Cholesky of the 8x8 diagonal block, R upper, r = 1 / diag(R)
+        if (dbg) t0 = clock64();
+        if (b > 0) {
+            leftlook_tile(T, W, b, w, g, q);
+            __syncthreads();
+        }
+        if (dbg) { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
         double R[8][8], r[8];
+        if (w < 4) {
+        // ---- every thread of warps 0-3: Cholesky of the 8x8 diagonal block, R upper, r = 1 / diag(R)
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -96,7 +161,8 @@ __device__ void factor_tile64(double* T, double* W, int kb, int tid, int* bad)
 #pragma unroll
                 for (int c = i; c < 8; ++c) R[i][c] -= R[j][i] * R[j][c];
         }
-        if (tid == 0 && neg && o < kb) *bad = 1;   // padded rows are identity, so any bad pivot is a real one
+        if (tid == 0 && neg) *bad = 1;
+        if (dbg) { const long long t1 = clock64(); tA += t1 - t0; t0 = t1; }
         // ---- per-thread substitutions against R
         const int ncol = kNB - o - 8;
         if (tid < ncol) {  // block row: column j of U(b, >b) = R^-T t
@@ -128,83 +194,21 @@ __device__ void factor_tile64(double* T, double* W, int kb, int tid, int* bad)
 #pragma unroll
             for (int j = 0; j < 8; ++j) wr[j] = x[j];
         }
+        }
         __syncthreads();
+        if (dbg) { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
         if (tid == 56 + (b & 1)) {  // the diagonal block of U (after the barrier: the other warps read it during their Cholesky)
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = i; j < 8; ++j) T[(o + i) * kSS + o + j] = R[i][j];
         }
-        // ---- rank-8 updates as 4x4 register blocks: trailing tile (upper blocks only) and the running inverse
-        const int nb4 = ncol / 4;
-        const int nTrail = nb4 * (nb4 + 1) / 2;
-        const int nGc = nb4, nG = 2 * (b + 1) * nGc;
-        const double* Ub = T + o * kSS;  // the finished block row: Ub[s][col]
-        for (int it = tid; it < nTrail + nG; it += 128) {
-            double acc[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-            if (it < nTrail) {
-                int br = 0, t = it;
-                while (t >= nb4 - br) { t -= nb4 - br; ++br; }
-                const int r0 = o + 8 + 4 * br, c0 = o + 8 + 4 * (br + t);
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(Ub + s * kSS + r0);
-                    const double2 a23 = *reinterpret_cast<const double2*>(Ub + s * kSS + r0 + 2);
-                    const double2 b01 = *reinterpret_cast<const double2*>(Ub + s * kSS + c0);
-                    const double2 b23 = *reinterpret_cast<const double2*>(Ub + s * kSS + c0 + 2);
-                    const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    double2* p0 = reinterpret_cast<double2*>(T + (r0 + i) * kSS + c0);
-                    double2 v0 = p0[0], v1 = p0[1];
-                    v0.x -= acc[i][0]; v0.y -= acc[i][1]; v1.x -= acc[i][2]; v1.y -= acc[i][3];
-                    p0[0] = v0; p0[1] = v1;
-                }
-            } else {
-                const int t = it - nTrail;
-                const int r0 = 4 * (t / nGc), c0 = o + 8 + 4 * (t % nGc);
-                double av[4][8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int s2 = 0; s2 < 4; ++s2) {
-                        const double2 w = *reinterpret_cast<const double2*>(W + (r0 + i) * kSS + o + 2 * s2);
-                        av[i][2 * s2] = w.x; av[i][2 * s2 + 1] = w.y;
-                    }
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const double2 b01 = *reinterpret_cast<const double2*>(Ub + s * kSS + c0);
-                    const double2 b23 = *reinterpret_cast<const double2*>(Ub + s * kSS + c0 + 2);
-                    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] += av[i][s] * bv[j];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    double2* p0 = reinterpret_cast<double2*>(W + (r0 + i) * kSS + c0);
-                    double2 v0 = p0[0], v1 = p0[1];
-                    v0.x += acc[i][0]; v0.y += acc[i][1]; v1.x += acc[i][2]; v1.y += acc[i][3];
-                    p0[0] = v0; p0[1] = v1;
-                }
-            }
-        }
-        __syncthreads();
     }
+    if (dbg) { dbg[0] = tA; dbg[1] = tB; dbg[2] = tC; }
 }
 
-// grid (nbC - (J+1), nbR - J, F), 128 threads, dynamic smem kStepSmem.  J = -1 only factors tile (0, 0).
-__global__ void __launch_bounds__(128, 1) k_schain_step(DevView v, int J)
+// grid (nbC - (J+1), max(nbR - (J+1), 1), F), 256 threads, dynamic smem kStepSmem.  J = -1 only factors tile (0, 0).
+__global__ void __launch_bounds__(256, 1) k_schain_step(DevView v, int J)
 {
     extern __shared__ __align__(16) double csm[];
     double* Ws = csm;                  // Uinv_J, later the inverse of the new diagonal block
@@ -222,17 +226,20 @@ __global__ void __launch_bounds__(128, 1) k_schain_step(DevView v, int J)
     if (J < 0 && C != 0) return;       // the first launch only factors tile (0, 0)
     const bool phantom = (I == nbR);   // no rows left: only the X_C of a column tile that holds just nu is produced
     if (phantom && blockIdx.y != 0) return;
-    const bool diag = (I == C) && !phantom;     // X_C is X_I
+    const bool diag = (I == C) && !phantom;     // X_C is X_I, only the upper 8x8 tiles of the update are needed
     const bool fac = diag && blockIdx.y == 0;  // tile (J+1, J+1): factored here
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int g = lane >> 2, q = lane & 3, wm = w >> 1, wn = w & 1;
+    const int g = lane >> 2, q = lane & 3, p = w & 3, nh = w >> 2;
     const int J0 = J * kNB, I0 = I * kNB, C0 = C * kNB;
     double* Sg = v.S + (size_t)f * v.kmax * v.ldS;
     double* Sf = v.Sf + (size_t)f * v.kmax * v.ldS;
     double* UinvG = v.Uinv + (size_t)f * (v.kmax / kNB) * kNB * kNB;
 
+    long long* dbg = (v.dbg != nullptr && fac && f == 0 && tid == 0 && J == 1) ? v.dbg + (k > 300 ? 16 : 40) : nullptr;
+    if (dbg) dbg[0] = clock64();
     if (J >= 0) {
-        for (int e = tid; e < kNB * 32; e += 128) {
+#pragma unroll 4
+        for (int e = tid; e < kNB * 32; e += 256) {
             const int r = e >> 5, c2 = (e & 31) * 2;
             cp_async16(Ws + r * kSS + c2, UinvG + (size_t)J * kNB * kNB + r * kNB + c2);
         }
@@ -243,21 +250,24 @@ __global__ void __launch_bounds__(128, 1) k_schain_step(DevView v, int J)
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    if (dbg) dbg[1] = clock64();
 
     if (J >= 0) {
-        double xa[4][4][2], xb[4][4][2];
+        // ---- X_I (-> As) and X_C (-> Bs), both = Uinv_J^T (raw block row J)
+        double xa[2][4][2], xb[2][4][2];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) xa[a][b][0] = xa[a][b][1] = xb[a][b][0] = xb[a][b][1] = 0.0;
-        if (!phantom) tile_gemm64<true>(Ws, As, wm, wn, g, q, xa);
-        if (!diag) tile_gemm64<true>(Ws, Bs, wm, wn, g, q, xb);
+        if (phantom) x_gemm<false>(Ws, Bs, Bs, p, nh, g, q, xb, xb);
+        else if (diag) x_gemm<false>(Ws, As, As, p, nh, g, q, xa, xa);
+        else x_gemm<true>(Ws, As, Bs, p, nh, g, q, xa, xb);
         __syncthreads();
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const int m = wm * 32 + a * 8 + g, nn = wn * 32 + b * 8 + 2 * q;
+                const int m = (a == 0 ? 8 * p : 8 * (7 - p)) + g, nn = 32 * nh + 8 * b + 2 * q;
                 if (!phantom) *reinterpret_cast<double2*>(As + m * kSS + nn) = make_double2(xa[a][b][0], xa[a][b][1]);
                 if (!diag) *reinterpret_cast<double2*>(Bs + m * kSS + nn) = make_double2(xb[a][b][0], xb[a][b][1]);
                 if (blockIdx.y == 0) {  // row I == J+1 publishes U(J, C)
@@ -269,48 +279,117 @@ __global__ void __launch_bounds__(128, 1) k_schain_step(DevView v, int J)
             }
         if (phantom) return;
         __syncthreads();
-        double acc[4][4][2];
+        if (dbg) dbg[2] = clock64();
+        // ---- S(I, C) -= X_I^T X_C
+        if (!diag) {
+            double acc[2][4][2];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-        tile_gemm64<false>(As, diag ? As : Bs, wm, wn, g, q, acc);
+                for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+            const int m0 = 16 * p, n0 = 32 * nh;
+#pragma unroll 2
+            for (int k4 = 0; k4 < kNB; k4 += 4) {
+                double af[2], bf[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 2; ++a) af[a] = As[(k4 + q) * kSS + m0 + 8 * a + g];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int m = wm * 32 + a * 8 + g, nn = wn * 32 + b * 8 + 2 * q;
-                double2 t = *reinterpret_cast<double2*>(Ts + m * kSS + nn);
-                t.x -= acc[a][b][0]; t.y -= acc[a][b][1];
-                if (fac) *reinterpret_cast<double2*>(Ts + m * kSS + nn) = t;
-                else if (I0 + m < k) {
+                for (int b = 0; b < 4; ++b) bf[b] = Bs[(k4 + q) * kSS + n0 + 8 * b + g];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int m = m0 + 8 * a + g;
+                if (I0 + m >= k) continue;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int nn = n0 + 8 * b + 2 * q;
+                    double2 t = *reinterpret_cast<double2*>(Ts + m * kSS + nn);
+                    t.x -= acc[a][b][0]; t.y -= acc[a][b][1];
                     double* dst = Sg + (size_t)(I0 + m) * v.ldS + C0 + nn;
                     if (C0 + nn + 1 <= k) *reinterpret_cast<double2*>(dst) = t;
                     else if (C0 + nn <= k) dst[0] = t.x;
                 }
             }
+            return;
+        }
+        {
+            double acc[5][2];
+            int mi[5], ni[5];
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                const int id = min(w + 8 * t, 35);
+                mi[t] = 8 * kUpperTile[id][0]; ni[t] = 8 * kUpperTile[id][1];
+                acc[t][0] = acc[t][1] = 0.0;
+            }
+            const bool five = (w + 32 < 36);
+#pragma unroll 2
+            for (int k4 = 0; k4 < kNB; k4 += 4) {
+                const double* Ar = As + (k4 + q) * kSS + g;
+                double af[5], bf[5];
+#pragma unroll
+                for (int t = 0; t < 5; ++t) { af[t] = Ar[mi[t]]; bf[t] = Ar[ni[t]]; }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) dmma8x8x4(acc[t][0], acc[t][1], af[t], bf[t]);
+                if (five) dmma8x8x4(acc[4][0], acc[4][1], af[4], bf[4]);
+            }
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                if (t == 4 && !five) break;
+                const int m = mi[t] + g, nn = ni[t] + 2 * q;
+                double2 tv = *reinterpret_cast<double2*>(Ts + m * kSS + nn);
+                tv.x -= acc[t][0]; tv.y -= acc[t][1];
+                if (fac) *reinterpret_cast<double2*>(Ts + m * kSS + nn) = tv;
+                else if (I0 + m < k) {
+                    double* dst = Sg + (size_t)(I0 + m) * v.ldS + C0 + nn;
+                    if (C0 + nn + 1 <= k) *reinterpret_cast<double2*>(dst) = tv;
+                    else if (C0 + nn <= k) dst[0] = tv.x;
+                }
+            }
+        }
         if (!fac) return;
         __syncthreads();
+        if (dbg) dbg[3] = clock64();
     }
     // ---- diagonal tile: factor, publish U_II, Uinv_I and (if nu lies in this tile) y_I
     const int kb = min(kNB, k - I0);
     const bool hasNu = (k - I0) < kNB;
     if (hasNu && tid < kNB) nu[tid] = (tid < kb) ? Ts[tid * kSS + kb] : 0.0;
-    __syncthreads();
     __shared__ int bad;
     if (tid == 0) bad = 0;
-    factor_tile64(Ts, Ws, kb, tid, &bad);
+    __syncthreads();
+    for (int e = tid; e < kNB * 32; e += 256) {  // identity outside the valid part; W starts at zero
+        const int i = e >> 5, j = (e & 31) * 2;
+        if (i >= kb || j + 1 >= kb) {
+            if (i >= kb || j >= kb) Ts[i * kSS + j] = (i == j) ? 1.0 : 0.0;
+            Ts[i * kSS + j + 1] = (i == j + 1) ? 1.0 : 0.0;
+        }
+        *reinterpret_cast<double2*>(Ws + i * kSS + j) = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (dbg) dbg[6] = clock64();
+    factor_tile64(Ts, Ws, tid, &bad, dbg ? dbg + 8 : nullptr);
+    __syncthreads();
+    if (dbg) dbg[4] = clock64();
     if (tid == 0 && bad) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
-    for (int e = tid; e < kNB * kNB; e += 128) {
-        const int i = e >> 6, j = e & 63;
-        UinvG[(size_t)I * kNB * kNB + e] = Ws[i * kSS + j];
-        if (i < kb && j < kb) Sf[(size_t)(I0 + i) * v.ldS + I0 + j] = (j >= i) ? Ts[i * kSS + j] : 0.0;
+    for (int e = tid; e < kNB * 32; e += 256) {
+        const int i = e >> 5, j = (e & 31) * 2;
+        *reinterpret_cast<double2*>(UinvG + (size_t)I * kNB * kNB + i * kNB + j) = *reinterpret_cast<const double2*>(Ws + i * kSS + j);
+        if (i < kb && j + 1 >= i) {
+            double* dst = Sf + (size_t)(I0 + i) * v.ldS + I0 + j;
+            if (j >= i && j < kb) dst[0] = Ts[i * kSS + j];
+            if (j + 1 < kb) dst[1] = Ts[i * kSS + j + 1];
+        }
     }
     if (hasNu && tid < kb) {
         double s = 0.0;
-        for (int p = 0; p <= tid; ++p) s += Ws[p * kSS + tid] * nu[p];
+        for (int pp = 0; pp <= tid; ++pp) s += Ws[pp * kSS + tid] * nu[pp];
         Sf[(size_t)(I0 + tid) * v.ldS + k] = s;
     }
+    if (dbg) dbg[5] = clock64();
 }
 
 }  // namespace ekf
