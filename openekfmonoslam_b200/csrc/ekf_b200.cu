@@ -563,6 +563,19 @@ static int launch_downdate(ekfb_ctx* c, int n)
     return EKFB_OK;
 }
 
+// launch with the programmatic-stream-serialization attribute (see grid_dependency_wait in ekf_linalg.cuh)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // Cholesky of [S | nu] for all filters of the handle (k = the largest 2 * ulist count): factor rows into Sf, inverses of
 // the diagonal blocks into Uinv
 static int launch_schain(ekfb_ctx* c, int k)
@@ -587,7 +600,8 @@ static int launch_schain(ekfb_ctx* c, int k)
         const int nbR = steps, nbC = (k + kNB) / kNB;
         for (int J = -1; J + 1 < nbC && J + 1 <= nbR; ++J) {
             if (J + 1 == nbR && nbC == nbR) break;
-            k_schain_step<<<dim3(J < 0 ? 1 : nbC - (J + 1), J < 0 ? 1 : std::max(nbR - (J + 1), 1), c->F), 256, kStepSmem, c->stream>>>(v, J);
+            CK(launch_pdl(k_schain_step, dim3(J < 0 ? 1 : nbC - (J + 1), J < 0 ? 1 : std::max(nbR - (J + 1), 1), c->F), dim3(256),
+                          (size_t)kStepSmem, c->stream, v, J));
             count_launch(c);
         }
     }
@@ -617,9 +631,9 @@ static int run_update(ekfb_ctx* c, int which)
             // fast path: S-only chain, diagonal-block inverses, slab TRSM
             { int rcC = launch_schain(c, k); if (rcC != EKFB_OK) return rcC; }
             if (smem24 <= smemMax)
-                k_trsm_slab<24><<<dim3(cdiv(n, 24), c->F), 256, smem24, c->stream>>>(v);
+                CK(launch_pdl(k_trsm_slab<24>, dim3(cdiv(n, 24), c->F), dim3(256), smem24, c->stream, v));
             else
-                k_trsm_slab<16><<<dim3(cdiv(n, 16), c->F), 256, smem16, c->stream>>>(v);
+                CK(launch_pdl(k_trsm_slab<16>, dim3(cdiv(n, 16), c->F), dim3(256), smem16, c->stream, v));
             count_launch(c);
         } else {
             // generic path (very large k): right-looking over the whole augmented matrix

@@ -278,6 +278,12 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still running; it must not touch the predecessor's output before
+// grid_dependency_wait().  grid_launch_dependents() lets the successor be scheduled early.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -832,6 +838,9 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
         const int r = e / SW, c = e % SW;
         Xs[(size_t)r * SWP + c] = (r < k && c0 + c < n) ? Bg[(size_t)r * v.ld + c0 + c] : 0.0;
     }
+    // The slab of B does not depend on the S-chain: with programmatic dependent launch this CTA was scheduled while the last
+    // chain step was still running; from here on the factor is read.
+    grid_dependency_wait();
     // chunk stream: for block J: J0/32 chunks of U, then 2 chunks of Uinv_J
     auto issue = [&](int J, int ch, int stage) {
         const int J0 = J * kNB, nU = J0 / 32;

@@ -99,31 +99,49 @@ __constant__ unsigned char kUpperTile[36][2] = {
     {0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {0, 6}, {0, 7}, {1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {1, 7}, {2, 2}, {2, 3}, {2, 4},
     {2, 5}, {2, 6}, {2, 7}, {3, 3}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {4, 4}, {4, 5}, {4, 6}, {4, 7}, {5, 5}, {5, 6}, {5, 7}, {6, 6}, {6, 7}, {7, 7}};
 
-// Left-looking tile updates of factor_tile64 before block step b >= 1, one 8x8 tile per warp:
-//   warps 0 .. 7-b : T(b, c) -= sum_{k < 8b} U[k][8b + .]^T U[k][8c + .],  c = b + w   (block row b brought up to date)
-//   warps 8-b .. 7 : G(a, b)  = sum_{8a <= k < 8b} W[8a + .][k] U[k][8b + .], a = w - (8 - b)  (column block b of U^-1)
-// Two accumulator pairs break the DMMA dependency chain.
-__device__ __forceinline__ void leftlook_tile(double* T, double* W, int b, int w, int g, int q)
+// Left-looking tile updates of factor_tile64.  Before block step s >= 1 can start, eight 8x8 tiles must be brought up to date,
+// one per warp (i = warp index):
+//   i < 8-s : T(s, c) -= sum_{k < 8s} U[k][8s + .]^T U[k][8c + .],  c = s + i          (block row s of the tile)
+//   else    : G(a, s)  = sum_{8a <= k < 8s} W[8a + .][k] U[k][8s + .], a = i - (8 - s)  (column block s of U^-1)
+// (Accumulating the k < 8(s-1) part ahead of time on warps 4-7, while warps 0-3 run the in-register Cholesky, was measured:
+// the DMMAs share the FP64 pipe with the Cholesky's dependent DFMA chain and slow it by as much as they save.)
+struct LLTile {
+    const double* ap;   // a-fragment A[k][m]: T[k][8s + m] (stride kSS in k) or W[8a + m][k] (stride 1)
+    const double* bp;   // b-fragment B[k][n] = T[k][8c + n]
+    double2* dst;
+    int astep, k0;
+    bool inv;
+};
+
+__device__ __forceinline__ LLTile ll_tile(double* T, double* W, int s, int i, int g, int q)
 {
-    const bool inv = w >= 8 - b;
-    const int a8 = inv ? w - (8 - b) : 0, c8 = inv ? b : b + w;
-    const int k0 = inv ? 8 * a8 : 0, k1 = 8 * b;
-    // a-fragment A[k][m]: T[k][8b + m] (trailing) or W[8a + m][k] (inverse); b-fragment B[k][n] = T[k][8 c8 + n]
-    const double* ap = inv ? W + (8 * a8 + g) * kSS + q : T + q * kSS + 8 * b + g;
-    const int astep = inv ? 1 : kSS;
-    const double* bp = T + q * kSS + 8 * c8 + g;
-    double2* dst = reinterpret_cast<double2*>((inv ? W + (8 * a8 + g) * kSS : T + (8 * b + g) * kSS) + 8 * c8 + 2 * q);
-    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-    for (int k = k0; k < k1; k += 8) {
-        const double aa0 = ap[k * astep], aa1 = ap[(k + 4) * astep];
-        const double bb0 = bp[k * kSS], bb1 = bp[(k + 4) * kSS];
-        dmma8x8x4(c0, c1, aa0, bb0);
-        dmma8x8x4(d0, d1, aa1, bb1);
+    LLTile t;
+    t.inv = i >= 8 - s;
+    const int a8 = t.inv ? i - (8 - s) : 0, c8 = t.inv ? s : s + i;
+    t.k0 = t.inv ? 8 * a8 : 0;
+    t.ap = t.inv ? W + (8 * a8 + g) * kSS + q : T + q * kSS + 8 * s + g;
+    t.astep = t.inv ? 1 : kSS;
+    t.bp = T + q * kSS + 8 * c8 + g;
+    t.dst = reinterpret_cast<double2*>((t.inv ? W + (8 * a8 + g) * kSS : T + (8 * s + g) * kSS) + 8 * c8 + 2 * q);
+    return t;
+}
+
+__device__ __forceinline__ void ll_accumulate(const LLTile& t, int kBegin, int kEnd, double (&c)[4])
+{
+    for (int k = kBegin; k < kEnd; k += 8) {
+        const double aa0 = t.ap[k * t.astep], aa1 = t.ap[(k + 4) * t.astep];
+        const double bb0 = t.bp[k * kSS], bb1 = t.bp[(k + 4) * kSS];
+        dmma8x8x4(c[0], c[1], aa0, bb0);
+        dmma8x8x4(c[2], c[3], aa1, bb1);
     }
-    double2 v0 = *dst;
-    if (inv) { v0.x += c0 + d0; v0.y += c1 + d1; }
-    else { v0.x -= c0 + d0; v0.y -= c1 + d1; }
-    *dst = v0;
+}
+
+__device__ __forceinline__ void ll_store(const LLTile& t, const double (&c)[4])
+{
+    double2 v0 = *t.dst;
+    if (t.inv) { v0.x += c[0] + c[2]; v0.y += c[1] + c[3]; }
+    else { v0.x -= c[0] + c[2]; v0.y -= c[1] + c[3]; }
+    *t.dst = v0;
 }
 
 // In-place factorisation of the SPD tile T (upper triangle read, [64][kSS]; the caller has replaced everything outside the
@@ -137,12 +155,15 @@ __device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int
     for (int b = 0; b < 8; ++b) {
         const int o = 8 * b;
         if (dbg) t0 = clock64();
-        if (b > 0) {
-            leftlook_tile(T, W, b, w, g, q);
+        double R[8][8], r[8];
+        if (b > 0) {  // bring block row b of T and column block b of U^-1 up to date: one tile per warp
+            const LLTile t = ll_tile(T, W, b, w, g, q);
+            double ca[4] = {0.0, 0.0, 0.0, 0.0};
+            ll_accumulate(t, t.k0, o, ca);
+            ll_store(t, ca);
             __syncthreads();
         }
         if (dbg) { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
-        double R[8][8], r[8];
         if (w < 4) {
         // ---- every thread of warps 0-3: Cholesky of the 8x8 diagonal block, R upper, r = 1 / diag(R)
 #pragma unroll
@@ -235,6 +256,8 @@ __global__ void __launch_bounds__(256, 1) k_schain_step(DevView v, int J)
     double* Sf = v.Sf + (size_t)f * v.kmax * v.ldS;
     double* UinvG = v.Uinv + (size_t)f * (v.kmax / kNB) * kNB * kNB;
 
+    grid_launch_dependents();   // the next step (or the slab TRSM) may be scheduled now; it waits for this grid's completion
+    grid_dependency_wait();     // block row J and Uinv_J come from the previous launch
     long long* dbg = (v.dbg != nullptr && fac && f == 0 && tid == 0 && J == 1) ? v.dbg + (k > 300 ? 16 : 40) : nullptr;
     if (dbg) dbg[0] = clock64();
     if (J >= 0) {
