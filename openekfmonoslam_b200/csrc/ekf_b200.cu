@@ -78,6 +78,7 @@ struct ekfb_ctx {
     size_t flush_bytes = 0;
     bool force_generic = false;
     int downdate_variant = 0;
+    int downdate_small_k = 128;   // updates with at most this many rows run the downdate as 64x64 tiles only
     int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches
     bool dd_timing = false;
     std::vector<cudaEvent_t> dd_ev;   // pairs
@@ -524,11 +525,17 @@ static int launch_downdate(ekfb_ctx* c, int n)
 {
     DevView& v = c->v;
     const int nI = cdiv(n, kDTM);
+    int kMax = 0;
+    for (int f = 0; f < c->F; ++f) kMax = std::max(kMax, 2 * c->h_dims[(size_t)f * D_STRIDE + D_ULIST]);
     const bool timeIt = c->dd_timing && c->dd_used + 2 <= c->dd_ev.size();
     if (timeIt) cudaEventRecord(c->dd_ev[c->dd_used], c->stream);
     if (c->downdate_variant == 1)
         k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
-    else {
+    else if (kMax <= c->downdate_small_k) {
+        // few update rows (the high-innovation update): the pass is bound by reading and writing P, not by the tensor pipe;
+        // 64x64 tiles, four CTAs per SM, hide the latency of the read-modify-write better than one 128x128 CTA per SM
+        k_downdate_small<<<dim3(nI * (nI + 1) / 2 * 4, c->F), 128, kSmallSmemBytes, c->stream>>>(v, 0);
+    } else {
         // 1-D grid over the T lower 128x128 tiles.  Single filter: if T is just above a multiple of the SM
         // count, the remainder would cost a whole extra wave; it runs as 64x64 tiles on a second stream,
         // co-resident with the big CTAs (register / smem budgets of the two kernels are sized for that).
@@ -938,8 +945,8 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option == EKFB_OPT_FORCE_GENERIC_FACTOR || option == EKFB_OPT_DOWNDATE_VARIANT || option == EKFB_OPT_SCHAIN_VARIANT,
-            "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_DOWNDATE_SMALL_K, "unknown option");
+    if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
     if (option == EKFB_OPT_FORCE_GENERIC_FACTOR) c->force_generic = value != 0;
     else if (option == EKFB_OPT_SCHAIN_VARIANT) c->schain_variant = value;
     else c->downdate_variant = value;
