@@ -505,9 +505,9 @@ extern "C" int ekfb_ransac(ekfb_handle c)
     GroupScope gs(c, G_RANSAC);
     const int CH = 16;
     const int n = max_of(c->hn), N = max_of(c->hN);
-    const size_t smem = sizeof(double) * (size_t)n;
+    (void)n;
     for (int chunk0 = 0; chunk0 < std::max(N, 1); chunk0 += CH) {
-        k_ransac_hyp<<<dim3(CH, c->F), 256, smem, c->stream>>>(c->v, chunk0);
+        k_ransac_hyp<<<dim3(CH, c->F, cdiv(c->Nmax, kHypFeat)), 416, 0, c->stream>>>(c->v, chunk0);
         k_ransac_select<<<c->F, 256, 0, c->stream>>>(c->v, chunk0, CH);
         count_launch(c, 2);
         CK(cudaGetLastError());

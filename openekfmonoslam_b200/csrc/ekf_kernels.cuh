@@ -384,92 +384,105 @@ __global__ void __launch_bounds__(256) k_after_match(DevView v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// R1: one CTA per hypothesis (E/1PointRansac.cpp:125-161).  Hypothesis i = i-th match.  The
-// state-only EKF update uses K_i = P H_i^T (H_i P H_i^T + sigma I)^-1 with the symmetric-row
-// gather P[:, c] = P[c, :] (13 coalesced row reads); x_i is staged in shared memory, then every
-// feature is re-projected with the un-normalised q_i and the support of matched features within
-// the pixel threshold is ballot-packed.  Hypotheses of a chunk are evaluated speculatively; the
-// sequential acceptance rule is replayed by k_ransac_select.
+// R1: the hypotheses of 1-point RANSAC (E/1PointRansac.cpp:125-161).  Hypothesis i = i-th match.  The state-only
+// EKF update uses K_i = P H_i^T (H_i P H_i^T + sigma I)^-1 with the symmetric-row gather P[:, c] = P[c, :]
+// (13 coalesced row reads).  grid (chunk, F, ceil(Nmax / 64)): CTA (i, f, part) updates the 13 camera rows and the rows
+// of its 64 features only, re-projects those features with the un-normalised q_i and ballot-packs the support of matched
+// features within the pixel threshold into two words of the hypothesis' support set (the count is the popcount of the
+// set, taken by k_ransac_select).  Hypotheses of a chunk are evaluated speculatively; the sequential acceptance rule is
+// replayed by k_ransac_select.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ransac_hyp(DevView v, int chunk0)
+constexpr int kHypFeat = 64;  // features per CTA
+
+__global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0)
 {
-    extern __shared__ __align__(16) double xh[];  // n doubles
+    __shared__ double xc[13], xs[kHypFeat * 6];
     __shared__ double sK[4], sNu[2], sHx[14], sHf[12], sR[27];
-    __shared__ int sCount;
-    const int f = blockIdx.y;
+    const int f = blockIdx.y, part = blockIdx.z;
     const int* dm = fdims(v, f);
     const int i = chunk0 + blockIdx.x;
     const int m = dm[D_N_MATCH];
     if (dm[D_RANSAC_DONE] || i >= m || (unsigned)i >= (unsigned)dm[D_RANSAC_CAP]) return;
-    const int n = dm[D_N_STATE], N = dm[D_N_FEAT];
+    const int N = dm[D_N_FEAT];
+    const int jBeg = part * kHypFeat;
+    if (jBeg >= N && 2 * part >= v.supWords) return;
     const size_t fo = (size_t)f * v.Nmax;
     const int j0 = v.mlist[fo + i];
     const double* x = v.x + (size_t)f * v.ld;
     const double* P = v.P + (size_t)f * v.nmax * v.ld;
     const int off0 = v.foff[fo + j0];
     const int d0 = v.ftype[fo + j0] == kTypeInvDepth ? 6 : 3;
-    if (threadIdx.x == 0) {
+    const int tid = threadIdx.x;
+    if (tid == 0) {
         // S = H P H^T + sigma I: the measurement kernel already formed H P H^T + I
         const double* Si = v.Si + (fo + j0) * 4;
         const double S2[4] = {Si[0] - 1.0 + v.sigma_px, Si[1], Si[2], Si[3] - 1.0 + v.sigma_px};
         inv2(S2, sK);
         sNu[0] = deadband(v.z[(fo + j0) * 2] - v.h[(fo + j0) * 2]);
         sNu[1] = deadband(v.z[(fo + j0) * 2 + 1] - v.h[(fo + j0) * 2 + 1]);
-        sCount = 0;
     }
-    if (threadIdx.x < 14) sHx[threadIdx.x] = v.Hx[(fo + j0) * 14 + threadIdx.x];
-    if (threadIdx.x >= 32 && threadIdx.x < 44) sHf[threadIdx.x - 32] = v.Hf[(fo + j0) * 12 + threadIdx.x - 32];
+    if (tid < 14) sHx[tid] = v.Hx[(fo + j0) * 14 + tid];
+    if (tid >= 32 && tid < 44) sHf[tid - 32] = v.Hf[(fo + j0) * 12 + tid - 32];
     __syncthreads();
-    for (int row = threadIdx.x; row < n; row += blockDim.x) {
+    // rows of this CTA: slot < 13 -> camera row, else feature jBeg + (slot - 13) / 6, component (slot - 13) % 6
+    for (int slot = tid; slot < 13 + kHypFeat * 6; slot += blockDim.x) {
+        int row = slot;
+        if (slot >= 13) {
+            const int jj = (slot - 13) / 6, a = (slot - 13) % 6, j = jBeg + jj;
+            row = -1;
+            if (j < N && v.mflag[fo + j] && a < (v.ftype[fo + j] == kTypeInvDepth ? 6 : 3)) row = v.foff[fo + j] + a;
+        }
+        if (row < 0) continue;
+        // all 13 row reads of P in flight at once (the loop over the feature's own columns has a fixed trip count of 6,
+        // the XYZ case masks the last three: same sums in the same order)
+        double pc[7], pf[6];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) pc[c] = P[(size_t)c * v.ld + row];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) pf[c] = c < d0 ? P[(size_t)(off0 + c) * v.ld + row] : 0.0;
         double p0 = 0., p1 = 0.;
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
-            const double pv = P[(size_t)c * v.ld + row];
-            p0 += pv * sHx[c];
-            p1 += pv * sHx[7 + c];
+            p0 += pc[c] * sHx[c];
+            p1 += pc[c] * sHx[7 + c];
         }
-        for (int c = 0; c < d0; ++c) {
-            const double pv = P[(size_t)(off0 + c) * v.ld + row];
-            p0 += pv * sHf[c];
-            p1 += pv * sHf[6 + c];
-        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+            if (c < d0) {
+                p0 += pf[c] * sHf[c];
+                p1 += pf[c] * sHf[6 + c];
+            }
         const double k0 = p0 * sK[0] + p1 * sK[2];
         const double k1 = p0 * sK[1] + p1 * sK[3];
         const double dx = deadband(k0 * sNu[0] + k1 * sNu[1]);
-        xh[row] = x[row] + dx;
+        const double val = x[row] + dx;
+        if (slot < 13) xc[slot] = val;
+        else xs[slot - 13] = val;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        quat_to_rot(xh + 3, sR);       // R(q_i), q_i not normalised (E/Update.cpp:168)
+    if (tid == 0) {
+        quat_to_rot(xc + 3, sR);       // R(q_i), q_i not normalised (E/Update.cpp:168)
         inv3(sR, sR + 9);
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) sR[18 + a * 3 + b] = sR[b * 3 + a];
     }
     __syncthreads();
+    if (tid >= kHypFeat) return;
     uint32_t* sup = v.hypsup + ((size_t)f * v.Nmax + i) * v.supWords;
-    int local = 0;
-    for (int base = 0; base < N; base += blockDim.x) {
-        const int j = base + threadIdx.x;
-        bool s = false;
-        if (j < N && v.mflag[fo + j]) {
-            const int type = v.ftype[fo + j], off = v.foff[fo + j];
-            double y[6], hh[2];
-            const int d = type == kTypeInvDepth ? 6 : 3;
-            for (int a = 0; a < 6; ++a) y[a] = a < d ? xh[off + a] : 0.;
-            if (predict_pixel(v.cam, xh, sR + 18, sR + 9, type, y, hh)) {
-                const double ex = v.z[(fo + j) * 2] - hh[0], ey = v.z[(fo + j) * 2 + 1] - hh[1];
-                s = sqrt(ex * ex + ey * ey) < v.ransac_thr;
-            }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, s);
-        if ((threadIdx.x & 31) == 0) {
-            if ((j >> 5) < v.supWords) sup[j >> 5] = bal;
-            local += __popc(bal);
+    const int j = jBeg + tid;
+    bool s = false;
+    if (j < N && v.mflag[fo + j]) {
+        const int type = v.ftype[fo + j];
+        double y[6], hh[2];
+        const int d = type == kTypeInvDepth ? 6 : 3;
+        for (int a = 0; a < 6; ++a) y[a] = a < d ? xs[tid * 6 + a] : 0.;
+        if (predict_pixel(v.cam, xc, sR + 18, sR + 9, type, y, hh)) {
+            const double ex = v.z[(fo + j) * 2] - hh[0], ey = v.z[(fo + j) * 2 + 1] - hh[1];
+            s = sqrt(ex * ex + ey * ey) < v.ransac_thr;
         }
     }
-    if ((threadIdx.x & 31) == 0) atomicAdd(&sCount, local);
-    __syncthreads();
-    if (threadIdx.x == 0) v.hypcount[(size_t)f * v.Nmax + i] = sCount;
+    const unsigned bal = __ballot_sync(0xffffffffu, s);
+    if ((tid & 31) == 0 && (j >> 5) < v.supWords) sup[j >> 5] = bal;
 }
 
 // Sequential replay of the acceptance / adaptive-cap rule over one evaluated chunk
@@ -482,6 +495,17 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
     const size_t fo = (size_t)f * v.Nmax;
     const int N = dm[D_N_FEAT], m = dm[D_N_MATCH];
     __shared__ int finished;
+    __shared__ int cnts[64];   // support counts of the chunk's hypotheses = popcount of their support sets
+    if ((int)threadIdx.x < chunkLen && threadIdx.x < 64) {
+        const int i = chunk0 + threadIdx.x;
+        int cnt = 0;
+        if (i < m && !dm[D_RANSAC_DONE]) {
+            const uint32_t* sw = v.hypsup + ((size_t)f * v.Nmax + i) * v.supWords;
+            for (int w = 0; w < v.supWords; ++w) cnt += __popc(sw[w]);
+        }
+        cnts[threadIdx.x] = cnt;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         finished = 0;
         if (!dm[D_RANSAC_DONE]) {
@@ -490,7 +514,7 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
             bool done = false;
             for (; i < end; ++i) {
                 if (!((unsigned)i < (unsigned)cap && i < m)) { done = true; break; }
-                const int cnt = v.hypcount[fo + i];
+                const int cnt = cnts[i - chunk0];
                 if (cnt > best) {
                     best = cnt;
                     bestHyp = i;
