@@ -626,7 +626,7 @@ static int run_update(ekfb_ctx* c, int which)
     {
         GroupScope gs(c, G_GAIN);
         k_gain_rows<<<dim3(cdiv(c->ld, 256), ku, c->F), 256, 0, c->stream>>>(v, which);
-        k_build_S<<<dim3(cdiv(k, 16), cdiv(k, 16), c->F), dim3(16, 16), 0, c->stream>>>(v, which);
+        k_build_S<<<dim3(cdiv(k, 32), cdiv(k, 32), c->F), dim3(32, 8), 0, c->stream>>>(v, which);
         count_launch(c, 2);
     }
     {

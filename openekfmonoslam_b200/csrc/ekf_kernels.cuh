@@ -249,70 +249,89 @@ __global__ void k_kp_mask(DevView v)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_match(DevView v)
 {
+    // keypoint positions and mask flags are staged in shared memory, 1024 at a time, for the eight features of the CTA
+    constexpr int CHUNK = 1024;
+    __shared__ float2 sxy[CHUNK];
+    __shared__ uint8_t sok[CHUNK];
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     const int N = dm[D_N_FEAT], Kp = dm[D_N_KP];
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= N) return;
-    const size_t fj = (size_t)f * v.Nmax + j;
-    if (!v.vis[fj]) {
-        if (lane == 0) v.mflag[fj] = 0;
-        return;
-    }
-    const float* xy = v.kpxy[f];
+    const size_t fj = (size_t)f * v.Nmax + (j < N ? j : 0);
+    const bool active = j < N && v.vis[fj];
+    const float2* xy2 = reinterpret_cast<const float2*>(v.kpxy[f]);
     const uint8_t* kd = v.kpdesc[f];
     const uint8_t* ok = v.kpok + (size_t)f * v.Kpmax;
-    const int iw = __float2int_rn(v.ellax[fj * 2]), ih = __float2int_rn(v.ellax[fj * 2 + 1]);  // Size2f -> Size rounds
-    const float cxf = (float)v.h[fj * 2], cyf = (float)v.h[fj * 2 + 1];
-    const double ang = v.ellang[fj];
-    const uint32_t* fd = reinterpret_cast<const uint32_t*>(v.desc + fj * 32);
-    uint32_t q[8];
+    int iw = 0, ih = 0;
+    float cxf = 0.f, cyf = 0.f;
+    double ang = 0.0;
+    uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+        iw = __float2int_rn(v.ellax[fj * 2]); ih = __float2int_rn(v.ellax[fj * 2 + 1]);  // Size2f -> Size rounds
+        cxf = (float)v.h[fj * 2]; cyf = (float)v.h[fj * 2 + 1];
+        ang = v.ellang[fj];
+        const uint32_t* fd = reinterpret_cast<const uint32_t*>(v.desc + fj * 32);
 #pragma unroll
-    for (int a = 0; a < 8; ++a) q[a] = fd[a];
-
+        for (int a = 0; a < 8; ++a) q[a] = fd[a];
+    }
     float minD = -1.f;
     int size = 0;
     float dFront = 0.f, dBack = 0.f;
     int iFront = -1, iBack = -1;
-    for (int base = 0; base < Kp; base += 32) {
-        const int kidx = base + lane;
-        bool cand = false;
-        float dist = 0.f;
-        if (kidx < Kp && ok[kidx]) {
-            cand = inside_gate(xy[2 * kidx], xy[2 * kidx + 1], cxf, cyf, iw, ih, ang);
-            if (cand) {
-                const uint32_t* cdp = reinterpret_cast<const uint32_t*>(kd + (size_t)kidx * 32);
-                int dd = 0;
-#pragma unroll
-                for (int a = 0; a < 8; ++a) dd += __popc(q[a] ^ cdp[a]);
-                dist = (float)dd;
-            }
+    float zx = 0.f, zy = 0.f;
+    for (int c0 = 0; c0 < Kp; c0 += CHUNK) {
+        const int cn = min(CHUNK, Kp - c0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cn; e += blockDim.x) {
+            sxy[e] = xy2[c0 + e];
+            sok[e] = ok[c0 + e];
         }
-        unsigned bal = __ballot_sync(0xffffffffu, cand);
-        while (bal) {
-            const int src = __ffs(bal) - 1;
-            bal &= bal - 1;
-            const float dcur = __shfl_sync(0xffffffffu, dist, src);
-            if (dcur < minD || size < 2) {
-                minD = (minD < 0.f) ? dcur : fminf(minD, dcur);
-                dBack = dFront; iBack = iFront;  // push_front; a 3rd element falls off the back
-                dFront = dcur; iFront = base + src;
-                if (size < 2) size++;
+        __syncthreads();
+        if (!active) continue;
+        for (int base = 0; base < cn; base += 32) {
+            const int kl = base + lane;
+            bool cand = false;
+            float dist = 0.f;
+            float2 pt = make_float2(0.f, 0.f);
+            if (kl < cn && sok[kl]) {
+                pt = sxy[kl];
+                cand = inside_gate(pt.x, pt.y, cxf, cyf, iw, ih, ang);
+                if (cand) {
+                    const uint32_t* cdp = reinterpret_cast<const uint32_t*>(kd + (size_t)(c0 + kl) * 32);
+                    int dd = 0;
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) dd += __popc(q[a] ^ cdp[a]);
+                    dist = (float)dd;
+                }
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, cand);
+            while (bal) {
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                const float dcur = __shfl_sync(0xffffffffu, dist, src);
+                if (dcur < minD || size < 2) {
+                    minD = (minD < 0.f) ? dcur : fminf(minD, dcur);
+                    dBack = dFront; iBack = iFront;  // push_front; a 3rd element falls off the back
+                    dFront = dcur; iFront = c0 + base + src;
+                    zx = __shfl_sync(0xffffffffu, pt.x, src); zy = __shfl_sync(0xffffffffu, pt.y, src);
+                    if (size < 2) size++;
+                }
             }
         }
     }
-    if (lane == 0) {
-        const bool accept = (size == 1) || (size >= 2 && (double)dFront <= (double)dBack * v.match_coef);
+    (void)iBack;
+    if (lane == 0 && j < N) {
+        const bool accept = active && ((size == 1) || (size >= 2 && (double)dFront <= (double)dBack * v.match_coef));
         if (accept) {
             v.mflag[fj] = 1;
             v.mkp[fj] = iFront;
             v.mdist[fj] = dFront;
-            v.z[fj * 2] = (double)xy[2 * iFront];
-            v.z[fj * 2 + 1] = (double)xy[2 * iFront + 1];
+            v.z[fj * 2] = (double)zx;
+            v.z[fj * 2 + 1] = (double)zy;
         } else {
             v.mflag[fj] = 0;
-            v.mkp[fj] = -1;
+            if (active) v.mkp[fj] = -1;
         }
     }
 }

@@ -61,17 +61,22 @@ __global__ void __launch_bounds__(256) k_gain_rows(DevView v, int which)
     double* B0 = v.Bu + ((size_t)f * v.kmax + 2 * a) * v.ld;
     double b0 = 0., b1 = 0.;
     if (i < n) {
+        double pc[7], pf[6];  // all row reads in flight at once; the XYZ case masks the last three feature rows
+#pragma unroll
+        for (int c = 0; c < 7; ++c) pc[c] = P[(size_t)c * v.ld + i];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) pf[c] = c < d ? P[(size_t)(off + c) * v.ld + i] : 0.0;
 #pragma unroll
         for (int c = 0; c < 7; ++c) {
-            const double p = P[(size_t)c * v.ld + i];
-            b0 += sHx[c] * p;
-            b1 += sHx[7 + c] * p;
+            b0 += sHx[c] * pc[c];
+            b1 += sHx[7 + c] * pc[c];
         }
-        for (int c = 0; c < d; ++c) {
-            const double p = P[(size_t)(off + c) * v.ld + i];
-            b0 += sHf[c] * p;
-            b1 += sHf[6 + c] * p;
-        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+            if (c < d) {
+                b0 += sHf[c] * pf[c];
+                b1 += sHf[6 + c] * pf[c];
+            }
     } else if (i == n) {
         b0 = deadband(v.z[(fo + j) * 2] - s.h[(fo + j) * 2]);
         b1 = deadband(v.z[(fo + j) * 2 + 1] - s.h[(fo + j) * 2 + 1]);
@@ -81,31 +86,77 @@ __global__ void __launch_bounds__(256) k_gain_rows(DevView v, int which)
     if (a == 0) v.dx[(size_t)f * v.ld + i] = 0.0;  // reset the state-correction accumulator
 }
 
-// S = H B^T + sigma I, sparse in H again (E/Update.cpp:95-107).  grid (ceil(k/16), ceil(k/16), F), block (16,16)
-__global__ void k_build_S(DevView v, int which)
+// S = H B^T + sigma I, sparse in H again (E/Update.cpp:95-107); only the 32x32 tiles on or above the diagonal are formed
+// (the factorisation reads the upper triangle).  CTA tile: 32 rows ra (16 features) x 32 columns rb.  The 7 camera columns
+// and the 16 x 6 feature columns of the 32 rows rb of B are staged in shared memory with coalesced reads, the products run
+// out of shared memory and S is written with the lanes along rb.  grid (ceil(k/32), ceil(k/32), F), block (32, 8).
+__global__ void __launch_bounds__(256) k_build_S(DevView v, int which)
 {
+    constexpr int BP = 105;  // 7 + 16 * 6 columns, odd pitch
+    __shared__ double Bs[32 * BP];
+    __shared__ double Hs[32 * 13];
+    __shared__ int sOff[16], sD[16], sJ[16];
     const int f = blockIdx.z;
     const int* dm = fdims(v, f);
     const int k = 2 * dm[D_ULIST];
-    const int ra = blockIdx.y * 16 + threadIdx.y, rb = blockIdx.x * 16 + threadIdx.x;
-    if (ra >= k || rb >= k) return;
+    if (blockIdx.x < blockIdx.y) return;  // strictly below the diagonal
+    const int ra0 = blockIdx.y * 32, rb0 = blockIdx.x * 32;
+    if (ra0 >= k || rb0 >= k) return;
     const size_t fo = (size_t)f * v.Nmax;
-    const int a = ra >> 1, r = ra & 1;
-    const int j = v.ulist[fo + a];
     const UpdSrc s = upd_src(v, which);
-    const double* Hx = s.Hx + (fo + j) * 14 + 7 * r;
-    const double* Hf = s.Hf + (fo + j) * 12 + 6 * r;
-    const int off = v.foff[fo + j];
-    const int d = v.ftype[fo + j] == kTypeInvDepth ? 6 : 3;
-    const double* Brow = v.Bu + ((size_t)f * v.kmax + rb) * v.ld;
-    double acc = 0.;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 16) {
+        const int a = (ra0 >> 1) + tid;
+        const int j = (2 * a < k) ? v.ulist[fo + a] : -1;
+        sJ[tid] = j;
+        sOff[tid] = j >= 0 ? v.foff[fo + j] : 0;
+        sD[tid] = j >= 0 ? (v.ftype[fo + j] == kTypeInvDepth ? 6 : 3) : 0;
+    }
+    __syncthreads();
+    for (int e = tid; e < 32 * 13; e += 256) {
+        const int rl = e / 13, c = e % 13, j = sJ[rl >> 1], r = rl & 1;
+        double h = 0.0;
+        if (j >= 0) h = c < 7 ? s.Hx[(fo + j) * 14 + 7 * r + c] : s.Hf[(fo + j) * 12 + 6 * r + (c - 7)];
+        Hs[e] = h;
+    }
+    const double* Bg = v.Bu + (size_t)f * v.kmax * v.ld;
 #pragma unroll
-    for (int c = 0; c < 7; ++c) acc += Hx[c] * Brow[c];
-    for (int c = 0; c < d; ++c) acc += Hf[c] * Brow[off + c];
-    if (ra == rb) acc += v.sigma_px;
-    v.S[((size_t)f * v.kmax + ra) * v.ldS + rb] = acc;
-    if (rb == 0)  // column k of S carries the dead-banded innovation nu (it becomes y = U^-T nu)
-        v.S[((size_t)f * v.kmax + ra) * v.ldS + k] = deadband(v.z[(fo + j) * 2 + r] - s.h[(fo + j) * 2 + r]);
+    for (int it = 0; it < (32 * 103 + 255) / 256; ++it) {  // unrolled: all 13 reads of a thread in flight
+        const int e = tid + 256 * it;
+        if (e >= 32 * 103) break;
+        const int rl = e / 103, cc = e % 103;
+        double val = 0.0;
+        if (rb0 + rl < k) {
+            if (cc < 7) val = Bg[(size_t)(rb0 + rl) * v.ld + cc];
+            else {
+                const int fa = (cc - 7) / 6, c = (cc - 7) % 6;
+                if (c < sD[fa]) val = Bg[(size_t)(rb0 + rl) * v.ld + sOff[fa] + c];
+            }
+        }
+        Bs[rl * BP + cc] = val;
+    }
+    __syncthreads();
+    const int rb = rb0 + threadIdx.x;
+    const double* Brow = Bs + threadIdx.x * BP;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+        const int rl = threadIdx.y * 4 + qq, ra = ra0 + rl;
+        if (ra >= k) continue;
+        const int fa = rl >> 1, d = sD[fa];
+        const double* H = Hs + rl * 13;
+        double acc = 0.;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) acc += H[c] * Brow[c];
+        for (int c = 0; c < d; ++c) acc += H[7 + c] * Brow[7 + 6 * fa + c];
+        if (rb < k) {
+            if (ra == rb) acc += v.sigma_px;
+            v.S[((size_t)f * v.kmax + ra) * v.ldS + rb] = acc;
+        }
+        if (blockIdx.x == blockIdx.y && threadIdx.x == 0) {  // column k of S carries the dead-banded innovation nu (-> y = U^-T nu)
+            const int j = sJ[fa], r = rl & 1;
+            v.S[((size_t)f * v.kmax + ra) * v.ldS + k] = deadband(v.z[(fo + j) * 2 + r] - s.h[(fo + j) * 2 + r]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
