@@ -823,6 +823,8 @@ extern "C" int ekfb_test_downdate(ekfb_handle c, int n, int k, const double* P_i
     hd[D_N_STATE] = n;
     hd[D_ULIST] = k / 2;
     CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    // once ekfb_flush_l2 has been used on this handle, the launch is measured with P and W evicted from L2
+    if (c->flush_buf) CK(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream));
     CK(cudaEventRecord(c->pe[0], c->stream));
     {
         const int saveN = c->hn[0];

@@ -417,10 +417,7 @@ __global__ void __maxnreg__(KIND == 2 ? 200 : 255) k_gemm_tn(DevView v, int J)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
     double acc[8][4][2];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int kq = lane & 3, mq = lane >> 2;
 
     const int nk = (K + kKC - 1) / kKC;
     auto stageA = [&](int s) { return gsm + (size_t)s * 2 * kKC * kLDS; };
@@ -433,7 +430,30 @@ __global__ void __maxnreg__(KIND == 2 ? 200 : 255) k_gemm_tn(DevView v, int J)
         }
         cp_async_commit();
     }
-    const int kq = lane & 3, mq = lane >> 2;
+    // The accumulators start at -C: all 64 loads of the thread's part of the C tile are issued here, independent of
+    // each other, and are in flight together with the operand ring's prologue; the epilogue is store-only
+    // (C_new = -(-C + sum)).  A load -> subtract -> store epilogue serialises 64 memory round trips per thread because
+    // the stores to C order the following loads from C.
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int gm = tm0 + wm * 64 + a * 8 + mq;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int gn = tn0 + wn * 32 + b * 8 + 2 * kq;
+            double c0 = 0.0, c1 = 0.0;
+            if ((KIND >= 2) && gm < mEnd) {   // KIND 0 (generic factorisation path) keeps the in-place epilogue
+                const double* cp = C + (size_t)gm * ldc + gn;
+                if (gn + 1 < nEnd) {
+                    const double2 t = *reinterpret_cast<const double2*>(cp);
+                    c0 = t.x; c1 = t.y;
+                } else if (gn < nEnd) {
+                    c0 = *cp;
+                }
+            }
+            acc[a][b][0] = -c0;
+            acc[a][b][1] = -c1;
+        }
+    }
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<kStages - 2>();
         __syncthreads();
@@ -475,7 +495,7 @@ __global__ void __maxnreg__(KIND == 2 ? 200 : 255) k_gemm_tn(DevView v, int J)
                 if (g >= nEnd) continue;
                 if ((KIND >= 2)) {
                     if (g > gm) continue;
-                    const double val = C[(size_t)gm * ldc + g] - acc[a][b][e];
+                    const double val = -acc[a][b][e];
                     C[(size_t)gm * ldc + g] = val;
                     if (g != gm) C[(size_t)g * ldc + gm] = val;
                 } else {
@@ -512,10 +532,6 @@ __global__ void __maxnreg__(112) k_downdate_small(DevView v, int firstBig)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
     double acc[4][4][2];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     const int nk = (K + kKC - 1) / kKC;
     auto stA = [&](int st) { return ssm2 + (size_t)st * kKC * 136; };
     auto stB = [&](int st) { return ssm2 + (size_t)st * kKC * 136 + kKC * 68; };
@@ -537,6 +553,27 @@ __global__ void __maxnreg__(112) k_downdate_small(DevView v, int firstBig)
     for (int st = 0; st < kStages - 1; ++st) {
         if (st < nk) load(st, st);
         cp_async_commit();
+    }
+    // accumulators start at -P (see k_gemm_tn): the tile's loads overlap the ring prologue, the epilogue only stores
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int gm = tm0 + wm * 32 + a * 8 + g;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int gn = tn0 + wn * 32 + b * 8 + 2 * q;
+            double c0 = 0.0, c1 = 0.0;
+            if (gm < n) {
+                const double* cp = P + (size_t)gm * ld + gn;
+                if (gn + 1 < n) {
+                    const double2 t = *reinterpret_cast<const double2*>(cp);
+                    c0 = t.x; c1 = t.y;
+                } else if (gn < n) {
+                    c0 = *cp;
+                }
+            }
+            acc[a][b][0] = -c0;
+            acc[a][b][1] = -c1;
+        }
     }
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<kStages - 2>();
@@ -569,7 +606,7 @@ __global__ void __maxnreg__(112) k_downdate_small(DevView v, int firstBig)
             for (int e = 0; e < 2; ++e) {
                 const int gn = tn0 + wn * 32 + b * 8 + 2 * q + e;
                 if (gn > gm || gn >= n) continue;
-                const double val = P[(size_t)gm * ld + gn] - acc[a][b][e];
+                const double val = -acc[a][b][e];
                 P[(size_t)gm * ld + gn] = val;
                 if (gn != gm) P[(size_t)gn * ld + gm] = val;
             }
