@@ -203,6 +203,8 @@ def main():
     T0, W_, K = args.filter_warm, args.warmup, args.steps
     n_frames = T0 + W_ + 2 * K                       # device-resident pass, then host-fed pass
     gpu = EkfBatch(next(iter(scenes.values())).params, F, N, 2 * N + 256, device=local)
+    for kv in filter(None, os.environ.get("EKFB_OPTS", "").split(",")):   # developer switches (ekfb_set_option), e.g. "4=128"
+        gpu.set_option(*(int(x) for x in kv.split("=")))
     frames_of = {}
     for f in sorted(set(my_filters)):
         sc = scenes[f]

@@ -118,6 +118,46 @@ int ekfb_update_map_features(ekfb_handle h); /* updateMapFeatures, E/MapManageme
  * rescue, update HI, updateMapFeatures */
 int ekfb_step(ekfb_handle h);
 
+/* ---- map management on the device (E/EKF.cpp:572-612; the covariance never leaves HBM) -------------- */
+/* POD mirror of the map-management fields of ExtendedKalmanFilterParameters (.../ExtendedKalmanFilterParameters.h:37-76) */
+typedef struct ekfb_map_policy {
+    int32_t min_matches_per_image;      /* MinMatchesPerImage            */
+    int32_t max_map_features_count;     /* MaxMapFeaturesCount (0 = off) */
+    int32_t max_map_size;               /* MaxMapSize, rows of the state (0 = off) */
+    int32_t always_remove_unseen;       /* AlwaysRemoveUnseenMapFeatures */
+    double good_feature_matching_percent;   /* GoodFeatureMatchingPercent            */
+    double linearity_index_threshold;       /* InverseDepthLinearityIndexThreshold   */
+} ekfb_map_policy;
+typedef struct ekfb_map_result {
+    int32_t n, n_features;              /* sizes after the call */
+    int32_t n_removed_bad, n_removed_unseen;
+    int32_t converted;                  /* index (new numbering) of the feature converted to XYZ, or -1 */
+    int32_t new_features_needed;        /* newFeaturesNeededCount, E/EKF.cpp:577 (may be <= 0) */
+} ekfb_map_result;
+/* After ekfb_step (or ekfb_update_map_features) of the same frame, for all filters of the handle:
+ * removeBadMapFeatures (E/MapManagement.cpp:279-307), removal of the features not predicted in this frame under the policy of
+ * E/EKF.cpp:580-589 (removeFeaturesFromStateAndCovariance, E/MapManagement.cpp:212-259) and convertMapFeaturesInverseDepthToDepth
+ * (at most one feature per call, E/MapManagement.cpp:311-524).  Synchronises; out (n_filters entries) may be NULL.
+ * Per-feature results of the frame (ekfb_get_feature_results) are indexed by the numbering BEFORE this call. */
+int ekfb_map_management(ekfb_handle h, const ekfb_map_policy* policy, ekfb_map_result* out);
+/* flags of the last ekfb_map_management for the n_features_before features present before it: 0 kept, 1 removed as bad,
+ * 2 removed as unseen (lets the host mirror State::removeFeatures, E/State.cpp:199-206) */
+int ekfb_get_removed_flags(ekfb_handle h, int filter, int n_features_before, uint8_t* flags);
+/* addFeaturesToStateAndCovariance (E/AddMapFeature.cpp:293-366): `count` new inverse-depth features observed at pixels
+ * uv (count x 2 doubles, ImageFeatureMeasurement::imagePos) with descriptors desc (count x 32).  EKFB_ERR_CAPACITY if they do not fit. */
+int ekfb_add_features(ekfb_handle h, int filter, int count, const double* uv, const uint8_t* desc);
+/* feature type (1 XYZ / 2 inverse depth) and covarianceMatrixPos of the current map (E/MapFeature.h:39-44,68) */
+int ekfb_get_feature_layout(ekfb_handle h, int filter, int32_t* type, int32_t* off);
+/* overwrite timesPredicted / timesMatched (E/MapFeature.h:72-73); for tests and for restoring a saved map */
+int ekfb_set_hit_counters(ekfb_handle h, int filter, const int32_t* times_predicted, const int32_t* times_matched);
+/* buildImageMask (E/DetectNewImageFeatures.cpp:101-122): 255 everywhere, 0 inside the gate ellipse of every feature predicted
+ * in this frame; built by the last ekfb_map_management when a filter asked for new features (pixels_y x pixels_x bytes) */
+int ekfb_get_new_feature_mask(ekfb_handle h, int filter, uint8_t* mask);
+/* one drawUncertaintyEllipse2D(img, (cx,cy), S, max_axes, value, filled) (Gui/Draw.cpp:42-64) into a host W x H byte image;
+ * the host side uses it once for the stamp of E/DetectNewImageFeatures.cpp:283-288, tests pin the rasteriser with it */
+int ekfb_raster_ellipse(ekfb_handle h, int W, int H, double cx, double cy, const double* S, int max_axes, int value,
+                        uint8_t* img_inout);
+
 /* ---- results ----------------------------------------------------------------------------------- */
 int ekfb_get_frame_info(ekfb_handle h, int filter, ekfb_frame_info* info);
 /* per-filter records of all filters, to a host buffer (n_filters records) */
@@ -160,7 +200,7 @@ int64_t ekfb_kernel_launches(ekfb_handle h);     /* kernels launched by this han
  * the whole augmented matrix (the path used when k is too large for the shared-memory slab TRSM). */
 enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* 0: 128x128 tiles (default), 1: 128x64 tiles, 2 CTAs/SM */,
        EKFB_OPT_SCHAIN_VARIANT = 3 /* factorisation of S: 0 = one fused launch per 64-row step (default), 1 = panel + trail launches */,
-       EKFB_OPT_DOWNDATE_SMALL_K = 4 /* updates with at most this many rows run the downdate as 64x64 tiles only (default 128) */ };
+       EKFB_OPT_DOWNDATE_SMALL_K = 4 /* updates with at most this many rows run the downdate as 64x64 tiles, 4 CTAs/SM (default: all); above it 128x128 tiles */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

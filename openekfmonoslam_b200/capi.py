@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 from . import build as _build
-from .params import EkfParams
+from .params import EkfParams, MapPolicy, MapResult
 
 
 class EkfError(RuntimeError):
@@ -182,6 +182,44 @@ class EkfBatch:
         ok = np.zeros(max(n_kp, 1), np.uint8)
         self._ck(self.L.ekfb_get_mask(self.h, ctypes.c_int(f), _ptr(mask), _ptr(ok)))
         return mask, ok[:n_kp]
+
+    # ---- map management on the device ----
+    def map_management(self, policy: MapPolicy):
+        """E/EKF.cpp:575-592 up to the detection of new features; returns one dict per filter"""
+        out = (MapResult * self.n_filters)()
+        self._ck(self.L.ekfb_map_management(self.h, ctypes.byref(policy), out))
+        return [o.as_dict() for o in out]
+
+    def removed_flags(self, f, n_features_before):
+        fl = np.zeros(max(n_features_before, 1), np.uint8)
+        self._ck(self.L.ekfb_get_removed_flags(self.h, ctypes.c_int(f), ctypes.c_int(n_features_before), _ptr(fl)))
+        return fl[:n_features_before]
+
+    def add_features(self, f, uv, desc):
+        uv = np.ascontiguousarray(uv, np.float64).reshape(-1, 2); desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self._ck(self.L.ekfb_add_features(self.h, ctypes.c_int(f), ctypes.c_int(uv.shape[0]), _ptr(uv), _ptr(desc)))
+
+    def feature_layout(self, f=0):
+        _, N = self.dims(f)
+        t = np.zeros(max(N, 1), np.int32); o = np.zeros(max(N, 1), np.int32)
+        self._ck(self.L.ekfb_get_feature_layout(self.h, ctypes.c_int(f), _ptr(t), _ptr(o)))
+        return t[:N], o[:N]
+
+    def set_hit_counters(self, f, tp, tm):
+        tp = np.ascontiguousarray(tp, np.int32); tm = np.ascontiguousarray(tm, np.int32)
+        self._ck(self.L.ekfb_set_hit_counters(self.h, ctypes.c_int(f), _ptr(tp), _ptr(tm)))
+
+    def new_feature_mask(self, f=0):
+        m = np.zeros((self.params.pixels_y, self.params.pixels_x), np.uint8)
+        self._ck(self.L.ekfb_get_new_feature_mask(self.h, ctypes.c_int(f), _ptr(m)))
+        return m
+
+    def raster_ellipse(self, img, cx, cy, S, max_axes, value=255):
+        assert img.dtype == np.uint8 and img.flags.c_contiguous
+        S = np.ascontiguousarray(S, np.float64)
+        self._ck(self.L.ekfb_raster_ellipse(self.h, ctypes.c_int(img.shape[1]), ctypes.c_int(img.shape[0]), ctypes.c_double(cx),
+                                            ctypes.c_double(cy), _ptr(S), ctypes.c_int(max_axes), ctypes.c_int(value), _ptr(img)))
+        return img
 
     # ---- isolated kernels / timing ----
     def test_downdate(self, P, Wt):

@@ -13,6 +13,7 @@
 
 #include "ekf_linalg.cuh"
 #include "ekf_schain.cuh"
+#include "ekf_map.cuh"
 
 using namespace ekf;
 
@@ -78,12 +79,18 @@ struct ekfb_ctx {
     size_t flush_bytes = 0;
     bool force_generic = false;
     int downdate_variant = 0;
-    int downdate_small_k = 128;   // updates with at most this many rows run the downdate as 64x64 tiles only
+    // updates with at most this many rows run the downdate as 64x64 tiles, 4 CTAs per SM.  Measured on B200 (profiles/
+    // r01_downdate_sweep.txt) that variant wins at every k and n tried (16 resident warps hide the tile read-modify-write
+    // and the operand ring better than 8 warps of one 128x128 CTA), so it is the default for all k; option 4 lowers it.
+    int downdate_small_k = 1 << 30;
     int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches
     bool dd_timing = false;
     std::vector<cudaEvent_t> dd_ev;   // pairs
     size_t dd_used = 0;               // events used
     double dd_flops = 0., dd_bytes = 0.;
+    bool map_ready = false;           // map-management buffers are allocated on first use
+    uint8_t* mask2 = nullptr;         // new-feature mask (E/DetectNewImageFeatures.cpp:101-122), built by ekfb_map_management
+    bool mask2_valid = false;
 };
 
 template <typename T>
@@ -483,7 +490,7 @@ extern "C" int ekfb_match(ekfb_handle c)
     CK(cudaMemsetAsync(v.mask, 0, (size_t)c->F * v.W * v.H, c->stream));
     if (N > 0) {
         const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
-        k_mask_raster<<<dim3(cdiv(N, 4), c->F), 128, rasterSmem, c->stream>>>(v);
+        k_mask_raster<<<dim3(cdiv(N, 4), c->F), 128, rasterSmem, c->stream>>>(v, v.mask, v.maxAxes, 255);
         count_launch(c);
         if (Kp > 0) {
             k_kp_mask<<<dim3(cdiv(Kp, 256), c->F), 256, 0, c->stream>>>(v);
@@ -532,8 +539,7 @@ static int launch_downdate(ekfb_ctx* c, int n)
     if (c->downdate_variant == 1)
         k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
     else if (kMax <= c->downdate_small_k) {
-        // few update rows (the high-innovation update): the pass is bound by reading and writing P, not by the tensor pipe;
-        // 64x64 tiles, four CTAs per SM, hide the latency of the read-modify-write better than one 128x128 CTA per SM
+        // 64x64 tiles, four CTAs per SM (the default at every k, see downdate_small_k)
         k_downdate_small<<<dim3(nI * (nI + 1) / 2 * 4, c->F), 128, kSmallSmemBytes, c->stream>>>(v, 0);
     } else {
         // 1-D grid over the T lower 128x128 tiles.  Single filter: if T is just above a multiple of the SM
@@ -703,6 +709,181 @@ extern "C" int ekfb_update_map_features(ekfb_handle c)
     k_update_map_features<<<dim3(cdiv(N, 256), c->F), 256, 0, c->stream>>>(c->v);
     count_launch(c);
     CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+// ---- map management (kernels in ekf_map.cuh) ----------------------------------------------
+static int ensure_map_buffers(ekfb_ctx* c)
+{
+    if (c->map_ready) return EKFB_OK;
+    DevView& v = c->v;
+    const size_t F = c->F, N = c->Nmax;
+    ALLOC(v.P2, F * c->nmax * c->ld); ALLOC(v.x2, F * c->ld);
+    ALLOC(v.ftype2, F * N); ALLOC(v.foff2, F * N); ALLOC(v.desc2, F * N * 32); ALLOC(v.tpred2, F * N); ALLOC(v.tmatch2, F * N);
+    ALLOC(v.rowsrc, F * c->nmax); ALLOC(v.mapflag, F * N); ALLOC(v.convJ, F * 18);
+    ALLOC(v.addJ, N * kAddJ); ALLOC(v.adduv, N * 2); ALLOC(v.adddesc, N * 32);
+    ALLOC(c->mask2, F * (size_t)v.W * v.H);
+    c->map_ready = true;
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_map_management(ekfb_handle c, const ekfb_map_policy* pol, ekfb_map_result* out)
+{
+    REQUIRE(c && pol, "null argument");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_map_buffers(c);
+    if (rc != EKFB_OK) return rc;
+    GroupScope gs(c, G_MISC);
+    DevView& v = c->v;
+    MapPolicy mp;
+    mp.min_matches = pol->min_matches_per_image; mp.max_features = pol->max_map_features_count;
+    mp.max_size = pol->max_map_size; mp.always_remove_unseen = pol->always_remove_unseen;
+    mp.good_pct = pol->good_feature_matching_percent; mp.linearity_thr = pol->linearity_index_threshold;
+    k_map_plan<<<c->F, 256, 0, c->stream>>>(v, mp);
+    count_launch(c);
+    CK(cudaGetLastError());
+    if ((rc = read_dims(c)) != EKFB_OK) return rc;
+    bool changed = false, needNew = false;
+    int nnMax = 13;
+    for (int f = 0; f < c->F; ++f) {
+        const int* d = c->h_dims + (size_t)f * D_STRIDE;
+        changed = changed || d[D_MAP_CHANGED];
+        needNew = needNew || d[D_MAP_NEEDED] > 0;
+        nnMax = std::max(nnMax, d[D_MAP_NEW_N]);
+    }
+    c->mask2_valid = false;
+    if (needNew && max_of(c->hN) > 0) {
+        // buildImageMask (E/DetectNewImageFeatures.cpp:101-122): white image, every prediction's ellipse in black.  Built
+        // here because the predictions are indexed by the feature numbering of this frame's measurement.
+        CK(cudaMemsetAsync(c->mask2, 255, (size_t)c->F * v.W * v.H, c->stream));
+        const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
+        k_mask_raster<<<dim3(cdiv(max_of(c->hN), 4), c->F), 128, rasterSmem, c->stream>>>(v, c->mask2, 2 * (v.W + v.H), 0);
+        count_launch(c);
+        c->mask2_valid = true;
+    } else if (needNew) {
+        CK(cudaMemsetAsync(c->mask2, 255, (size_t)c->F * v.W * v.H, c->stream));
+        c->mask2_valid = true;
+    }
+    if (changed) {
+        k_map_gather<<<dim3(cdiv(nnMax, 32), cdiv(nnMax, 32), c->F), dim3(32, 8), 0, c->stream>>>(v);
+        k_map_convert<<<dim3(cdiv(nnMax, 256), c->F), 256, 0, c->stream>>>(v);
+        k_map_commit<<<cdiv(c->F, 128), 128, 0, c->stream>>>(v);
+        count_launch(c, 3);
+        CK(cudaGetLastError());
+        std::swap(v.P, v.P2); std::swap(v.x, v.x2); std::swap(v.ftype, v.ftype2); std::swap(v.foff, v.foff2);
+        std::swap(v.desc, v.desc2); std::swap(v.tpred, v.tpred2); std::swap(v.tmatch, v.tmatch2);
+    }
+    for (int f = 0; f < c->F; ++f) {
+        int* d = c->h_dims + (size_t)f * D_STRIDE;
+        if (changed) {
+            c->hn[f] = d[D_N_STATE] = d[D_MAP_NEW_N];
+            c->hN[f] = d[D_N_FEAT] = d[D_MAP_NEW_NF];
+        }
+        if (out) {
+            out[f].n = c->hn[f]; out[f].n_features = c->hN[f]; out[f].n_removed_bad = d[D_MAP_NBAD];
+            out[f].n_removed_unseen = d[D_MAP_NUNSEEN]; out[f].converted = d[D_MAP_CONVERT];
+            out[f].new_features_needed = d[D_MAP_NEEDED];
+        }
+    }
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_removed_flags(ekfb_handle c, int f, int n_features_before, uint8_t* flags)
+{
+    REQUIRE(c && flags, "null argument");
+    REQUIRE(f >= 0 && f < c->F && n_features_before >= 0 && n_features_before <= c->Nmax, "bad filter index or count");
+    REQUIRE(c->map_ready, "ekfb_map_management has not been called");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(flags, c->v.mapflag + (size_t)f * c->Nmax, n_features_before, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_add_features(ekfb_handle c, int f, int count, const double* uv, const uint8_t* desc)
+{
+    REQUIRE(c && (count == 0 || (uv && desc)), "null argument");
+    REQUIRE(f >= 0 && f < c->F && count >= 0, "bad filter index or count");
+    if (count == 0) return EKFB_OK;
+    const int n0 = c->hn[f], N0 = c->hN[f];
+    if (N0 + count > c->Nmax || n0 + 6 * count > c->nmax) {
+        g_err = "new features exceed the capacity reserved by ekfb_create";
+        return EKFB_ERR_CAPACITY;
+    }
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_map_buffers(c);
+    if (rc != EKFB_OK) return rc;
+    GroupScope gs(c, G_MISC);
+    DevView& v = c->v;
+    CK(cudaMemcpyAsync(v.adduv, uv, sizeof(double) * 2 * count, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(v.adddesc, desc, (size_t)32 * count, cudaMemcpyHostToDevice, c->stream));
+    k_add_prepare<<<count, 32, 0, c->stream>>>(v, f, n0, N0, count, c->prm.pixel_error_x, c->prm.pixel_error_y,
+                                                c->prm.init_inv_depth_rho, c->prm.inverse_depth_rho_sd);
+    k_add_cov<<<dim3(cdiv(n0 + 6 * count, 256), count), 256, 0, c->stream>>>(v, f, n0, count);
+    count_launch(c, 2);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));   // uv / desc may be pageable
+    c->hn[f] = n0 + 6 * count;
+    c->hN[f] = N0 + count;
+    c->h_dims[(size_t)f * D_STRIDE + D_N_STATE] = c->hn[f];
+    c->h_dims[(size_t)f * D_STRIDE + D_N_FEAT] = c->hN[f];
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_feature_layout(ekfb_handle c, int f, int32_t* type, int32_t* off)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    const int N = c->hN[f];
+    if (type) CK(cudaMemcpyAsync(type, c->v.ftype + (size_t)f * c->Nmax, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+    if (off) CK(cudaMemcpyAsync(off, c->v.foff + (size_t)f * c->Nmax, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_set_hit_counters(ekfb_handle c, int f, const int32_t* tp, const int32_t* tm)
+{
+    REQUIRE(c && tp && tm, "null argument");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    const int N = c->hN[f];
+    CK(cudaMemcpyAsync(c->v.tpred + (size_t)f * c->Nmax, tp, sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v.tmatch + (size_t)f * c->Nmax, tm, sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_new_feature_mask(ekfb_handle c, int f, uint8_t* mask)
+{
+    REQUIRE(c && mask, "null argument");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    REQUIRE(c->map_ready && c->mask2_valid, "no new-feature mask: the last ekfb_map_management asked for no new features");
+    CK(cudaSetDevice(c->device));
+    const size_t wh = (size_t)c->v.W * c->v.H;
+    CK(cudaMemcpyAsync(mask, c->mask2 + (size_t)f * wh, wh, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_raster_ellipse(ekfb_handle c, int W, int H, double cx, double cy, const double* S, int max_axes, int value,
+                                   uint8_t* img)
+{
+    REQUIRE(c && S && img && W > 0 && H > 0, "bad argument");
+    CK(cudaSetDevice(c->device));
+    uint8_t* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)W * H));
+    const int smem = (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)H);
+    cudaError_t e = cudaMemcpyAsync(d, img, (size_t)W * H, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_raster_one, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) {
+        k_raster_one<<<1, 32, smem, c->stream>>>(d, W, H, cx, cy, S[0], S[1], S[2], S[3], max_axes, value);
+        count_launch(c);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(img, d, (size_t)W * H, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    CK(e);
     return EKFB_OK;
 }
 

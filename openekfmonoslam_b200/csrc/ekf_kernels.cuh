@@ -23,7 +23,10 @@ namespace ekf {
 enum DimSlot {
     D_N_STATE = 0, D_N_FEAT = 1, D_N_KP = 2, D_N_PRED = 3, D_N_MATCH = 4, D_N_HYP = 5, D_BEST_HYP = 6, D_N_INL = 7,
     D_N_OUT = 8, D_N_RESC = 9, D_STATUS = 10, D_RANSAC_DONE = 11, D_RANSAC_NEXT = 12, D_RANSAC_CAP = 13,
-    D_BEST_COUNT = 14, D_ULIST = 15, D_N_PRED2 = 16, D_STRIDE = 32
+    D_BEST_COUNT = 14, D_ULIST = 15, D_N_PRED2 = 16,
+    // map management plan (ekf_map.cuh)
+    D_MAP_CHANGED = 17, D_MAP_NEW_N = 18, D_MAP_NEW_NF = 19, D_MAP_CONVERT = 20, D_MAP_NEEDED = 21, D_MAP_NBAD = 22,
+    D_MAP_NUNSEEN = 23, D_MAP_CONV_OLDOFF = 24, D_MAP_CONV_NEWOFF = 25, D_STRIDE = 32
 };
 
 struct DevView {
@@ -39,6 +42,10 @@ struct DevView {
     const float* const* kpxy; const uint8_t* const* kpdesc; uint8_t* kpok; uint8_t* mask;
     int* hypcount; uint32_t* hypsup;
     double* Bu; double* S; double* Sf; double* dx; double* Jq; double* Uinv; long long* dbg;
+    // map management (ekf_map.cuh): second copies the compaction writes into (swapped with the live ones afterwards),
+    // new row -> old row table, per-feature removal flags, conversion Jacobian, add-feature staging
+    double* P2; double* x2; int* ftype2; int* foff2; uint8_t* desc2; int* tpred2; int* tmatch2;
+    int* rowsrc; uint8_t* mapflag; double* convJ; double* addJ; double* adduv; uint8_t* adddesc;
 };
 
 __device__ __forceinline__ int* fdims(const DevView& v, int f) { return v.dims + (size_t)f * D_STRIDE; }
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(256) k_measure(DevView v, int mode)
 // M1(1): mask = union of filled gate ellipses (E/Matching.cpp:193-202 -> Gui/Draw.cpp:42-64).
 // One warp per predicted feature; dynamic smem: per warp a RasterScratch and 2*H span ints.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_mask_raster(DevView v)
+__global__ void __launch_bounds__(128) k_mask_raster(DevView v, uint8_t* maskBase, int maxAxes, int val)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.y;
@@ -221,10 +228,10 @@ __global__ void __launch_bounds__(128) k_mask_raster(DevView v)
     // cv::Point2d -> Point2f -> Point (truncation); Size2f -> MIN(axis, maxAxes) -> int (truncation)
     const float cxf = (float)v.h[fj * 2], cyf = (float)v.h[fj * 2 + 1];
     const int icx = (int)cxf, icy = (int)cyf;
-    const float mw = fminf(v.ellax[fj * 2], (float)v.maxAxes), mh = fminf(v.ellax[fj * 2 + 1], (float)v.maxAxes);
+    const float mw = fminf(v.ellax[fj * 2], (float)maxAxes), mh = fminf(v.ellax[fj * 2 + 1], (float)maxAxes);
     const int iw = (int)mw, ih = (int)mh;
     const double angDeg = v.ellang[fj] * 180.0 / kPiTrunc;
-    raster_ellipse_warp(v.mask + (size_t)f * v.W * v.H, v.W, v.H, icx, icy, iw, ih, angDeg, sc, spans, lane);
+    raster_ellipse_warp(maskBase + (size_t)f * v.W * v.H, v.W, v.H, icx, icy, iw, ih, angDeg, sc, spans, lane, (uint8_t)val);
 }
 
 // keypoint survives the detector mask iff mask[(int)(y+0.5f)][(int)(x+0.5f)] != 0

@@ -43,9 +43,9 @@ __device__ __forceinline__ float sin_deg(int k)  // k in [0, 450]
 
 struct RasterPt { long long x, y; };
 
-__device__ __forceinline__ void put_px(uint8_t* img, int W, int H, long long x, long long y)
+__device__ __forceinline__ void put_px(uint8_t* img, int W, int H, long long x, long long y, uint8_t val)
 {
-    if (0 <= x && x < W && 0 <= y && y < H) img[(size_t)y * W + x] = 255;
+    if (0 <= x && x < W && 0 <= y && y < H) img[(size_t)y * W + x] = val;
 }
 
 // fixed-point clip of a segment to [0, W<<16) x [0, H<<16) (OpenCV clipLine on scaled coordinates)
@@ -88,7 +88,7 @@ __device__ inline bool clip_segment(long long width, long long height, RasterPt&
 }
 
 // outline edge: fixed-point DDA (OpenCV Line2 for 1-byte pixels)
-__device__ inline void draw_edge(uint8_t* img, int W, int H, RasterPt p1, RasterPt p2)
+__device__ inline void draw_edge(uint8_t* img, int W, int H, RasterPt p1, RasterPt p2, uint8_t val)
 {
     if (!clip_segment((long long)W << kXYShift, (long long)H << kXYShift, p1, p2)) return;
     long long dx = p2.x - p1.x, dy = p2.y - p1.y;
@@ -113,11 +113,11 @@ __device__ inline void draw_edge(uint8_t* img, int W, int H, RasterPt p1, Raster
     }
     p1.x += (kXYOne >> 1);
     p1.y += (kXYOne >> 1);
-    put_px(img, W, H, (p2.x + (kXYOne >> 1)) >> kXYShift, (p2.y + (kXYOne >> 1)) >> kXYShift);
+    put_px(img, W, H, (p2.x + (kXYOne >> 1)) >> kXYShift, (p2.y + (kXYOne >> 1)) >> kXYShift, val);
     if (ax > ay) {
         p1.x >>= kXYShift;
         while (ecount >= 0) {
-            put_px(img, W, H, p1.x, p1.y >> kXYShift);
+            put_px(img, W, H, p1.x, p1.y >> kXYShift, val);
             p1.x++;
             p1.y += y_step;
             ecount--;
@@ -125,7 +125,7 @@ __device__ inline void draw_edge(uint8_t* img, int W, int H, RasterPt p1, Raster
     } else {
         p1.y >>= kXYShift;
         while (ecount >= 0) {
-            put_px(img, W, H, p1.x >> kXYShift, p1.y);
+            put_px(img, W, H, p1.x >> kXYShift, p1.y, val);
             p1.x += x_step;
             p1.y++;
             ecount--;
@@ -142,8 +142,9 @@ struct RasterScratch {
 };
 
 // Rasterise one ellipse with the whole warp.  `spans` is per-warp shared scratch of 2*H ints.
+// `val` is the colour: 255 for the matching mask, 0 for the new-feature mask (E/DetectNewImageFeatures.cpp:115-121).
 __device__ inline void raster_ellipse_warp(uint8_t* img, int W, int H, int cx, int cy, int aw, int ah, double angle_deg,
-                                           RasterScratch* sc, int* spans, int lane)
+                                           RasterScratch* sc, int* spans, int lane, uint8_t val = 255)
 {
     int angle = __double2int_rn(angle_deg);
     const long long ctrx = (long long)cx << kXYShift, ctry = (long long)cy << kXYShift;
@@ -187,7 +188,7 @@ __device__ inline void raster_ellipse_warp(uint8_t* img, int W, int H, int cx, i
     __syncwarp();
     const int npts = sc->nv;
     // outline: edge e joins v[e-1] (v[npts-1] for e = 0) and v[e]
-    for (int e = lane; e < npts; e += 32) draw_edge(img, W, H, sc->v[e == 0 ? npts - 1 : e - 1], sc->v[e]);
+    for (int e = lane; e < npts; e += 32) draw_edge(img, W, H, sc->v[e == 0 ? npts - 1 : e - 1], sc->v[e], val);
 
     if (lane == 0) {  // convex scanline walk -> spans
         sc->y_first = 0;
@@ -266,7 +267,7 @@ __device__ inline void raster_ellipse_warp(uint8_t* img, int W, int H, int cx, i
     const int y0 = sc->y_first, y1 = sc->y_last;
     for (int y = y0; y <= y1; ++y) {
         const int xx1 = spans[2 * y], xx2 = spans[2 * y + 1];
-        for (int x = xx1 + lane; x <= xx2; x += 32) img[(size_t)y * W + x] = 255;
+        for (int x = xx1 + lane; x <= xx2; x += 32) img[(size_t)y * W + x] = val;
     }
     __syncwarp();
 }

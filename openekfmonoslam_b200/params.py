@@ -34,6 +34,27 @@ class EkfParams(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+
+class MapPolicy(ctypes.Structure):
+    """ekfb_map_policy (include/ekf_b200.h): the map-management fields of ExtendedKalmanFilterParameters
+    (.../ExtendedKalmanFilterParameters.h:37-76).  Defaults = experiments/s3/config.yml."""
+    _fields_ = [("min_matches_per_image", ctypes.c_int32), ("max_map_features_count", ctypes.c_int32),
+                ("max_map_size", ctypes.c_int32), ("always_remove_unseen", ctypes.c_int32),
+                ("good_feature_matching_percent", ctypes.c_double), ("linearity_index_threshold", ctypes.c_double)]
+
+    def __init__(self, min_matches_per_image=60, max_map_features_count=0, max_map_size=240, always_remove_unseen=0,
+                 good_feature_matching_percent=0.5, linearity_index_threshold=0.1):
+        super().__init__(min_matches_per_image, max_map_features_count, max_map_size, always_remove_unseen,
+                         good_feature_matching_percent, linearity_index_threshold)
+
+
+class MapResult(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("n", "n_features", "n_removed_bad", "n_removed_unseen", "converted",
+                                              "new_features_needed")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
 # EKF-section defaults of experiments/s3/config.yml:9-37
 _S3_EKF = dict(init_inv_depth_rho=1.0, init_linear_accel_sd=0.001, init_angular_accel_sd=0.004,
                linear_accel_sd=0.0007, angular_accel_sd=0.002, inverse_depth_rho_sd=1.0,

@@ -1646,6 +1646,150 @@ void orc_remove_features(orc_filter* f, const uint8_t* flags)  // MapManagement.
     s.features = nf;
 }
 
+// removeBadMapFeatures (MapManagement.cpp:279-307): float ratio timesMatched / timesPredicted below the threshold.
+// 0/0 is NaN and x/0 is inf, both compare false: a feature never predicted is never "bad".
+static void badFeatureFlags(const orc_filter* f, double goodPct, std::vector<uint8_t>& flags)
+{
+    const State& s = f->state;
+    flags.assign(s.features.size(), 0);
+    for (size_t i = 0; i < s.features.size(); ++i) {
+        float pct = static_cast<float>(s.features[i].timesMatched) / static_cast<float>(s.features[i].timesPredicted);
+        if (pct < goodPct) flags[i] = 1;
+    }
+}
+
+// computeLinearityIndex (MapManagement.cpp:311-341)
+static double linearityIndex(const orc_filter* f, const Feature& mf)
+{
+    const State& s = f->state;
+    int idx = mf.covPos + mf.dim - 1;
+    double invDepthError = sqrt(f->P(idx, idx));
+    double invDepthValue = mf.position[mf.dim - 1];
+    double sigma = invDepthError / (invDepthValue * invDepthValue);
+    double xyz[3], m[3];
+    makeDirectionalVector(mf.position[3], mf.position[4], m);       // changeInverseDepthToDepth, CommonFunctions.cpp
+    for (int i = 0; i < 3; ++i) xyz[i] = mf.position[i] + m[i] / mf.position[5];
+    double toCam[3], toFirst[3];
+    for (int i = 0; i < 3; ++i) {
+        toCam[i] = xyz[i] - s.position[i];
+        toFirst[i] = xyz[i] - mf.position[i];
+    }
+    double dot = 0.0L;
+    for (int i = 0; i < 3; ++i) dot += toCam[i] * toFirst[i];
+    double dFirst = sqrt(toFirst[0] * toFirst[0] + toFirst[1] * toFirst[1] + toFirst[2] * toFirst[2]);
+    double dCam = sqrt(toCam[0] * toCam[0] + toCam[1] * toCam[1] + toCam[2] * toCam[2]);
+    double cosAlpha = dot / (dFirst * dCam);
+    return 4.0L * sigma * cosAlpha / dCam;
+}
+
+// convertToDepth (MapManagement.cpp:345-497): 6 -> 3 rows/columns with the 3x6 Jacobian of (x,y,z) + m(theta,phi)/rho
+static void convertToDepth(orc_filter* f, int fi)
+{
+    State& s = f->state;
+    Feature& mf = s.features[fi];
+    double theta = mf.position[3], phi = mf.position[4], rho = mf.position[5];
+    double mi[3], xyz[3];
+    makeDirectionalVector(theta, phi, mi);
+    for (int i = 0; i < 3; ++i) xyz[i] = mf.position[i] + mi[i] / rho;
+    Mat J(3, 6);
+    J(0, 0) = J(1, 1) = J(2, 2) = 1.0L;
+    J(0, 3) = cos(phi) * cos(theta) / rho;  J(1, 3) = 0.0;                J(2, 3) = -cos(phi) * sin(theta) / rho;
+    J(0, 4) = -sin(phi) * sin(theta) / rho; J(1, 4) = -cos(phi) / rho;    J(2, 4) = -sin(phi) * cos(theta) / rho;
+    for (int i = 0; i < 3; ++i) J(i, 5) = -mi[i] / (rho * rho);
+    const int n = f->P.r, c0 = mf.covPos, c1 = c0 + 6;
+    Mat P6n = block(f->P, c0, c1, 0, n);
+    Mat sub3n = mul(J, P6n);                                   // 3 x n
+    Mat sub36 = block(sub3n, 0, 3, c0, c1);
+    Mat Jt = transpose(J);
+    Mat d33 = mul(sub36, Jt);
+    Mat colsK = mul(block(f->P, 0, c0, c0, c1), Jt);           // k x 3
+    Mat colsL = (c1 < n) ? mul(block(f->P, c1, n, c0, c1), Jt) : Mat(0, 3);
+    Mat NP(n - 3, n - 3);
+    auto src = [&](int i) { return i < c0 + 3 ? i : i + 3; };  // new index -> old index (outside the feature block)
+    for (int i = 0; i < n - 3; ++i)
+        for (int j = 0; j < n - 3; ++j) {
+            const bool fi_ = (i >= c0 && i < c0 + 3), fj_ = (j >= c0 && j < c0 + 3);
+            double val;
+            if (fi_ && fj_) val = d33(i - c0, j - c0);
+            else if (fi_) val = sub3n(i - c0, src(j));
+            else if (fj_) val = (i < c0) ? colsK(i, j - c0) : colsL(src(i) - c1, j - c0);
+            else val = f->P(src(i), src(j));
+            NP(i, j) = val;
+        }
+    f->P = NP;
+    mf.dim = 3;
+    mf.type = TYPE_DEPTH;
+    for (int i = 0; i < 3; ++i) mf.position[i] = xyz[i];
+    for (int i = 3; i < 6; ++i) mf.position[i] = 0.0;
+    for (Feature& o : s.features)
+        if (o.covPos > c0) o.covPos = o.covPos - 6 + 3;
+}
+
+void orc_set_hit_counters(orc_filter* f, const int32_t* tp, const int32_t* tm)
+{
+    for (size_t i = 0; i < f->state.features.size(); ++i) {
+        f->state.features[i].timesPredicted = (unsigned)tp[i];
+        f->state.features[i].timesMatched = (unsigned)tm[i];
+    }
+}
+
+int32_t orc_remove_bad_features(orc_filter* f, double goodPct, uint8_t* removed)  // MapManagement.cpp:279-307
+{
+    std::vector<uint8_t> flags;
+    badFeatureFlags(f, goodPct, flags);
+    int32_t c = 0;
+    for (size_t i = 0; i < flags.size(); ++i) {
+        c += flags[i];
+        if (removed) removed[i] = flags[i];
+    }
+    if (c) orc_remove_features(f, flags.data());
+    return c;
+}
+
+int32_t orc_convert_features(orc_filter* f, double threshold)  // MapManagement.cpp:501-524: at most ONE per call
+{
+    State& s = f->state;
+    for (size_t i = 0; i < s.features.size(); ++i) {
+        if (s.features[i].type != TYPE_INVERSE_DEPTH) continue;
+        if (linearityIndex(f, s.features[i]) < threshold) {
+            convertToDepth(f, (int)i);
+            return (int32_t)i;
+        }
+    }
+    return -1;
+}
+
+// EKF.cpp:575-592 up to (not including) the detection of new features.  removed[i] for the N features present
+// before the call: 0 kept, 1 removed as bad, 2 removed as unseen; *converted = index (in the NEW numbering) of the
+// feature converted to XYZ or -1.  Returns newFeaturesNeededCount.
+int32_t orc_map_management(orc_filter* f, const orc_map_policy* pol, uint8_t* removed, int32_t* converted)
+{
+    State& s = f->state;
+    const size_t N0 = s.features.size();
+    int needed = pol->min_matches_per_image - (int)(f->inlierIdx.size() + f->rescuedIdx.size());
+    std::vector<uint8_t> rem(N0, 0), bad;
+    badFeatureFlags(f, pol->good_feature_matching_percent, bad);
+    std::vector<int> alive;                  // old index of every surviving feature
+    for (size_t i = 0; i < N0; ++i)
+        if (bad[i]) rem[i] = 1; else alive.push_back((int)i);
+    bool anyBad = alive.size() != N0;
+    if (anyBad) orc_remove_features(f, bad.data());
+    if (needed > 0 && (pol->always_remove_unseen ||
+                       (pol->max_map_features_count > 0 && (int)s.features.size() + needed > pol->max_map_features_count) ||
+                       (pol->max_map_size > 0 && f->P.r + needed * 6 > pol->max_map_size))) {
+        std::vector<uint8_t> un(s.features.size(), 0);
+        bool any = false;
+        for (int oldIdx : f->unseen)          // unseen features that survived removeBadMapFeatures
+            for (size_t a = 0; a < alive.size(); ++a)
+                if (alive[a] == oldIdx) { un[a] = 1; rem[oldIdx] = 2; any = true; }
+        if (any) orc_remove_features(f, un.data());
+    }
+    int32_t conv = orc_convert_features(f, pol->linearity_index_threshold);
+    if (removed) std::memcpy(removed, rem.data(), N0);
+    if (converted) *converted = conv;
+    return needed;
+}
+
 void orc_dims(const orc_filter* f, int32_t* n, int32_t* nf)
 {
     *n = f->P.r;

@@ -98,6 +98,27 @@ class OracleFilter:
         self.L.orc_get_features(self.h, _p(t), _p(o), _p(d), _p(tp), _p(tm))
         return dict(type=t, off=o, desc=d, times_predicted=tp, times_matched=tm)
 
+    # ---- map management (E/EKF.cpp:575-592, E/MapManagement.cpp) ----
+    def set_hit_counters(self, tp, tm):
+        tp = np.ascontiguousarray(tp, np.int32); tm = np.ascontiguousarray(tm, np.int32)
+        self.L.orc_set_hit_counters(self.h, _p(tp), _p(tm))
+
+    def map_management(self, policy):
+        """policy: any ctypes struct with the layout of orc_map_policy.  Returns (needed, removed flags, converted)"""
+        _, N = self.dims()
+        rem = np.zeros(max(N, 1), np.uint8)
+        conv = ctypes.c_int32(-1)
+        self.L.orc_map_management.restype = ctypes.c_int32
+        needed = self.L.orc_map_management(self.h, ctypes.byref(policy), _p(rem), ctypes.byref(conv))
+        return needed, rem[:N], conv.value
+
+    def remove_bad_features(self, good_pct):
+        return self.L.orc_remove_bad_features(self.h, ctypes.c_double(good_pct), None)
+
+    def convert_features(self, threshold):
+        self.L.orc_convert_features.restype = ctypes.c_int32
+        return self.L.orc_convert_features(self.h, ctypes.c_double(threshold))
+
     # ---- phases ----
     def predict(self):
         self.L.orc_predict(self.h)

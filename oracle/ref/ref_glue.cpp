@@ -21,6 +21,7 @@
 #include "../../../reference/kalmanFilter/modules/1PointRansacEKF/Update.h"
 #include "../../../reference/kalmanFilter/modules/1PointRansacEKF/MapManagement.h"
 #include "../../../reference/kalmanFilter/modules/1PointRansacEKF/AddMapFeature.h"
+#include "../../../reference/kalmanFilter/modules/1PointRansacEKF/DetectNewImageFeatures.h"
 #include "../../../reference/kalmanFilter/modules/1PointRansacEKF/CommonFunctions.h"
 #include "../../../reference/kalmanFilter/modules/Core/EKFMath.h"
 
@@ -215,6 +216,79 @@ void ref_add_feature(ref_filter* f, const double* uv, const uint8_t* desc32)
     std::memcpy(d.ptr<uchar>(0), desc32, 32);
     ImageFeatureMeasurement m(uv, d);
     addFeatureToStateAndCovariance(&m, f->ekf->state, f->ekf->stateCovarianceMatrix);
+}
+
+// ---- map management: the reference's own functions, glued like EKF.cpp:575-592 ----
+void ref_set_policy(ref_filter* f, const orc_map_policy* pol, int32_t map_management_frequency)
+{
+    ExtendedKalmanFilterParameters& e = f->ekfp;
+    e.minMatchesPerImage = pol->min_matches_per_image;
+    e.maxMapFeaturesCount = pol->max_map_features_count;
+    e.maxMapSize = pol->max_map_size;
+    e.alwaysRemoveUnseenMapFeatures = pol->always_remove_unseen != 0;
+    e.goodFeatureMatchingPercent = pol->good_feature_matching_percent;
+    e.inverseDepthLinearityIndexThreshold = pol->linearity_index_threshold;
+    e.mapManagementFrequency = map_management_frequency;   // > 0: ref_step runs the reference's whole map management
+}
+
+void ref_get_layout(const ref_filter* f, int32_t* type, int32_t* off)
+{
+    const State& s = f->ekf->state;
+    for (size_t i = 0; i < s.mapFeatures.size(); ++i) {
+        type[i] = (int32_t)s.mapFeatures[i]->featureType;
+        off[i] = s.mapFeatures[i]->covarianceMatrixPos;
+    }
+}
+
+void ref_set_counters(ref_filter* f, const int32_t* tp, const int32_t* tm)
+{
+    State& s = f->ekf->state;
+    for (size_t i = 0; i < s.mapFeatures.size(); ++i) {
+        s.mapFeatures[i]->timesPredicted = tp[i];
+        s.mapFeatures[i]->timesMatched = tm[i];
+    }
+}
+
+// after ref_measure .. ref_update_map_features of the same frame; returns newFeaturesNeededCount
+int32_t ref_map_management(ref_filter* f)
+{
+    ExtendedKalmanFilterParameters* p = &f->ekfp;
+    State& state = f->ekf->state;
+    Matd& P = f->ekf->stateCovarianceMatrix;
+    int needed = p->minMatchesPerImage - static_cast<int>(f->inlierMatches.size() + f->rescuedMatches.size());
+    removeBadMapFeatures(state, P);
+    if (needed > 0 && (p->alwaysRemoveUnseenMapFeatures ||
+                       (p->maxMapFeaturesCount > 0 && state.mapFeatures.size() + needed > p->maxMapFeaturesCount) ||
+                       (p->maxMapSize > 0 && P.rows + needed * 6 > p->maxMapSize)))
+        removeFeaturesFromStateAndCovariance(f->unseen, state, P);
+    convertMapFeaturesInverseDepthToDepth(state, P);
+    return needed;
+}
+
+int32_t ref_remove_bad(ref_filter* f)
+{
+    const size_t before = f->ekf->state.mapFeatures.size();
+    removeBadMapFeatures(f->ekf->state, f->ekf->stateCovarianceMatrix);
+    return (int32_t)(before - f->ekf->state.mapFeatures.size());
+}
+
+void ref_convert(ref_filter* f) { convertMapFeaturesInverseDepthToDepth(f->ekf->state, f->ekf->stateCovarianceMatrix); }
+
+// detectNewImageFeatures (DetectNewImageFeatures.cpp:321-419) on the injected keypoints, with the predictions of the
+// last ref_measure; consumes libc rand() exactly as the reference does.  out_kp = indices into the injected keypoints.
+int32_t ref_detect_new(ref_filter* f, const float* kp, const uint8_t* desc, int32_t nkp, int32_t max_new, double* out_uv,
+                       uint8_t* out_desc)
+{
+    inject(f, kp, desc, nkp);
+    VectorImageFeatureMeasurement found;
+    detectNewImageFeatures(f->image, f->preds, (uint)max_new, found);
+    for (size_t i = 0; i < found.size(); ++i) {
+        out_uv[2 * i] = found[i]->imagePos[0];
+        out_uv[2 * i + 1] = found[i]->imagePos[1];
+        std::memcpy(out_desc + i * 32, found[i]->descriptorData.ptr<uchar>(0), 32);
+        delete found[i];
+    }
+    return (int32_t)found.size();
 }
 
 void ref_init(ref_filter* f)

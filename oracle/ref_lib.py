@@ -83,6 +83,36 @@ class ReferenceFilter:
         self.L.ref_get_features(self.h, _p(d), _p(tp), _p(tm))
         return dict(desc=d, times_predicted=tp, times_matched=tm)
 
+    # ---- map management: the reference's own functions (E/MapManagement.cpp, E/DetectNewImageFeatures.cpp) ----
+    def set_policy(self, policy, map_management_frequency=0):
+        self.L.ref_set_policy(self.h, ctypes.byref(policy), ctypes.c_int32(map_management_frequency))
+
+    def get_layout(self):
+        _, N = self.dims()
+        t = np.zeros(max(N, 1), np.int32); o = np.zeros(max(N, 1), np.int32)
+        self.L.ref_get_layout(self.h, _p(t), _p(o))
+        return t[:N], o[:N]
+
+    def set_hit_counters(self, tp, tm):
+        tp = np.ascontiguousarray(tp, np.int32); tm = np.ascontiguousarray(tm, np.int32)
+        self.L.ref_set_counters(self.h, _p(tp), _p(tm))
+
+    def map_management(self):
+        self.L.ref_map_management.restype = ctypes.c_int32
+        return self.L.ref_map_management(self.h)
+
+    def remove_bad(self):
+        return self.L.ref_remove_bad(self.h)
+
+    def convert(self):
+        self.L.ref_convert(self.h)
+
+    def detect_new(self, kp_xy, kp_desc, max_new):
+        uv = np.zeros((max(max_new, 1), 2)); ds = np.zeros((max(max_new, 1), 32), np.uint8)
+        self.L.ref_detect_new.restype = ctypes.c_int32
+        k = self.L.ref_detect_new(self.h, *self._kp(kp_xy, kp_desc), ctypes.c_int32(max_new), _p(uv), _p(ds))
+        return uv[:k], ds[:k]
+
     def _kp(self, kp_xy, kp_desc):
         self._kpxy = np.ascontiguousarray(kp_xy, np.float32)
         self._kpds = np.ascontiguousarray(kp_desc, np.uint8)   # must outlive the frame (descriptors are read lazily)

@@ -124,3 +124,64 @@ def test_every_phase_mixed_xyz_features():
     for t in range(4, 9):
         phase_by_phase(sc, o, r, t, tol=1e-9)
     r.close()
+
+
+# ---- map management: the oracle's restatement against the reference's own MapManagement.cpp ----
+def map_scenario(N=40, behind=(5, 17, 30)):
+    """A map whose features `behind` lie behind the camera (never predicted -> "unseen")."""
+    from openekfmonoslam_b200.params import MapPolicy
+    sc, o, r, (x, P, ft, fo, desc, uv0) = pair(N)
+    x = x.copy()
+    for i in behind:
+        x[fo[i] + 3] += np.pi
+    o.set_state(x, P, ft, fo, desc)
+    r.set_state(x, P, ft, fo, desc)
+    return sc, o, r, MapPolicy
+
+
+def same_map(o, r, what, tol=TOL):
+    assert o.dims() == r.dims(), what
+    same_state(o, r, what, tol)
+    fo_, fr_ = o.get_features(), r.get_features()
+    t, off = r.get_layout()
+    assert np.array_equal(fo_["type"], t) and np.array_equal(fo_["off"], off), what
+    for k in ("desc", "times_predicted", "times_matched"):
+        assert np.array_equal(fo_[k], fr_[k]), (what, k)
+
+
+def test_map_management_remove_convert_add():
+    """removeBadMapFeatures, removal of the unseen features under the MaxMapSize policy, one inverse-depth -> XYZ conversion
+    per frame and the reference's own new-feature selection + add, frame after frame (E/EKF.cpp:572-612)."""
+    sc, o, r, MapPolicy = map_scenario()
+    for t in range(1, 9):
+        phase_by_phase(sc, o, r, t, 1e-9 if t > 2 else TOL)   # XYZ features make S ill-conditioned: looser state tolerance
+        if t == 2:   # features 3 and 11 become "bad": matched in 1 of 5 predictions
+            f_ = o.get_features()
+            tp, tm = np.full_like(f_["times_predicted"], 5), np.full_like(f_["times_matched"], 5)
+            tm[[3, 11]] = 1
+            tp[[5, 17, 30]] = 0; tm[[5, 17, 30]] = 0      # never predicted: 0/0 is not "bad"
+            o.set_hit_counters(tp, tm); r.set_hit_counters(tp, tm)
+        # t = 1: nothing to do; t = 2: bad + unseen features go; t >= 3: one conversion per frame (huge threshold)
+        pol = MapPolicy(min_matches_per_image=60 if t == 2 else 0, max_map_size=240,
+                        good_feature_matching_percent=0.5 if t == 2 else 0.0,
+                        linearity_index_threshold=1e9 if t >= 3 else 1e-9)
+        r.set_policy(pol)
+        N0 = o.dims()[1]
+        needed, removed, conv = o.map_management(pol)
+        assert needed == r.map_management()
+        same_map(o, r, f"map management {t}", 1e-9)
+        if t == 1:
+            assert not removed.any() and conv == -1
+        if t == 2:
+            assert sorted(np.flatnonzero(removed == 1)) == [3, 11] and sorted(np.flatnonzero(removed == 2)) == [5, 17, 30]
+            assert o.dims()[1] == N0 - 5 and needed > 0
+            kp, ds = sc.frame(t)
+            uv, dd = r.detect_new(kp, ds, 4)     # the reference's zone-balanced selection (libc rand)
+            assert len(uv) == 4
+            for a in range(len(uv)):
+                o.add_feature(uv[a], dd[a]); r.add_feature(uv[a], dd[a])
+            same_map(o, r, "add after removal", 1e-9)
+        if t >= 3:
+            assert conv == t - 3      # the first remaining inverse-depth feature each frame
+    assert (o.get_features()["type"] == 1).sum() == 6
+    r.close()

@@ -6,7 +6,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from openekfmonoslam_b200.capi import EkfBatch
 from openekfmonoslam_b200.scenario import Scenario
 

@@ -4,7 +4,7 @@ import json
 import sys
 import time
 
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from openekfmonoslam_b200.capi import EkfBatch
 from openekfmonoslam_b200.scenario import Scenario
 
