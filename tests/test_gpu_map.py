@@ -60,6 +60,7 @@ def test_map_management_remove_convert_add():
                         good_feature_matching_percent=0.5 if t == 2 else 0.0,
                         linearity_index_threshold=1e9 if t >= 3 else 1e-9)
         N0 = orc.dims()[1]
+        mo = orc.get_measure()      # indexed by the numbering before the map changes
         needed, removed, conv = orc.map_management(pol)
         res = gpu.map_management(pol)[0]
         assert res["new_features_needed"] == needed and res["converted"] == conv
@@ -70,7 +71,6 @@ def test_map_management_remove_convert_add():
             assert orc.dims()[1] == N0 - 5
             # buildImageMask: every prediction's ellipse in black on white
             mask = gpu.new_feature_mask(0)
-            mo = orc.get_measure()
             ref = np.full_like(mask, 255)
             black = np.zeros_like(mask)
             for i in np.flatnonzero(mo["vis"]):
