@@ -57,6 +57,41 @@ private:
 
 struct EkfKeyPoint { float x, y; };
 
+// everything EKF reads from the configuration file: camera + filter parameters (ekfb_params), the map-management policy
+// (ekfb_map_policy) and the host-side fields of ExtendedKalmanFilterParameters (.../ExtendedKalmanFilterParameters.h:37-76)
+struct EkfHostConfig {
+    ekfb_params params;
+    ekfb_map_policy policy;
+    int mapManagementFrequency;                     // MapManagementFrequency
+    int detectNewFeaturesImageAreasDivideTimes;     // DetectNewFeaturesImageAreasDivideTimes
+    double detectNewFeaturesImageMaskEllipseSize;   // DetectNewFeaturesImageMaskEllipseSize
+};
+
+typedef void (*EkfbDrawFn)(void* user, unsigned char* mask, int W, int H, double x, double y);
+
+// one "Frame k" record of output.yml (E/EKF.cpp:257-268 ... 618-628)
+struct EkfbFrameTrace {
+    double usPrediction, usMatching, usRansac, usUpdateLI, usRescue, usUpdateHI, usMapManagement;
+    int totalMatches, liInliers, hiInliers, invDepthCount, depthCount;
+    double state[13];
+    double cov[169];
+};
+
+class EkfbTraceWriter {
+public:
+    EkfbTraceWriter();
+    ~EkfbTraceWriter();
+    bool open(const std::string& path);
+    bool isOpen() const { return _f != nullptr; }
+    void frame(int step, const EkfbFrameTrace& t);
+    void close();
+
+private:
+    void* _f;
+    EkfbTraceWriter(const EkfbTraceWriter&);
+    EkfbTraceWriter& operator=(const EkfbTraceWriter&);
+};
+
 // host front end: keypoints + 32-byte binary descriptors of one frame
 class FrontEnd {
 public:
@@ -86,23 +121,44 @@ public:
     ekfb_handle handle() const { return _h; }
     bool ok() const { return _h != nullptr; }
 
+    const ekfb_map_result& lastMapResult() const { return _mapResult; }
+    int lastNewFeatures() const { return _lastAdded; }
+
 private:
-    void uploadState(const std::vector<double>& P, int n);
     void downloadState();
+    void mirrorLayout();
+    int addNewFeatures(int wanted, bool useDeviceMask);
     int _ekfSteps;
     std::string _strOutputPath;
-    ekfb_params _params;
-    int _minMatchesPerImage, _maxFeatures, _device;
+    EkfHostConfig _cfg;
+    int _maxFeatures, _device;
     bool _configOk;
     FrontEnd* _frontEnd;
     ekfb_handle _h;
     ekfb_frame_info _info;
+    ekfb_map_result _mapResult;
+    int _lastAdded;
     std::vector<EkfKeyPoint> _kps;
     std::vector<unsigned char> _desc;
+    std::vector<unsigned char> _mask, _stamp;
+    std::vector<double> _predXY;   // predicted pixels of the frame (zone occupancy of the new-feature search)
+    int _stampR;
+    EkfbTraceWriter _trace;
 };
 
 // reads the reference's YAML 1.0 configuration (experiments/s3/config.yml, kalmanFilter/samples/EKF/config.yml)
 bool ekfbLoadConfig(const char* fileName, ekfb_params* params, int* minMatchesPerImage, int* maxMapSize);
+bool ekfbLoadConfigFull(const char* fileName, EkfHostConfig* config);
+
+// detectNewImageFeatures after the detector call (E/DetectNewImageFeatures.cpp:172-419): keypoints are filtered by
+// `mask` (W x H, 0 = masked) the way the detector's mask argument does, then -- if more than maxNew survive -- picked zone by
+// zone with libc rand() so that the (2^divideTimes)^2 image zones end up evenly populated; `predXY` are the predicted
+// features of the frame (zone occupancy).  After each accepted feature `draw` blacks out its neighbourhood in `mask`.
+// Returns the count; outIdx = indices into kpXY in selection order.
+int ekfbSelectNewFeatures(int W, int H, int divideTimes, unsigned char* mask, const float* kpXY, int nKp, const double* predXY,
+                          int nPred, int maxNew, EkfbDrawFn draw, void* user, int* outIdx);
+// blacks out a (2R+1)^2 stamp (0 = ellipse pixel) centred on the truncated pixel of (x, y), clipped to the image
+void ekfbStampEllipse(const unsigned char* stamp, int R, unsigned char* mask, int W, int H, double x, double y);
 
 // Host-side addFeatureToStateAndCovariance for one inverse-depth feature (AddMapFeature.cpp:43-350): appends the six
 // feature rows to x and grows the row-major n x n covariance P to (n+6) x (n+6); n is updated.

@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
     return OUT
 
 
-HOST_SRCS = [os.path.join(HERE, "host", "EKF.cpp"), os.path.join(HERE, "host", "config_yaml.cpp")]
+HOST_SRCS = [os.path.join(HERE, "host", f) for f in ("EKF.cpp", "config_yaml.cpp", "new_features.cpp", "trace_yaml.cpp")]
 SAMPLE_SRC = os.path.join(HERE, "..", "samples", "ekf_main.cpp")
 SAMPLE_OUT = os.path.join(OUT_DIR, "ekf_sample")
 HOST_OUT = os.path.join(OUT_DIR, "libekf_host.so")

@@ -104,6 +104,7 @@ extern "C" int ekfb_host_load_config(const char* file, ekfb_params* p, int* minM
 {
     return ekfbLoadConfig(file, p, minMatches, maxMapSize) ? 0 : 1;
 }
+extern "C" int ekfb_host_load_config_full(const char* file, EkfHostConfig* out) { return ekfbLoadConfigFull(file, out) ? 0 : 1; }
 extern "C" void ekfb_host_add_feature(const ekfb_params* p, const double* uv, const double* xIn, const double* PIn, int n,
                                       double* xOut, double* POut)
 {
@@ -132,41 +133,30 @@ void State::removeAllFeatures()
 }
 
 EKF::EKF(const char* configurationFileName, const char* outputPath)
-    : _ekfSteps(0), _strOutputPath(outputPath ? outputPath : ""), _minMatchesPerImage(0), _maxFeatures(0), _device(0),
-      _configOk(false), _frontEnd(nullptr), _h(nullptr)
+    : _ekfSteps(0), _strOutputPath(outputPath ? outputPath : ""), _maxFeatures(0), _device(0), _configOk(false),
+      _frontEnd(nullptr), _h(nullptr), _lastAdded(0), _stampR(0)
 {
-    std::memset(&_params, 0, sizeof(_params));
     std::memset(&_info, 0, sizeof(_info));
-    int maxMapSize = 0;
-    _configOk = ekfbLoadConfig(configurationFileName, &_params, &_minMatchesPerImage, &maxMapSize);
+    std::memset(&_mapResult, 0, sizeof(_mapResult));
+    _configOk = ekfbLoadConfigFull(configurationFileName, &_cfg);
     if (!_configOk) std::cerr << "EKF: could not load configuration " << configurationFileName << std::endl;
-    // capacity in features: MaxMapSize is in rows of the state (E/EKF.cpp:582-584); without it allow 4x the target
-    _maxFeatures = maxMapSize > 13 ? (maxMapSize - 13) / 3 : 4 * (_minMatchesPerImage > 0 ? _minMatchesPerImage : 64);
-    if (!_strOutputPath.empty())
-        std::cerr << "EKF: output traces (output.yml, log.txt, overlays) are not written by this build" << std::endl;
+    // capacity in features: MaxMapSize is in rows of the state (E/EKF.cpp:582-584) and a frame may add up to
+    // MinMatchesPerImage features on top of it before the next removal; without a limit allow 4x the target
+    const int minM = _cfg.policy.min_matches_per_image > 0 ? _cfg.policy.min_matches_per_image : 64;
+    if (_cfg.policy.max_map_features_count > 0) _maxFeatures = _cfg.policy.max_map_features_count + minM;
+    else if (_cfg.policy.max_map_size > 13) _maxFeatures = (_cfg.policy.max_map_size - 13) / 3 + minM;
+    else _maxFeatures = 4 * minM;
+    if (!_strOutputPath.empty()) {
+        // E/EKF.cpp:129-143: output.yml in outputPath.  log.txt, the per-frame PNG overlays and videoOutput.mpg are GUI
+        // artefacts (modules/Gui) and are not written by this build.
+        if (!_trace.open(_strOutputPath + "output.yml"))
+            std::cerr << "EKF: cannot write " << _strOutputPath << "output.yml" << std::endl;
+    }
 }
 
 EKF::~EKF()
 {
     if (_h) ekfb_destroy(_h);
-}
-
-void EKF::uploadState(const std::vector<double>& P, int n)
-{
-    const int N = (int)state.mapFeatures.size();
-    std::vector<double> x(n, 0.0);
-    std::vector<int32_t> type(N), off(N);
-    std::vector<unsigned char> desc((size_t)N * 32);
-    for (int i = 0; i < 3; ++i) { x[i] = state.position[i]; x[7 + i] = state.linearVelocity[i]; x[10 + i] = state.angularVelocity[i]; }
-    for (int i = 0; i < 4; ++i) x[3 + i] = state.orientation[i];
-    for (int i = 0; i < N; ++i) {
-        const MapFeature* f = state.mapFeatures[i];
-        type[i] = f->featureType; off[i] = f->covarianceMatrixPos;
-        for (int j = 0; j < f->positionDimension; ++j) x[f->covarianceMatrixPos + j] = f->position[j];
-        std::memcpy(&desc[(size_t)i * 32], f->descriptor, 32);
-    }
-    if (ekfb_set_state(_h, 0, n, N, x.data(), type.data(), off.data(), P.data(), desc.data()) != EKFB_OK)
-        std::cerr << "EKF: " << ekfb_last_error() << std::endl;
 }
 
 void EKF::downloadState()
@@ -177,15 +167,244 @@ void EKF::downloadState()
     if (ekfb_get_state(_h, 0, x.data(), nullptr, 0) != EKFB_OK) { std::cerr << "EKF: " << ekfb_last_error() << std::endl; return; }
     for (int i = 0; i < 3; ++i) { state.position[i] = x[i]; state.linearVelocity[i] = x[7 + i]; state.angularVelocity[i] = x[10 + i]; }
     state.setOrientation(&x[3]);
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < N && i < (int)state.mapFeatures.size(); ++i) {
         MapFeature* f = state.mapFeatures[i];
         for (int j = 0; j < f->positionDimension; ++j) f->position[j] = x[f->covarianceMatrixPos + j];
     }
     ekfb_record rec;
     if (ekfb_get_records(_h, &rec) == EKFB_OK) {
-        _info = rec.info;
+        if (stateCovarianceMatrix.rows < 13) stateCovarianceMatrix = Matd(13, 13);
         for (int i = 0; i < 13; ++i)
             for (int j = 0; j < 13; ++j) stateCovarianceMatrix[i][j] = rec.P_cam[i * 13 + j];
+    }
+}
+
+// bring the host mirror of the map (State::mapFeatures and the two per-type lists) in line with the device's layout
+// after features were removed, converted or added (what State::removeFeatures / addFeature / convertToDepth do to the
+// reference's vectors: E/State.cpp:142-206, E/MapManagement.cpp:457-496)
+void EKF::mirrorLayout()
+{
+    int32_t n = 0, N = 0;
+    ekfb_get_dims(_h, 0, &n, &N);
+    std::vector<int32_t> type(N > 0 ? N : 1), off(N > 0 ? N : 1), tp(N > 0 ? N : 1), tm(N > 0 ? N : 1);
+    std::vector<unsigned char> desc((size_t)(N > 0 ? N : 1) * 32);
+    if (ekfb_get_feature_layout(_h, 0, type.data(), off.data()) != EKFB_OK ||
+        ekfb_get_descriptors(_h, 0, desc.data(), tp.data(), tm.data()) != EKFB_OK) {
+        std::cerr << "EKF: " << ekfb_last_error() << std::endl;
+        return;
+    }
+    while ((int)state.mapFeatures.size() < N) state.mapFeatures.push_back(new MapFeature());
+    state.mapFeaturesDepth.clear();
+    state.mapFeaturesInvDepth.clear();
+    for (int i = 0; i < N; ++i) {
+        MapFeature* f = state.mapFeatures[i];
+        f->featureType = (MapFeatureType)type[i];
+        f->positionDimension = type[i] == MAPFEATURE_TYPE_INVERSE_DEPTH ? 6 : 3;
+        f->covarianceMatrixPos = off[i];
+        f->timesPredicted = (unsigned)tp[i];
+        f->timesMatched = (unsigned)tm[i];
+        std::memcpy(f->descriptor, &desc[(size_t)i * 32], 32);
+        (type[i] == MAPFEATURE_TYPE_INVERSE_DEPTH ? state.mapFeaturesInvDepth : state.mapFeaturesDepth).push_back(f);
+    }
+}
+
+namespace {
+struct DrawCtx {
+    ekfb_handle h;
+    const std::vector<unsigned char>* stamp;
+    int R, maxAxes;
+    double ellipseSize;
+};
+// drawUncertaintyEllipse2D(mask, (x, y), diag(size, size), 2 (cols + rows), black, filled) (E/DetectNewImageFeatures.cpp:286-291):
+// the pixel set is the same for every centre as long as the ellipse lies inside the image, so it is stamped from the
+// copy the device rasterised once; an ellipse that crosses the border is rasterised by the device on the mask itself.
+void drawNewFeatureEllipse(void* user, unsigned char* mask, int W, int H, double x, double y)
+{
+    const DrawCtx* c = (const DrawCtx*)user;
+    const int cx = (int)(float)x, cy = (int)(float)y;
+    if (cx - c->R >= 0 && cx + c->R < W && cy - c->R >= 0 && cy + c->R < H) {
+        ekfbStampEllipse(c->stamp->data(), c->R, mask, W, H, x, y);
+    } else {
+        const double S[4] = {c->ellipseSize, 0.0, 0.0, c->ellipseSize};
+        if (ekfb_raster_ellipse(c->h, W, H, x, y, S, c->maxAxes, 0, mask) != EKFB_OK)
+            std::cerr << "EKF: " << ekfb_last_error() << std::endl;
+    }
+}
+}  // namespace
+
+// detectNewImageFeatures + addFeaturesToStateAndCovariance (E/EKF.cpp:196-222 at init, :594-611 per frame) on the
+// keypoints of the current frame (_kps / _desc).  Returns the number of features added.
+int EKF::addNewFeatures(int wanted, bool useDeviceMask)
+{
+    const int W = _cfg.params.pixels_x, H = _cfg.params.pixels_y;
+    int32_t n = 0, N = 0;
+    ekfb_get_dims(_h, 0, &n, &N);
+    if (wanted > _maxFeatures - N) wanted = _maxFeatures - N;
+    if (wanted <= 0 || _kps.empty()) return 0;
+    _mask.assign((size_t)W * H, 255);
+    std::vector<double> pred;
+    if (useDeviceMask) {
+        if (ekfb_get_new_feature_mask(_h, 0, _mask.data()) != EKFB_OK) {
+            std::cerr << "EKF: " << ekfb_last_error() << std::endl;
+            return 0;
+        }
+        pred = _predXY;
+    }
+    if (_stamp.empty()) {   // the ellipse of E/DetectNewImageFeatures.cpp:221-223, rasterised once by the device
+        const double es = _cfg.detectNewFeaturesImageMaskEllipseSize;
+        _stampR = (int)(2.0 * std::sqrt(es * 5.9915)) + 2;
+        const int D = 2 * _stampR + 1;
+        _stamp.assign((size_t)D * D, 255);
+        const double S[4] = {es, 0.0, 0.0, es};
+        if (ekfb_raster_ellipse(_h, D, D, _stampR, _stampR, S, 2 * (W + H), 0, _stamp.data()) != EKFB_OK) {
+            std::cerr << "EKF: " << ekfb_last_error() << std::endl;
+            _stamp.clear();
+            return 0;
+        }
+    }
+    std::vector<float> xy(_kps.size() * 2);
+    for (size_t i = 0; i < _kps.size(); ++i) { xy[2 * i] = _kps[i].x; xy[2 * i + 1] = _kps[i].y; }
+    std::vector<int> idx(wanted);
+    DrawCtx ctx = {_h, &_stamp, _stampR, 2 * (W + H), _cfg.detectNewFeaturesImageMaskEllipseSize};
+    const int k = ekfbSelectNewFeatures(W, H, _cfg.detectNewFeaturesImageAreasDivideTimes, _mask.data(), xy.data(), (int)_kps.size(),
+                                        pred.data(), (int)pred.size() / 2, wanted, &drawNewFeatureEllipse, &ctx, idx.data());
+    if (k == 0) return 0;
+    std::vector<double> uv(2 * k);
+    std::vector<unsigned char> dd((size_t)32 * k);
+    for (int a = 0; a < k; ++a) {
+        uv[2 * a] = _kps[idx[a]].x;
+        uv[2 * a + 1] = _kps[idx[a]].y;
+        std::memcpy(&dd[(size_t)32 * a], &_desc[(size_t)32 * idx[a]], 32);
+    }
+    if (ekfb_add_features(_h, 0, k, uv.data(), dd.data()) != EKFB_OK) {
+        std::cerr << "EKF: " << ekfb_last_error() << std::endl;
+        return 0;
+    }
+    return k;
+}
+
+void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
+{
+    if (!_configOk || !_frontEnd) {
+        std::cerr << "EKF::init: no configuration or no front end" << std::endl;
+        return;
+    }
+    if (!_h && ekfb_create(&_cfg.params, _device, 1, _maxFeatures, 16384, &_h) != EKFB_OK) {
+        std::cerr << "EKF::init: " << ekfb_last_error() << std::endl;
+        _h = nullptr;
+        return;
+    }
+    // initState / initCovariance (E/CommonFunctions.cpp:39-80)
+    std::vector<double> x(13, 0.0), P(169, 0.0);
+    x[3] = 1.0; x[10] = x[11] = x[12] = kEpsilon;
+    for (int i = 0; i < 7; ++i) P[i * 13 + i] = kEpsilon;
+    for (int i = 0; i < 3; ++i) {
+        P[(7 + i) * 13 + 7 + i] = _cfg.params.init_linear_accel_sd * _cfg.params.init_linear_accel_sd;
+        P[(10 + i) * 13 + 10 + i] = _cfg.params.init_angular_accel_sd * _cfg.params.init_angular_accel_sd;
+    }
+    state.removeAllFeatures();
+    if (ekfb_set_state(_h, 0, 13, 0, x.data(), nullptr, nullptr, P.data(), nullptr) != EKFB_OK) {
+        std::cerr << "EKF::init: " << ekfb_last_error() << std::endl;
+        return;
+    }
+    // detectNewImageFeatures(image, noPredictions, MinMatchesPerImage) + addFeaturesToStateAndCovariance, on the device
+    _frontEnd->detectAndDescribe(image, _kps, _desc);
+    _predXY.clear();
+    _lastAdded = addNewFeatures(_cfg.policy.min_matches_per_image, false);
+    mirrorLayout();
+    downloadState();
+}
+
+void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
+{
+    if (!_h || !_frontEnd) {
+        std::cerr << "EKF::step: filter not initialised" << std::endl;
+        return;
+    }
+    _ekfSteps++;
+    _frontEnd->detectAndDescribe(image, _kps, _desc);
+    std::vector<float> xy(_kps.size() * 2);
+    for (size_t i = 0; i < _kps.size(); ++i) { xy[2 * i] = _kps[i].x; xy[2 * i + 1] = _kps[i].y; }
+    bool ok = ekfb_set_keypoints(_h, 0, xy.data(), _desc.data(), (int)_kps.size()) == EKFB_OK;
+    float ms[8] = {0};
+    if (ok && _trace.isOpen()) {
+        // phase by phase with device timers, the seven intervals the reference writes (E/EKF.cpp:291 ... 618)
+        ekfb_timer_record(_h, 0);
+        ok = ekfb_predict(_h) == EKFB_OK && ekfb_measure(_h) == EKFB_OK;
+        ekfb_timer_record(_h, 1);
+        ok = ok && ekfb_match(_h) == EKFB_OK;
+        ekfb_timer_record(_h, 2);
+        ok = ok && ekfb_ransac(_h) == EKFB_OK;
+        ekfb_timer_record(_h, 3);
+        ok = ok && ekfb_update(_h, 0) == EKFB_OK;
+        ekfb_timer_record(_h, 4);
+        ok = ok && ekfb_rescue(_h) == EKFB_OK;
+        ekfb_timer_record(_h, 5);
+        ok = ok && ekfb_update(_h, 1) == EKFB_OK;
+        ekfb_timer_record(_h, 6);
+        ok = ok && ekfb_update_map_features(_h) == EKFB_OK;
+    } else if (ok) {
+        ok = ekfb_step(_h) == EKFB_OK;
+    }
+    if (!ok) {
+        std::cerr << "EKF::step: " << ekfb_last_error() << std::endl;
+        return;
+    }
+    ekfb_get_frame_info(_h, 0, &_info);
+    // map management (E/EKF.cpp:572-612): bad / unseen features out, one conversion, new features in
+    std::memset(&_mapResult, 0, sizeof(_mapResult));
+    _mapResult.converted = -1;
+    _lastAdded = 0;
+    bool layoutChanged = false;
+    if (_cfg.mapManagementFrequency > 0 && _ekfSteps % _cfg.mapManagementFrequency == 0) {
+        const int nBefore = (int)state.mapFeatures.size();
+        if (_cfg.policy.min_matches_per_image - (_info.n_inliers + _info.n_rescued) > 0) {
+            // the zone occupancy of detectNewImageFeatures counts this frame's predictions: fetch them before the map changes
+            std::vector<unsigned char> vis(nBefore > 0 ? nBefore : 1);
+            std::vector<double> h(2 * (size_t)(nBefore > 0 ? nBefore : 1));
+            _predXY.clear();
+            if (ekfb_get_feature_results(_h, 0, vis.data(), h.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                         nullptr, nullptr, nullptr) == EKFB_OK)
+                for (int i = 0; i < nBefore; ++i)
+                    if (vis[i]) { _predXY.push_back(h[2 * i]); _predXY.push_back(h[2 * i + 1]); }
+        }
+        if (ekfb_map_management(_h, &_cfg.policy, &_mapResult) != EKFB_OK) {
+            std::cerr << "EKF::step: " << ekfb_last_error() << std::endl;
+            return;
+        }
+        if (_mapResult.n_removed_bad + _mapResult.n_removed_unseen > 0) {
+            std::vector<unsigned char> flags(nBefore > 0 ? nBefore : 1);
+            if (ekfb_get_removed_flags(_h, 0, nBefore, flags.data()) == EKFB_OK) {
+                VectorMapFeature keep;
+                for (int i = 0; i < nBefore; ++i) {
+                    if (flags[i]) delete state.mapFeatures[i];
+                    else keep.push_back(state.mapFeatures[i]);
+                }
+                state.mapFeatures.swap(keep);
+            }
+            layoutChanged = true;
+        }
+        if (_mapResult.converted >= 0) layoutChanged = true;
+        if (_mapResult.new_features_needed > 0) {
+            _lastAdded = addNewFeatures(_mapResult.new_features_needed, true);
+            layoutChanged = layoutChanged || _lastAdded > 0;
+        }
+    }
+    if (_trace.isOpen()) ekfb_timer_record(_h, 7);
+    if (layoutChanged) mirrorLayout();
+    downloadState();
+    if (_trace.isOpen()) {
+        for (int i = 0; i < 7; ++i) ekfb_timer_elapsed_ms(_h, i, i + 1, &ms[i]);
+        EkfbFrameTrace t;
+        t.usPrediction = 1e3 * ms[0]; t.usMatching = 1e3 * ms[1]; t.usRansac = 1e3 * ms[2]; t.usUpdateLI = 1e3 * ms[3];
+        t.usRescue = 1e3 * ms[4]; t.usUpdateHI = 1e3 * ms[5]; t.usMapManagement = 1e3 * ms[6];
+        t.totalMatches = _info.n_matches; t.liInliers = _info.n_inliers; t.hiInliers = _info.n_rescued;
+        t.invDepthCount = (int)state.mapFeaturesInvDepth.size(); t.depthCount = (int)state.mapFeaturesDepth.size();
+        for (int i = 0; i < 3; ++i) { t.state[i] = state.position[i]; t.state[7 + i] = state.linearVelocity[i]; t.state[10 + i] = state.angularVelocity[i]; }
+        for (int i = 0; i < 4; ++i) t.state[3 + i] = state.orientation[i];
+        for (int i = 0; i < 13; ++i)
+            for (int j = 0; j < 13; ++j) t.cov[i * 13 + j] = stateCovarianceMatrix[i][j];
+        _trace.frame(_ekfSteps, t);
     }
 }
 
@@ -200,65 +419,3 @@ void EKF::syncCovariance()
     for (int i = 0; i < n; ++i) std::memcpy(stateCovarianceMatrix[i], &P[(size_t)i * n], sizeof(double) * n);
 }
 
-void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
-{
-    if (!_configOk || !_frontEnd) {
-        std::cerr << "EKF::init: no configuration or no front end" << std::endl;
-        return;
-    }
-    if (!_h && ekfb_create(&_params, _device, 1, _maxFeatures, 16384, &_h) != EKFB_OK) {
-        std::cerr << "EKF::init: " << ekfb_last_error() << std::endl;
-        _h = nullptr;
-        return;
-    }
-    // initState / initCovariance (E/CommonFunctions.cpp:39-80)
-    std::vector<double> x(13, 0.0), P(169, 0.0);
-    x[3] = 1.0; x[10] = x[11] = x[12] = kEpsilon;
-    for (int i = 0; i < 7; ++i) P[i * 13 + i] = kEpsilon;
-    for (int i = 0; i < 3; ++i) {
-        P[(7 + i) * 13 + 7 + i] = _params.init_linear_accel_sd * _params.init_linear_accel_sd;
-        P[(10 + i) * 13 + 10 + i] = _params.init_angular_accel_sd * _params.init_angular_accel_sd;
-    }
-    state.removeAllFeatures();
-    for (int i = 0; i < 3; ++i) { state.position[i] = 0; state.linearVelocity[i] = 0; state.angularVelocity[i] = kEpsilon; }
-    state.setOrientation(&x[3]);
-    // new features: the front end's keypoints, in its order, up to MinMatchesPerImage (the reference balances them over
-    // a 4x4 zone grid with libc rand(), E/DetectNewImageFeatures.cpp:172-419 -- front-end policy, out of the hot path)
-    _frontEnd->detectAndDescribe(image, _kps, _desc);
-    int want = _minMatchesPerImage > 0 ? _minMatchesPerImage : (int)_kps.size();
-    if (want > _maxFeatures) want = _maxFeatures;
-    int n = 13;
-    for (int i = 0; i < (int)_kps.size() && i < want; ++i) {
-        const double uv[2] = {_kps[i].x, _kps[i].y};
-        MapFeature* f = new MapFeature();
-        f->featureType = MAPFEATURE_TYPE_INVERSE_DEPTH;
-        f->positionDimension = 6;
-        f->covarianceMatrixPos = n;
-        f->timesPredicted = f->timesMatched = 0;
-        std::memcpy(f->descriptor, &_desc[(size_t)i * 32], 32);
-        ekfbAddInverseDepthFeature(_params, uv, x, P, n);
-        std::memcpy(f->position, &x[n - 6], sizeof(double) * 6);
-        state.mapFeatures.push_back(f);
-        state.mapFeaturesInvDepth.push_back(f);
-    }
-    stateCovarianceMatrix = Matd(n, n);
-    for (int i = 0; i < n; ++i) std::memcpy(stateCovarianceMatrix[i], &P[(size_t)i * n], sizeof(double) * n);
-    uploadState(P, n);
-}
-
-void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
-{
-    if (!_h || !_frontEnd) {
-        std::cerr << "EKF::step: filter not initialised" << std::endl;
-        return;
-    }
-    _ekfSteps++;
-    _frontEnd->detectAndDescribe(image, _kps, _desc);
-    std::vector<float> xy(_kps.size() * 2);
-    for (size_t i = 0; i < _kps.size(); ++i) { xy[2 * i] = _kps[i].x; xy[2 * i + 1] = _kps[i].y; }
-    if (ekfb_set_keypoints(_h, 0, xy.data(), _desc.data(), (int)_kps.size()) != EKFB_OK || ekfb_step(_h) != EKFB_OK) {
-        std::cerr << "EKF::step: " << ekfb_last_error() << std::endl;
-        return;
-    }
-    downloadState();
-}

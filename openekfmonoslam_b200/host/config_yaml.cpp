@@ -28,6 +28,18 @@ std::string unquote(const std::string& s)
 
 bool ekfbLoadConfig(const char* fileName, ekfb_params* p, int* minMatches, int* maxMapSize)
 {
+    EkfHostConfig c;
+    const bool ok = ekfbLoadConfigFull(fileName, &c);
+    *p = c.params;
+    if (minMatches) *minMatches = c.policy.min_matches_per_image;
+    if (maxMapSize) *maxMapSize = c.policy.max_map_size;
+    return ok;
+}
+
+bool ekfbLoadConfigFull(const char* fileName, EkfHostConfig* cfg)
+{
+    ekfb_params* p = &cfg->params;
+    *cfg = EkfHostConfig();
     std::ifstream in(fileName);
     if (!in) return false;
     // flat map "Section/Name/Key" -> value, path built from indentation levels 0 / 2 / 4
@@ -73,7 +85,19 @@ bool ekfbLoadConfig(const char* fileName, ekfb_params* p, int* minMatches, int* 
     p->ransac_threshold = num(e + "RansacThresholdPredictDistance", true);
     p->ransac_all_inliers_prob = num(e + "RansacAllInliersProbability", true);
     p->ransac_chi2 = num(e + "RansacChi2Threshold", true);
-    if (minMatches) *minMatches = (int)num(e + "MinMatchesPerImage", true);
-    if (maxMapSize) *maxMapSize = (int)num(e + "MaxMapSize", false);  // optional, defaults to 0 like the reference
+    // map management; optional keys default as in ExtendedKalmanFilterParametersConfiguration (0 / false)
+    auto flag = [&](const std::string& k) {
+        KV::const_iterator it = kv.find(k);
+        return it != kv.end() && (it->second == "true" || it->second == "1");
+    };
+    cfg->policy.min_matches_per_image = (int)num(e + "MinMatchesPerImage", true);
+    cfg->policy.max_map_size = (int)num(e + "MaxMapSize", false);
+    cfg->policy.max_map_features_count = (int)num(e + "MaxMapFeaturesCount", false);
+    cfg->policy.always_remove_unseen = flag(e + "AlwaysRemoveUnseenMapFeatures") ? 1 : 0;
+    cfg->policy.good_feature_matching_percent = num(e + "GoodFeatureMatchingPercent", false);
+    cfg->policy.linearity_index_threshold = num(e + "InverseDepthLinearityIndexThreshold", false);
+    cfg->mapManagementFrequency = (int)num(e + "MapManagementFrequency", false);
+    cfg->detectNewFeaturesImageAreasDivideTimes = (int)num(e + "DetectNewFeaturesImageAreasDivideTimes", false);
+    cfg->detectNewFeaturesImageMaskEllipseSize = num(e + "DetectNewFeaturesImageMaskEllipseSize", false);
     return ok;
 }

@@ -132,7 +132,7 @@ _EKF_KEYS = (("InitInvDepthRho", "init_inv_depth_rho"), ("InitLinearAccelSD", "i
              ("RansacAllInliersProbability", "ransac_all_inliers_prob"), ("RansacChi2Threshold", "ransac_chi2"))
 
 
-def write_config(path, p, min_matches_per_image, max_map_size=0):
+def write_config(path, p, min_matches_per_image, max_map_size=0, extra=None):
     """Write params in the reference's config.yml layout (samples/EKF/config.yml): a RunConfiguration block naming one
     entry per section, every value a quoted string."""
     lines = ["%YAML:1.0", "", "RunConfiguration:", '  ExtendedKalmanFilter: "EKF"', '  FeatureDetector: "STAR"',
@@ -142,6 +142,8 @@ def write_config(path, p, min_matches_per_image, max_map_size=0):
     lines.append(f'    MinMatchesPerImage: "{int(min_matches_per_image)}"')
     if max_map_size:
         lines.append(f'    MaxMapSize: "{int(max_map_size)}"')
+    for key, val in (extra or {}).items():      # e.g. MapManagementFrequency, GoodFeatureMatchingPercent, ...
+        lines.append(f'    {key}: "{val}"')
     lines += ["FeatureDetector:", "  STAR:", '    Type: "STAR"', "DescriptorExtractor:", "  BRIEF:", '    Type: "BRIEF"',
               "CameraCalibration:", "  CAM:"]
     for key, attr in _CAM_KEYS:

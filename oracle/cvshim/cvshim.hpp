@@ -365,15 +365,25 @@ inline bool eigen(const Mat& src, Mat& evals, Mat& evecs)
     return true;
 }
 
-// cv::ellipse: only the filled full ellipse on an 8-bit single-channel image has an effect (the matching mask);
+// cv::ellipse: only the filled full ellipse on an 8-bit single-channel image has an effect (the matching mask and the
+// new-feature mask);
 // every other drawing call of the reference's GUI code is a no-op here.
 inline void ellipse(Mat& img, Point center, Size axes, double angle, double startAngle, double endAngle, const Scalar& color,
                     int thickness = 1, int lineType = 8, int shift = 0)
 {
     (void)startAngle; (void)endAngle; (void)lineType; (void)shift;
     if (thickness >= 0 || img.type() != CV_8UC1 || !img.isContinuous()) return;
-    if (color.val[0] == 0) return;
-    orc_fill_ellipse(img.data, img.cols, img.rows, center.x, center.y, axes.width, axes.height, angle);
+    if (color.val[0] == 255) {
+        orc_fill_ellipse(img.data, img.cols, img.rows, center.x, center.y, axes.width, axes.height, angle);
+        return;
+    }
+    // any other colour (the black ellipses of the new-feature mask, DetectNewImageFeatures.cpp:115-121,286-291): rasterise
+    // into a scratch image and copy the covered pixels in that colour
+    std::vector<uchar> tmp((size_t)img.rows * img.cols, 0);
+    orc_fill_ellipse(tmp.data(), img.cols, img.rows, center.x, center.y, axes.width, axes.height, angle);
+    const uchar c = (uchar)color.val[0];
+    for (size_t i = 0; i < tmp.size(); ++i)
+        if (tmp[i]) img.data[i] = c;
 }
 inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) {}
 inline void circle(Mat&, Point, int, const Scalar&, int = 1, int = 8, int = 0) {}

@@ -298,6 +298,16 @@ void ref_init(ref_filter* f)
     initCovariance(f->ekf->stateCovarianceMatrix);
 }
 
+// the reference's own EKF::init (EKF.cpp:170-237) on the injected keypoints: initState, initCovariance,
+// detectNewImageFeatures (zone-balanced, libc rand) and addFeaturesToStateAndCovariance
+void ref_full_init(ref_filter* f, const float* kp, const uint8_t* desc, int32_t nkp)
+{
+    clear_frame(f);
+    f->ekf->state.removeAllFeatures();
+    inject(f, kp, desc, nkp);
+    f->ekf->init(f->image);
+}
+
 // ---- whole frame through the reference's own orchestrator ----
 void ref_step(ref_filter* f, const float* kp, const uint8_t* desc, int32_t nkp)
 {

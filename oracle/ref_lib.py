@@ -118,6 +118,10 @@ class ReferenceFilter:
         self._kpds = np.ascontiguousarray(kp_desc, np.uint8)   # must outlive the frame (descriptors are read lazily)
         return _p(self._kpxy), _p(self._kpds), ctypes.c_int32(self._kpxy.shape[0])
 
+    def full_init(self, kp_xy, kp_desc):
+        """the reference's own EKF::init on the injected keypoints"""
+        self.L.ref_full_init(self.h, *self._kp(kp_xy, kp_desc))
+
     def step(self, kp_xy, kp_desc):
         self.L.ref_step(self.h, *self._kp(kp_xy, kp_desc))
 

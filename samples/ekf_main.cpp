@@ -70,7 +70,10 @@ int main(int argc, const char* argv[])
         for (int i = 0; i < 4; ++i) std::printf(" %.17g", s.orientation[i]);
         for (int i = 0; i < 3; ++i) std::printf(" %.17g", s.linearVelocity[i]);
         for (int i = 0; i < 3; ++i) std::printf(" %.17g", s.angularVelocity[i]);
-        std::printf(" P00 %.17g\n", extendedKalmanFilter.stateCovarianceMatrix[0][0]);
+        std::printf(" P00 %.17g N %d n %d removed %d converted %d added %d\n", extendedKalmanFilter.stateCovarianceMatrix[0][0],
+                    (int)s.mapFeatures.size(), fi.n, extendedKalmanFilter.lastMapResult().n_removed_bad +
+                    extendedKalmanFilter.lastMapResult().n_removed_unseen, extendedKalmanFilter.lastMapResult().converted,
+                    extendedKalmanFilter.lastNewFeatures());
     }
     return 0;
 }
