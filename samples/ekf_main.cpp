@@ -65,13 +65,15 @@ int main(int argc, const char* argv[])
         extendedKalmanFilter.step(image);
         const State& s = extendedKalmanFilter.state;
         const ekfb_frame_info& fi = extendedKalmanFilter.lastFrameInfo();
+        int32_t nNow = 0, NNow = 0;   // state dimension after this frame's map management
+        ekfb_get_dims(extendedKalmanFilter.handle(), 0, &nNow, &NNow);
         std::printf("STEP %d matches %d inliers %d rescued %d x", ++stepCount, fi.n_matches, fi.n_inliers, fi.n_rescued);
         for (int i = 0; i < 3; ++i) std::printf(" %.17g", s.position[i]);
         for (int i = 0; i < 4; ++i) std::printf(" %.17g", s.orientation[i]);
         for (int i = 0; i < 3; ++i) std::printf(" %.17g", s.linearVelocity[i]);
         for (int i = 0; i < 3; ++i) std::printf(" %.17g", s.angularVelocity[i]);
         std::printf(" P00 %.17g N %d n %d removed %d converted %d added %d\n", extendedKalmanFilter.stateCovarianceMatrix[0][0],
-                    (int)s.mapFeatures.size(), fi.n, extendedKalmanFilter.lastMapResult().n_removed_bad +
+                    (int)s.mapFeatures.size(), nNow, extendedKalmanFilter.lastMapResult().n_removed_bad +
                     extendedKalmanFilter.lastMapResult().n_removed_unseen, extendedKalmanFilter.lastMapResult().converted,
                     extendedKalmanFilter.lastNewFeatures());
     }
