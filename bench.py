@@ -326,7 +326,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_total // K,
                     "d2h_bytes_per_step": filters_total * RECORD_BYTES},
             "gpu_launches": launches_total,
-            "roofline": {"bound": "tensor", "kernel": "k_gemm_tn<2> (covariance downdate P -= W W^T, FP64 DMMA)",
+            "roofline": {"bound": "tensor", "kernel": "k_downdate64 (covariance downdate P -= W W^T: lower 64x64 tiles, 4 CTAs/SM, FP64 DMMA m8n8k4)",
                          "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak if peak else None,
                          "traffic": traffic, "launches": dd["launches"], "avg_launch_ms": dd["ms"] / max(dd["launches"], 1),
                          "algorithmic_flops_per_launch": dd["flops"] / max(dd["launches"], 1),

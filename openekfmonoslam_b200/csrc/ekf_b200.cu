@@ -229,7 +229,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     CK(cudaFuncSetAttribute(k_gemm_tn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_gemm_tn<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     CK(cudaFuncSetAttribute(k_downdate, cudaFuncAttributeMaxDynamicSharedMemorySize, kDownSmemBytes));
-    CK(cudaFuncSetAttribute(k_downdate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+    CK(cudaFuncSetAttribute(k_downdate64, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
     CK(cudaFuncSetAttribute(k_schain_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, kSTrailSmem));
     CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
     CK(cudaFuncSetAttribute(k_schain_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem));
@@ -540,7 +540,7 @@ static int launch_downdate(ekfb_ctx* c, int n)
         k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
     else if (kMax <= c->downdate_small_k) {
         // 64x64 tiles, four CTAs per SM (the default at every k, see downdate_small_k)
-        k_downdate_small<<<dim3(nI * (nI + 1) / 2 * 4, c->F), 128, kSmallSmemBytes, c->stream>>>(v, 0);
+        k_downdate64<<<dim3(nI * (nI + 1) / 2 * 4, c->F), 128, kSmallSmemBytes, c->stream>>>(v, 0);
     } else {
         // 1-D grid over the T lower 128x128 tiles.  Single filter: if T is just above a multiple of the SM
         // count, the remainder would cost a whole extra wave; it runs as 64x64 tiles on a second stream,
@@ -552,7 +552,7 @@ static int launch_downdate(ekfb_ctx* c, int n)
         if (rem > 0) {
             CK(cudaEventRecord(c->evFork, c->stream));
             CK(cudaStreamWaitEvent(c->stream2, c->evFork, 0));
-            k_downdate_small<<<dim3(rem * 4, c->F), 128, kSmallSmemBytes, c->stream2>>>(v, nBig);
+            k_downdate64<<<dim3(rem * 4, c->F), 128, kSmallSmemBytes, c->stream2>>>(v, nBig);
             CK(cudaEventRecord(c->evJoin, c->stream2));
             count_launch(c);
         }

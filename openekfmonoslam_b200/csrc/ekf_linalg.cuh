@@ -400,7 +400,7 @@ __global__ void __maxnreg__(KIND == 2 ? 200 : 255) k_gemm_tn(DevView v, int J)
     int tileM = blockIdx.y;
     if ((KIND >= 2)) {
         // 1-D grid over the lower-triangular 128x128 tiles, row block by row block; tiles with index >= J are
-        // left to k_downdate_small (wave-quantisation remainder, see run_update)
+        // left to k_downdate64 (wave-quantisation remainder, see run_update)
         const int idx = blockIdx.x;
         if (idx >= J) return;
         int I = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
@@ -512,7 +512,7 @@ __global__ void __maxnreg__(KIND == 2 ? 200 : 255) k_gemm_tn(DevView v, int J)
 // registers, 52 KB smem) on a second stream, co-resident with the big CTAs.  Big tile `idx` -> 4 small tiles.
 constexpr int kSmallSmemBytes = kStages * kKC * (68 + 68) * (int)sizeof(double);
 
-__global__ void __maxnreg__(112) k_downdate_small(DevView v, int firstBig)
+__global__ void __maxnreg__(112) k_downdate64(DevView v, int firstBig)
 {
     extern __shared__ __align__(16) double ssm2[];
     const int f = blockIdx.y;

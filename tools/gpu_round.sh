@@ -1,16 +1,22 @@
 #!/bin/bash
-# One gpurun call: parity tests, smoke, the bench lines and the ncu launch list.  usage: tools/gpu_round.sh TAG
-TAG=${1:-r01b}
+# One gpurun call: parity tests, smoke, the bench lines, the ncu launch list and one full capture of the roofline kernel.
+# usage: tools/gpu_round.sh TAG
+TAG=${1:-r01}
 O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > $O/smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc $?" >> $O/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > $O/smoke.log 2>&1
 timeout 400 python bench.py > $O/bench_c3.json 2> $O/bench_c3.err
-timeout 200 python bench.py --workload c2 --no-cpu-baseline > $O/bench_c2.json 2> $O/bench_c2.err
+timeout 400 python bench.py --impl reference --steps 2 --warmup 0 > $O/bench_reference_c3.json 2> $O/bench_reference_c3.err
+timeout 200 python bench.py --workload c2 > $O/bench_c2.json 2> $O/bench_c2.err
 timeout 300 python bench.py --workload c4 --steps 20 --warmup 5 --no-cpu-baseline > $O/bench_c4.json 2> $O/bench_c4.err
+for n in 100 200 500 1000 1500 2000; do
+  timeout 300 python bench.py --workload c5 --features $n --steps 20 --warmup 5 --filter-warm 10 --no-cpu-baseline > $O/bench_c5_$n.json 2> $O/bench_c5_$n.err
+done
 timeout 300 python tools/quick_time.py 640 480 500 1 80 > $O/quick_c3.txt 2>&1
 timeout 300 python tools/quick_time.py 640 480 200 256 30 > $O/quick_c4.txt 2>&1
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/launches_bench_c3.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --filter-warm 4 > $O/ncu_bench.log 2>&1
 python tools/agg_launches.py $O/launches_bench_c3.csv > $O/launches_bench_c3.txt 2>&1
-tail -3 $O/pytest_gpu.log; cat $O/smoke.log | tail -2; cat $O/bench_c3.json; cat $O/quick_c3.txt | tail -2
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_downdate64 -s 8 -c 2 -o $O/prof_downdate python bench.py --steps 2 --warmup 3 --no-cpu-baseline --filter-warm 4 > $O/ncu_full.log 2>&1
+tail -3 $O/pytest_gpu.log; tail -2 $O/smoke.log; cat $O/bench_c3.json; tail -2 $O/quick_c3.txt
