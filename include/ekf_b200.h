@@ -158,6 +158,20 @@ int ekfb_get_new_feature_mask(ekfb_handle h, int filter, uint8_t* mask);
 int ekfb_raster_ellipse(ekfb_handle h, int W, int H, double cx, double cy, const double* S, int max_axes, int value,
                         uint8_t* img_inout);
 
+/* ---- NCC active search (the north star's matching path; the reference has no counterpart) ----------- */
+/* Matching by normalised cross-correlation of 11 x 11 templates inside each feature's gate ellipse over a 3-level image
+ * pyramid, in place of ekfb_match (csrc/ekf_ncc.cuh states the exact rule; oracle/ncc_oracle.py restates it on the CPU).
+ * gray: pixels_y rows of pixels_x bytes, `stride` bytes apart; the pyramid is built on the device. */
+int ekfb_ncc_set_image(ekfb_handle h, int filter, const uint8_t* gray, int stride);
+/* templates of features [first_feature, first_feature + count): count x 3 levels x 121 bytes (row-major 11 x 11) */
+int ekfb_ncc_set_templates(ekfb_handle h, int filter, int first_feature, int count, const uint8_t* templates);
+/* after ekfb_measure, instead of ekfb_match: fills the same match arrays (z = matched pixel, distance = 1 - score) */
+int ekfb_match_ncc(ekfb_handle h, double ncc_min);
+/* level-0 score (-2: no candidate) and start level (-1: not predicted) per feature of the last ekfb_match_ncc */
+int ekfb_ncc_get_scores(ekfb_handle h, int filter, double* score, int32_t* level);
+/* one pyramid level back to the host (w x h bytes, tightly packed); out may be NULL to query the size */
+int ekfb_ncc_get_level(ekfb_handle h, int filter, int level, uint8_t* out, int32_t* w, int32_t* h_out);
+
 /* ---- results ----------------------------------------------------------------------------------- */
 int ekfb_get_frame_info(ekfb_handle h, int filter, ekfb_frame_info* info);
 /* per-filter records of all filters, to a host buffer (n_filters records) */

@@ -221,6 +221,31 @@ class EkfBatch:
                                             ctypes.c_double(cy), _ptr(S), ctypes.c_int(max_axes), ctypes.c_int(value), _ptr(img)))
         return img
 
+    # ---- NCC active search (north-star matching path) ----
+    def ncc_set_image(self, f, gray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        self._ck(self.L.ekfb_ncc_set_image(self.h, ctypes.c_int(f), _ptr(gray), ctypes.c_int(gray.shape[1])))
+
+    def ncc_set_templates(self, f, first, templates):
+        t = np.ascontiguousarray(templates, np.uint8).reshape(-1, 3, 121)
+        self._ck(self.L.ekfb_ncc_set_templates(self.h, ctypes.c_int(f), ctypes.c_int(first), ctypes.c_int(t.shape[0]), _ptr(t)))
+
+    def match_ncc(self, ncc_min=0.8):
+        self._ck(self.L.ekfb_match_ncc(self.h, ctypes.c_double(ncc_min)))
+
+    def ncc_scores(self, f=0):
+        _, N = self.dims(f)
+        s = np.zeros(max(N, 1)); lv = np.zeros(max(N, 1), np.int32)
+        self._ck(self.L.ekfb_ncc_get_scores(self.h, ctypes.c_int(f), _ptr(s), _ptr(lv)))
+        return s[:N], lv[:N]
+
+    def ncc_level(self, f, level):
+        w, h = ctypes.c_int32(), ctypes.c_int32()
+        self._ck(self.L.ekfb_ncc_get_level(self.h, ctypes.c_int(f), ctypes.c_int(level), None, ctypes.byref(w), ctypes.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self._ck(self.L.ekfb_ncc_get_level(self.h, ctypes.c_int(f), ctypes.c_int(level), _ptr(out), None, None))
+        return out
+
     # ---- isolated kernels / timing ----
     def test_downdate(self, P, Wt):
         P = np.ascontiguousarray(P, np.float64); Wt = np.ascontiguousarray(Wt, np.float64)

@@ -14,6 +14,7 @@
 #include "ekf_linalg.cuh"
 #include "ekf_schain.cuh"
 #include "ekf_map.cuh"
+#include "ekf_ncc.cuh"
 
 using namespace ekf;
 
@@ -91,6 +92,13 @@ struct ekfb_ctx {
     bool map_ready = false;           // map-management buffers are allocated on first use
     uint8_t* mask2 = nullptr;         // new-feature mask (E/DetectNewImageFeatures.cpp:101-122), built by ekfb_map_management
     bool mask2_valid = false;
+    // NCC active search (ekf_ncc.cuh): image pyramid, templates and one TMA descriptor per filter and level
+    bool ncc_ready = false;
+    uint8_t* ncc_img[kNccLevels] = {nullptr, nullptr, nullptr};
+    size_t ncc_level_bytes[kNccLevels] = {0, 0, 0};
+    NccView ncc;
+    uint8_t* ncc_tmpl = nullptr;
+    std::vector<NccMaps> ncc_maps;
 };
 
 template <typename T>
@@ -884,6 +892,137 @@ extern "C" int ekfb_raster_ellipse(ekfb_handle c, int W, int H, double cx, doubl
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d);
     CK(e);
+    return EKFB_OK;
+}
+
+// ---- NCC active search (north-star path, ekf_ncc.cuh) ---------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ensure_ncc(ekfb_ctx* c)
+{
+    if (c->ncc_ready) return EKFB_OK;
+    DevView& v = c->v;
+    NccView& nv = c->ncc;
+    int W = v.W, H = v.H;
+    for (int l = 0; l < kNccLevels; ++l) {
+        nv.W[l] = W; nv.H[l] = H; nv.pitch[l] = rup(W, 16);
+        c->ncc_level_bytes[l] = (size_t)nv.pitch[l] * H;
+        ALLOC(c->ncc_img[l], (size_t)c->F * c->ncc_level_bytes[l]);
+        W /= 2; H /= 2;
+    }
+    ALLOC(c->ncc_tmpl, (size_t)c->F * c->Nmax * kNccLevels * 128);
+    ALLOC(nv.score, (size_t)c->F * c->Nmax);
+    ALLOC(nv.level, (size_t)c->F * c->Nmax);
+    nv.ncc_min = 0.8;
+    // one 2-D tensor map per filter and level: bytes, box 48 x 36, no swizzle, zero fill outside the image
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+        g_err = "cuTensorMapEncodeTiled is not available in this driver";
+        return EKFB_ERR_CUDA;
+    }
+    EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
+    c->ncc_maps.resize(c->F);
+    for (int f = 0; f < c->F; ++f)
+        for (int l = 0; l < kNccLevels; ++l) {
+            const cuuint64_t dims[2] = {(cuuint64_t)nv.W[l], (cuuint64_t)nv.H[l]};
+            const cuuint64_t strides[1] = {(cuuint64_t)nv.pitch[l]};
+            const cuuint32_t box[2] = {(cuuint32_t)kNccBoxW, (cuuint32_t)kNccBoxH};
+            const cuuint32_t estr[2] = {1, 1};
+            CUresult r = encode(&c->ncc_maps[f].m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l],
+                                dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                g_err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+                return EKFB_ERR_CUDA;
+            }
+        }
+    c->ncc_ready = true;
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_ncc_set_image(ekfb_handle c, int f, const uint8_t* gray, int stride)
+{
+    REQUIRE(c && gray, "null argument");
+    REQUIRE(f >= 0 && f < c->F && stride >= c->v.W, "bad filter index or stride");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_ncc(c);
+    if (rc != EKFB_OK) return rc;
+    NccView& nv = c->ncc;
+    uint8_t* L[kNccLevels];
+    for (int l = 0; l < kNccLevels; ++l) L[l] = c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l];
+    CK(cudaMemcpy2DAsync(L[0], nv.pitch[0], gray, stride, nv.W[0], nv.H[0], cudaMemcpyHostToDevice, c->stream));
+    for (int l = 1; l < kNccLevels; ++l) {
+        k_pyr_down<<<dim3(cdiv(nv.W[l], 32), cdiv(nv.H[l], 8)), dim3(32, 8), 0, c->stream>>>(L[l - 1], nv.pitch[l - 1], L[l], nv.pitch[l],
+                                                                                          nv.W[l], nv.H[l]);
+        count_launch(c);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));   // the caller's image may be pageable
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_ncc_get_level(ekfb_handle c, int f, int level, uint8_t* out, int32_t* w, int32_t* h)
+{
+    REQUIRE(c && c->ncc_ready, "no image set");
+    REQUIRE(f >= 0 && f < c->F && level >= 0 && level < kNccLevels, "bad filter index or level");
+    CK(cudaSetDevice(c->device));
+    NccView& nv = c->ncc;
+    if (w) *w = nv.W[level];
+    if (h) *h = nv.H[level];
+    if (out)
+        CK(cudaMemcpy2DAsync(out, nv.W[level], c->ncc_img[level] + (size_t)f * c->ncc_level_bytes[level], nv.pitch[level], nv.W[level],
+                             nv.H[level], cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_ncc_set_templates(ekfb_handle c, int f, int first_feature, int count, const uint8_t* templates)
+{
+    REQUIRE(c && templates, "null argument");
+    REQUIRE(f >= 0 && f < c->F && first_feature >= 0 && count >= 0 && first_feature + count <= c->Nmax, "bad filter index or range");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_ncc(c);
+    if (rc != EKFB_OK) return rc;
+    uint8_t* dst = c->ncc_tmpl + ((size_t)f * c->Nmax + first_feature) * kNccLevels * 128;
+    CK(cudaMemcpy2DAsync(dst, 128, templates, kNccPP, kNccPP, (size_t)count * kNccLevels, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_match_ncc(ekfb_handle c, double ncc_min)
+{
+    REQUIRE(c && c->ncc_ready, "ekfb_ncc_set_image / ekfb_ncc_set_templates first");
+    CK(cudaSetDevice(c->device));
+    GroupScope gs(c, G_MATCH);
+    for (int f = 0; f < c->F; ++f) {
+        if (c->hN[f] == 0) continue;
+        NccView nv = c->ncc;
+        nv.tmpl = c->ncc_tmpl + (size_t)f * c->Nmax * kNccLevels * 128;
+        nv.score = c->ncc.score + (size_t)f * c->Nmax;
+        nv.level = c->ncc.level + (size_t)f * c->Nmax;
+        nv.ncc_min = ncc_min;
+        k_search_ncc<<<c->hN[f], 128, 0, c->stream>>>(c->v, nv, c->ncc_maps[f], f);
+        count_launch(c);
+    }
+    k_after_match<<<c->F, 256, 0, c->stream>>>(c->v);
+    count_launch(c);
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_ncc_get_scores(ekfb_handle c, int f, double* score, int32_t* level)
+{
+    REQUIRE(c && c->ncc_ready, "no NCC search has run");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    const int N = c->hN[f];
+    if (score) CK(cudaMemcpyAsync(score, c->ncc.score + (size_t)f * c->Nmax, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+    if (level) CK(cudaMemcpyAsync(level, c->ncc.level + (size_t)f * c->Nmax, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return EKFB_OK;
 }
 

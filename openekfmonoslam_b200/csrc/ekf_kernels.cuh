@@ -634,6 +634,7 @@ __global__ void k_update_map_features(DevView v)
     if (v.vis[fj]) v.tpred[fj] += 1;
     if (v.inl[fj] || v.resc[fj]) {
         v.tmatch[fj] += 1;
+        if (v.mkp[fj] < 0) return;   // matched by the NCC search: there is no keypoint descriptor to refresh from
         const uint32_t* src = reinterpret_cast<const uint32_t*>(v.kpdesc[f] + (size_t)v.mkp[fj] * 32);
         uint32_t* dst = reinterpret_cast<uint32_t*>(v.desc + fj * 32);
 #pragma unroll

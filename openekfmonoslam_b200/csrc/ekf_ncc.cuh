@@ -1,0 +1,201 @@
+// ekf_ncc.cuh -- active search by normalised cross-correlation (the north star's matching path; the reference has no
+// counterpart: its matcher is the descriptor path of ekf_kernels.cuh, see SURVEY.md 0.3 / 8b `ekfb_match_ncc`).
+//
+// Specification (restated on the CPU in oracle/ncc_oracle.py, which the GPU tests compare against bit for bit):
+//   pyramid   L0 = the frame (8-bit grey), L(l+1)(y,x) = (a + b + c + d + 2) >> 2 over the 2x2 block, floor(W/2) x floor(H/2)
+//   template  per feature and level an 11 x 11 8-bit patch T_l
+//   search    for every predicted feature: centre c0 = (int)(float)h, integer gate axes (aw, ah) and angle as in the
+//             descriptor matcher (E/Matching.cpp:227-239); start level l = smallest level with ceil(max(aw,ah) / 2^l) <= 12
+//             (at most 2), window half-size R = min(12, that value); candidates = displacements in [-R, R]^2 around c0 >> l
+//             whose patch lies inside the level and whose level-0 position passes the foci gate (C/EKFMath.cpp:302-351);
+//             score = (121 S_tw - S_t S_w) / sqrt((121 S_tt - S_t^2)(121 S_ww - S_w^2)) from exact integer sums (flat patches
+//             are skipped); best = highest score, ties to the smaller dy, then dx; then one 3 x 3 refinement around twice
+//             the best position per finer level.  Match iff the level-0 score >= ncc_min: z = that pixel.
+//
+// One CTA per feature.  The search window -- (2R + 11)^2 <= 35 x 35 bytes -- is staged in shared memory by ONE TMA 2-D
+// tile load per level (cp.async.bulk.tensor.2d, 48 x 36 byte box, zero fill outside the image, completion on an
+// mbarrier); warp w takes displacement rows w, w + 4, ..., lane = dx, so the 32 lanes of a warp read consecutive window
+// bytes (conflict-free) and the same template byte (broadcast); template sums and the arg-max are warp-shuffle
+// reductions.  Bound: shared-memory bandwidth (2 x 121 byte reads per candidate) / latency; HBM traffic is the
+// window bytes only.
+#pragma once
+
+#include <cuda.h>
+
+#include "ekf_kernels.cuh"
+
+namespace ekf {
+
+constexpr int kNccP = 11, kNccPP = 121, kNccR = 12, kNccBoxW = 48, kNccBoxH = 36, kNccLevels = 3;
+
+struct NccMaps { CUtensorMap m[kNccLevels]; };
+struct NccView {
+    int W[kNccLevels], H[kNccLevels], pitch[kNccLevels];
+    const uint8_t* tmpl;   // [Nmax][3][128] (121 used)
+    double* score;         // [Nmax] level-0 score of the last search (-2: none)
+    int* level;            // [Nmax] start level
+    double ncc_min;
+};
+
+// L(l+1) from L(l).  grid (ceil(Wo/32), ceil(Ho/8)), block (32, 8)
+__global__ void k_pyr_down(const uint8_t* src, int sp, uint8_t* dst, int dp, int Wo, int Ho)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= Wo || y >= Ho) return;
+    const uint8_t* s = src + (size_t)(2 * y) * sp + 2 * x;
+    dst[(size_t)y * dp + x] = (uint8_t)((s[0] + s[1] + s[sp] + s[sp + 1] + 2) >> 2);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int phase)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int x, int y, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+                 : "memory");
+}
+
+struct NccBest { double s; int dy, dx; };
+__device__ __forceinline__ bool ncc_better(double s, int dy, int dx, const NccBest& b)
+{
+    return s > b.s || (s == b.s && (dy < b.dy || (dy == b.dy && dx < b.dx)));
+}
+
+// grid N (one CTA per feature of filter f), block 128
+__global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, const __grid_constant__ NccMaps maps, int f)
+{
+    __shared__ __align__(128) uint8_t win[kNccBoxW * kNccBoxH];
+    __shared__ __align__(16) uint8_t tm[128];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ NccBest wbest[4];
+    __shared__ int sBest[3];   // x, y (level coordinates), valid
+    __shared__ int sSum[2];    // S_t, S_tt
+    const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = fdims(v, f)[D_N_FEAT];
+    if (j >= N) return;
+    const size_t fj = (size_t)f * v.Nmax + j;
+    if (tid == 0) {   // unmatched unless the search succeeds
+        v.mflag[fj] = 0;
+        v.mkp[fj] = -1;
+        nv.score[j] = -2.0;
+        nv.level[j] = -1;
+    }
+    if (!v.vis[fj]) return;
+    const int aw = __float2int_rn(v.ellax[fj * 2]), ah = __float2int_rn(v.ellax[fj * 2 + 1]);
+    const float cxf = (float)v.h[fj * 2], cyf = (float)v.h[fj * 2 + 1];
+    const double ang = v.ellang[fj];
+    const int R0 = max(aw, ah);
+    int lev = 0;
+    while (lev < kNccLevels - 1 && ((R0 + (1 << lev) - 1) >> lev) > kNccR) ++lev;
+    int R = min(kNccR, (R0 + (1 << lev) - 1) >> lev);
+    int cx = ((int)cxf) >> lev, cy = ((int)cyf) >> lev;   // arithmetic shift: floor, also for negative centres
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        nv.level[j] = lev;
+    }
+    __syncthreads();
+    int phase = 0;
+    double finalScore = -2.0;
+    bool first = true;
+    for (int l = lev; l >= 0; --l) {
+        const int Wl = nv.W[l], Hl = nv.H[l];
+        if (tid == 0) {
+            mbar_expect_tx(&bar, kNccBoxW * kNccBoxH);
+            tma_load_2d(win, &maps.m[l], cx - R - 5, cy - R - 5, &bar);
+        }
+        if (tid < 32) reinterpret_cast<uint32_t*>(tm)[tid] = reinterpret_cast<const uint32_t*>(nv.tmpl + ((size_t)j * kNccLevels + l) * 128)[tid];
+        __syncthreads();
+        if (warp == 0) {   // template sums by warp-shuffle reduction
+            int st = 0, stt = 0;
+            for (int e = lane; e < kNccPP; e += 32) { const int t = tm[e]; st += t; stt += t * t; }
+            for (int o = 16; o > 0; o >>= 1) { st += __shfl_down_sync(0xffffffffu, st, o); stt += __shfl_down_sync(0xffffffffu, stt, o); }
+            if (lane == 0) { sSum[0] = st; sSum[1] = stt; }
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        __syncthreads();
+        const long long St = sSum[0], Stt = sSum[1];
+        const long long dt = kNccPP * Stt - St * St;
+        NccBest best = {-3.0, 0, 0};
+        for (int iy = warp; iy <= 2 * R; iy += 4) {
+            const int dy = iy - R, dx = lane - R, px = cx + dx, py = cy + dy;
+            bool ok = lane <= 2 * R && dt != 0 && px >= 5 && px < Wl - 5 && py >= 5 && py < Hl - 5;
+            if (ok && first) ok = inside_gate((float)(px << l), (float)(py << l), cxf, cyf, aw, ah, ang);
+            if (ok) {
+                int sw = 0, sww = 0, stw = 0;
+                const uint8_t* wp = win + iy * kNccBoxW + lane;
+#pragma unroll
+                for (int ty = 0; ty < kNccP; ++ty)
+#pragma unroll
+                    for (int tx = 0; tx < kNccP; ++tx) {
+                        const int w = wp[ty * kNccBoxW + tx], t = tm[ty * kNccP + tx];
+                        sw += w; sww += w * w; stw += t * w;
+                    }
+                const long long num = (long long)kNccPP * stw - St * sw;
+                const long long dw = (long long)kNccPP * sww - (long long)sw * sw;
+                if (dw != 0) {
+                    const double s = __ddiv_rn((double)num, __dsqrt_rn(__dmul_rn((double)dt, (double)dw)));
+                    if (ncc_better(s, dy, dx, best)) { best.s = s; best.dy = dy; best.dx = dx; }
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {   // warp arg-max with the tie rule
+            NccBest ot;
+            ot.s = __shfl_down_sync(0xffffffffu, best.s, o);
+            ot.dy = __shfl_down_sync(0xffffffffu, best.dy, o);
+            ot.dx = __shfl_down_sync(0xffffffffu, best.dx, o);
+            if (ncc_better(ot.s, ot.dy, ot.dx, best)) best = ot;
+        }
+        if (lane == 0) wbest[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            NccBest b = wbest[0];
+            for (int w = 1; w < 4; ++w)
+                if (ncc_better(wbest[w].s, wbest[w].dy, wbest[w].dx, b)) b = wbest[w];
+            sBest[2] = b.s > -2.5;
+            sBest[0] = cx + b.dx;
+            sBest[1] = cy + b.dy;
+            if (l == 0 && sBest[2]) nv.score[j] = b.s;
+        }
+        __syncthreads();
+        if (!sBest[2]) return;   // no valid candidate at this level
+        if (l == 0) {
+            finalScore = wbest[0].s;   // only used by thread 0 below through nv.score
+            cx = sBest[0];
+            cy = sBest[1];
+        } else {
+            cx = 2 * sBest[0];
+            cy = 2 * sBest[1];
+            R = 1;
+            first = false;
+        }
+        __syncthreads();   // window and wbest are rewritten by the next level
+    }
+    (void)finalScore;
+    if (tid == 0 && nv.score[j] >= nv.ncc_min) {
+        v.mflag[fj] = 1;
+        v.z[fj * 2] = (double)cx;
+        v.z[fj * 2 + 1] = (double)cy;
+        v.mdist[fj] = (float)(1.0 - nv.score[j]);
+        v.mkp[fj] = -1;
+    }
+}
+
+}  // namespace ekf
