@@ -92,13 +92,12 @@ struct ekfb_ctx {
     bool map_ready = false;           // map-management buffers are allocated on first use
     uint8_t* mask2 = nullptr;         // new-feature mask (E/DetectNewImageFeatures.cpp:101-122), built by ekfb_map_management
     bool mask2_valid = false;
-    // NCC active search (ekf_ncc.cuh): image pyramid, templates and one TMA descriptor per filter and level
+    // NCC active search (ekf_ncc.cuh): image pyramid and templates
     bool ncc_ready = false;
     uint8_t* ncc_img[kNccLevels] = {nullptr, nullptr, nullptr};
     size_t ncc_level_bytes[kNccLevels] = {0, 0, 0};
     NccView ncc;
     uint8_t* ncc_tmpl = nullptr;
-    std::vector<NccMaps> ncc_maps;
 };
 
 template <typename T>
@@ -896,10 +895,6 @@ extern "C" int ekfb_raster_ellipse(ekfb_handle c, int W, int H, double cx, doubl
 }
 
 // ---- NCC active search (north-star path, ekf_ncc.cuh) ---------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static int ensure_ncc(ekfb_ctx* c)
 {
     if (c->ncc_ready) return EKFB_OK;
@@ -916,30 +911,6 @@ static int ensure_ncc(ekfb_ctx* c)
     ALLOC(nv.score, (size_t)c->F * c->Nmax);
     ALLOC(nv.level, (size_t)c->F * c->Nmax);
     nv.ncc_min = 0.8;
-    // one 2-D tensor map per filter and level: bytes, box 48 x 36, no swizzle, zero fill outside the image
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) {
-        g_err = "cuTensorMapEncodeTiled is not available in this driver";
-        return EKFB_ERR_CUDA;
-    }
-    EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
-    c->ncc_maps.resize(c->F);
-    for (int f = 0; f < c->F; ++f)
-        for (int l = 0; l < kNccLevels; ++l) {
-            const cuuint64_t dims[2] = {(cuuint64_t)nv.W[l], (cuuint64_t)nv.H[l]};
-            const cuuint64_t strides[1] = {(cuuint64_t)nv.pitch[l]};
-            const cuuint32_t box[2] = {(cuuint32_t)kNccBoxW, (cuuint32_t)kNccBoxH};
-            const cuuint32_t estr[2] = {1, 1};
-            CUresult r = encode(&c->ncc_maps[f].m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l],
-                                dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) {
-                g_err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
-                return EKFB_ERR_CUDA;
-            }
-        }
     c->ncc_ready = true;
     return EKFB_OK;
 }
@@ -1005,7 +976,8 @@ extern "C" int ekfb_match_ncc(ekfb_handle c, double ncc_min)
         nv.score = c->ncc.score + (size_t)f * c->Nmax;
         nv.level = c->ncc.level + (size_t)f * c->Nmax;
         nv.ncc_min = ncc_min;
-        k_search_ncc<<<c->hN[f], 128, 0, c->stream>>>(c->v, nv, c->ncc_maps[f], f);
+        for (int l = 0; l < kNccLevels; ++l) nv.img[l] = c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l];
+        k_search_ncc<<<c->hN[f], 128, 0, c->stream>>>(c->v, nv, f);
         count_launch(c);
     }
     k_after_match<<<c->F, 256, 0, c->stream>>>(c->v);

@@ -12,25 +12,26 @@
 //             are skipped); best = highest score, ties to the smaller dy, then dx; then one 3 x 3 refinement around twice
 //             the best position per finer level.  Match iff the level-0 score >= ncc_min: z = that pixel.
 //
-// One CTA per feature.  The search window -- (2R + 11)^2 <= 35 x 35 bytes -- is staged in shared memory by ONE TMA 2-D
-// tile load per level (cp.async.bulk.tensor.2d, 48 x 36 byte box, zero fill outside the image, completion on an
-// mbarrier); warp w takes displacement rows w, w + 4, ..., lane = dx, so the 32 lanes of a warp read consecutive window
-// bytes (conflict-free) and the same template byte (broadcast); template sums and the arg-max are warp-shuffle
-// reductions.  Bound: shared-memory bandwidth (2 x 121 byte reads per candidate) / latency; HBM traffic is the
-// window bytes only.
+// One CTA per feature.  The search window -- (2R + 11)^2 <= 35 x 35 bytes -- is staged in shared memory by the TMA
+// engine: one bulk asynchronous copy (cp.async.bulk.shared::cluster.global, 64 bytes from a 16-byte aligned source) per
+// window row, all completing on one mbarrier (complete_tx); rows and columns outside the image are clamped away (their
+// bytes are never read: a candidate's patch must lie inside the level).  The tensor-map form (cp.async.bulk.tensor.2d)
+// would need one instruction per window instead of 35, but raised "illegal instruction" at the UTMALDG on this pool's
+// driver (580.x) in every variant tried -- tools/tma_probe.cu keeps the reproducer -- so the 1-D form is used.
+// Warp w takes displacement rows w, w + 4, ..., lane = dx, so the 32 lanes of a warp read consecutive window bytes
+// (conflict-free) and the same template byte (broadcast); template sums and the arg-max are warp-shuffle reductions.
+// Bound: shared-memory bandwidth (2 x 121 byte reads per candidate) / latency; HBM traffic is the window bytes only.
 #pragma once
-
-#include <cuda.h>
 
 #include "ekf_kernels.cuh"
 
 namespace ekf {
 
-constexpr int kNccP = 11, kNccPP = 121, kNccR = 12, kNccBoxW = 48, kNccBoxH = 36, kNccLevels = 3;
+constexpr int kNccP = 11, kNccPP = 121, kNccR = 12, kNccBoxW = 64, kNccBoxH = 36, kNccLevels = 3;
 
-struct NccMaps { CUtensorMap m[kNccLevels]; };
 struct NccView {
     int W[kNccLevels], H[kNccLevels], pitch[kNccLevels];
+    const uint8_t* img[kNccLevels];   // this filter's pyramid levels, 16-byte aligned rows
     const uint8_t* tmpl;   // [Nmax][3][128] (121 used)
     double* score;         // [Nmax] level-0 score of the last search (-2: none)
     int* level;            // [Nmax] start level
@@ -64,11 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int phase)
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
         "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int x, int y, uint64_t* bar)
+// TMA bulk copy global -> shared (bytes a multiple of 16, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void tma_bulk_load(void* smem, const void* gmem, int bytes, uint64_t* bar)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                     smem_u32(smem)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)), "l"(gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ bool ncc_better(double s, int dy, int dx, const NccBe
 }
 
 // grid N (one CTA per feature of filter f), block 128
-__global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, const __grid_constant__ NccMaps maps, int f)
+__global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f)
 {
     __shared__ __align__(128) uint8_t win[kNccBoxW * kNccBoxH];
     __shared__ __align__(16) uint8_t tm[128];
@@ -116,9 +117,17 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, const
     bool first = true;
     for (int l = lev; l >= 0; --l) {
         const int Wl = nv.W[l], Hl = nv.H[l];
+        // window origin (x0, y0); columns are fetched from the 16-byte aligned x0a <= x0, clamped to the row
+        const int x0 = cx - R - 5, y0 = cy - R - 5, x0a = x0 & ~15, xoff = x0 - x0a;
         if (tid == 0) {
-            mbar_expect_tx(&bar, kNccBoxW * kNccBoxH);
-            tma_load_2d(win, &maps.m[l], cx - R - 5, cy - R - 5, &bar);
+            const int xs = max(x0a, 0), xe = min(x0a + kNccBoxW, nv.pitch[l]);
+            const int ys = max(y0, 0), ye = min(y0 + kNccBoxH, Hl);
+            const int bytes = xe - xs, rows = ye - ys;
+            const bool any = bytes > 0 && rows > 0;
+            mbar_expect_tx(&bar, any ? bytes * rows : 0);
+            if (any)
+                for (int yy = ys; yy < ye; ++yy)
+                    tma_bulk_load(win + (yy - y0) * kNccBoxW + (xs - x0a), nv.img[l] + (size_t)yy * nv.pitch[l] + xs, bytes, &bar);
         }
         if (tid < 32) reinterpret_cast<uint32_t*>(tm)[tid] = reinterpret_cast<const uint32_t*>(nv.tmpl + ((size_t)j * kNccLevels + l) * 128)[tid];
         __syncthreads();
@@ -140,7 +149,7 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, const
             if (ok && first) ok = inside_gate((float)(px << l), (float)(py << l), cxf, cyf, aw, ah, ang);
             if (ok) {
                 int sw = 0, sww = 0, stw = 0;
-                const uint8_t* wp = win + iy * kNccBoxW + lane;
+                const uint8_t* wp = win + iy * kNccBoxW + lane + xoff;
 #pragma unroll
                 for (int ty = 0; ty < kNccP; ++ty)
 #pragma unroll
