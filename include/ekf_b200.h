@@ -158,6 +158,16 @@ int ekfb_get_new_feature_mask(ekfb_handle h, int filter, uint8_t* mask);
 int ekfb_raster_ellipse(ekfb_handle h, int W, int H, double cx, double cy, const double* S, int max_axes, int value,
                         uint8_t* img_inout);
 
+/* ---- detector + descriptor on the device (what detector->detect + extractor->compute do, E/Matching.cpp:204-215) */
+/* the frame as 8-bit grey (pixels_y rows of pixels_x bytes, `stride` bytes apart); also builds the NCC pyramid */
+int ekfb_set_image(ekfb_handle h, int filter, const uint8_t* gray, int stride);
+/* FAST-9/16 corners with 3x3 non-maximum suppression (OpenCV's FastFeatureDetector(threshold, true), the "FAST" entry of the
+ * reference's FeatureDetectorFactory) in raster order, keypoints closer than 18 pixels to the border dropped, each with a
+ * 256-bit BRIEF-style descriptor; they replace ekfb_set_keypoints for this frame.  At most max_keypoints are kept. */
+int ekfb_detect_keypoints(ekfb_handle h, int filter, int threshold, int32_t* n_keypoints);
+/* the current frame's keypoints back to the host (n x 2 float32, n x 32 bytes; n from ekfb_detect_keypoints / ekfb_set_keypoints) */
+int ekfb_get_keypoints(ekfb_handle h, int filter, float* xy, uint8_t* desc);
+
 /* ---- NCC active search (the north star's matching path; the reference has no counterpart) ----------- */
 /* Matching by normalised cross-correlation of 11 x 11 templates inside each feature's gate ellipse over a 3-level image
  * pyramid, in place of ekfb_match (csrc/ekf_ncc.cuh states the exact rule; oracle/ncc_oracle.py restates it on the CPU).

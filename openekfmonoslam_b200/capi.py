@@ -221,6 +221,21 @@ class EkfBatch:
                                             ctypes.c_double(cy), _ptr(S), ctypes.c_int(max_axes), ctypes.c_int(value), _ptr(img)))
         return img
 
+    # ---- detector + descriptor on the device ----
+    def set_image(self, f, gray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        self._ck(self.L.ekfb_set_image(self.h, ctypes.c_int(f), _ptr(gray), ctypes.c_int(gray.shape[1])))
+
+    def detect_keypoints(self, f, threshold):
+        n = ctypes.c_int32()
+        self._ck(self.L.ekfb_detect_keypoints(self.h, ctypes.c_int(f), ctypes.c_int(threshold), ctypes.byref(n)))
+        return n.value
+
+    def get_keypoints(self, f, n):
+        xy = np.zeros((max(n, 1), 2), np.float32); ds = np.zeros((max(n, 1), 32), np.uint8)
+        self._ck(self.L.ekfb_get_keypoints(self.h, ctypes.c_int(f), _ptr(xy), _ptr(ds)))
+        return xy[:n], ds[:n]
+
     # ---- NCC active search (north-star matching path) ----
     def ncc_set_image(self, f, gray):
         gray = np.ascontiguousarray(gray, np.uint8)

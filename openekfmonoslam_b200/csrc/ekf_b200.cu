@@ -15,6 +15,7 @@
 #include "ekf_schain.cuh"
 #include "ekf_map.cuh"
 #include "ekf_ncc.cuh"
+#include "ekf_frontend.cuh"
 
 using namespace ekf;
 
@@ -98,6 +99,10 @@ struct ekfb_ctx {
     size_t ncc_level_bytes[kNccLevels] = {0, 0, 0};
     NccView ncc;
     uint8_t* ncc_tmpl = nullptr;
+    // device front end (ekf_frontend.cuh): corner-score image, per-row counts / offsets, keypoint count per filter
+    uint8_t* fe_score = nullptr;
+    int* fe_rows = nullptr;   // [F][2][H]
+    int* fe_count = nullptr;  // [F]
 };
 
 template <typename T>
@@ -911,6 +916,10 @@ static int ensure_ncc(ekfb_ctx* c)
     ALLOC(nv.score, (size_t)c->F * c->Nmax);
     ALLOC(nv.level, (size_t)c->F * c->Nmax);
     nv.ncc_min = 0.8;
+    ALLOC(c->fe_score, (size_t)c->F * c->ncc_level_bytes[0]);
+    ALLOC(c->fe_rows, (size_t)c->F * 2 * v.H);
+    ALLOC(c->fe_count, (size_t)c->F);
+    CK(cudaMemcpyToSymbolAsync(c_brief, kBriefPattern, sizeof(kBriefPattern), 0, cudaMemcpyHostToDevice, c->stream));
     c->ncc_ready = true;
     return EKFB_OK;
 }
@@ -933,6 +942,58 @@ extern "C" int ekfb_ncc_set_image(ekfb_handle c, int f, const uint8_t* gray, int
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));   // the caller's image may be pageable
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_set_image(ekfb_handle c, int f, const uint8_t* gray, int stride) { return ekfb_ncc_set_image(c, f, gray, stride); }
+
+// detector + descriptor on the device for the image of ekfb_set_image: the keypoints become the frame's front-end output
+extern "C" int ekfb_detect_keypoints(ekfb_handle c, int f, int threshold, int32_t* n_kp)
+{
+    REQUIRE(c && c->ncc_ready, "ekfb_set_image first");
+    REQUIRE(f >= 0 && f < c->F && threshold >= 1 && threshold <= 254, "bad filter index or threshold");
+    CK(cudaSetDevice(c->device));
+    GroupScope gs(c, G_MATCH);
+    NccView& nv = c->ncc;
+    const int W = nv.W[0], H = nv.H[0], pitch = nv.pitch[0];
+    const uint8_t* img = c->ncc_img[0] + (size_t)f * c->ncc_level_bytes[0];
+    uint8_t* score = c->fe_score + (size_t)f * c->ncc_level_bytes[0];
+    int* rowCount = c->fe_rows + (size_t)f * 2 * H;
+    int* rowOff = rowCount + H;
+    int* count = c->fe_count + f;
+    float* dxy = c->d_kpxy + (size_t)f * c->Kpmax * 2;
+    uint8_t* dds = c->d_kpdesc + (size_t)f * c->Kpmax * 32;
+    k_fast_score<<<dim3(cdiv(W, 32), cdiv(H, 8)), dim3(32, 8), 0, c->stream>>>(img, pitch, W, H, threshold, score);
+    k_fast_rows<<<cdiv(H, 8), 256, 0, c->stream>>>(score, pitch, W, H, rowCount, rowOff, dxy, c->Kpmax, 0);
+    k_fast_scan<<<1, 1024, 0, c->stream>>>(rowCount, rowOff, H, c->Kpmax, count);
+    k_fast_rows<<<cdiv(H, 8), 256, 0, c->stream>>>(score, pitch, W, H, rowCount, rowOff, dxy, c->Kpmax, 1);
+    k_brief<<<cdiv(c->Kpmax, 8), 256, 0, c->stream>>>(img, pitch, W, H, dxy, count, dds);
+    count_launch(c, 5);
+    CK(cudaGetLastError());
+    int hcount = 0;
+    CK(cudaMemcpyAsync(&hcount, count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->hKp[f] = hcount;
+    c->h_kpxy_ptr[f] = dxy;
+    c->h_kpdesc_ptr[f] = dds;
+    c->h_dims[(size_t)f * D_STRIDE + D_N_KP] = hcount;
+    CK(cudaMemcpyAsync(c->d_kpxy_ptr + f, c->h_kpxy_ptr + f, sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_kpdesc_ptr + f, c->h_kpdesc_ptr + f, sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v.dims + (size_t)f * D_STRIDE + D_N_KP, c->h_dims + (size_t)f * D_STRIDE + D_N_KP, sizeof(int),
+                       cudaMemcpyHostToDevice, c->stream));
+    if (n_kp) *n_kp = hcount;
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_get_keypoints(ekfb_handle c, int f, float* xy, uint8_t* desc)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    const int n = c->hKp[f];
+    if (xy && n) CK(cudaMemcpyAsync(xy, c->h_kpxy_ptr[f], sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (desc && n) CK(cudaMemcpyAsync(desc, c->h_kpdesc_ptr[f], (size_t)32 * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return EKFB_OK;
 }
 
