@@ -115,6 +115,11 @@ public:
 
     // ---- additions (no counterpart in the reference's header) ----
     void setFrontEnd(FrontEnd* fe) { _frontEnd = fe; }
+    // detector + descriptor on the GPU instead of a host FrontEnd object: FAST-9/16 (threshold) + 3x3 NMS + BRIEF-style
+    // descriptor (ekfb_set_image / ekfb_detect_keypoints).  init / step then need the frame itself: CV_8UC1, CV_8UC3 (BGR,
+    // desktop: FileSequenceImageGenerator.cpp:82) or CV_8UC4 (Android: EKFNative.cpp:134-137), converted to grey like
+    // cv::cvtColor(COLOR_BGR2GRAY).
+    void useDeviceFrontEnd(int fastThreshold) { _deviceFrontEnd = true; _fastThreshold = fastThreshold; }
     void setDevice(int device) { _device = device; }
     void syncCovariance();
     const ekfb_frame_info& lastFrameInfo() const { return _info; }
@@ -127,6 +132,7 @@ public:
 private:
     void downloadState();
     void mirrorLayout();
+    bool acquireKeypoints(const cv::Mat& image);
     int addNewFeatures(int wanted, bool useDeviceMask);
     int _ekfSteps;
     std::string _strOutputPath;
@@ -134,6 +140,9 @@ private:
     int _maxFeatures, _device;
     bool _configOk;
     FrontEnd* _frontEnd;
+    bool _deviceFrontEnd;
+    int _fastThreshold;
+    std::vector<unsigned char> _gray;
     ekfb_handle _h;
     ekfb_frame_info _info;
     ekfb_map_result _mapResult;

@@ -134,7 +134,7 @@ void State::removeAllFeatures()
 
 EKF::EKF(const char* configurationFileName, const char* outputPath)
     : _ekfSteps(0), _strOutputPath(outputPath ? outputPath : ""), _maxFeatures(0), _device(0), _configOk(false),
-      _frontEnd(nullptr), _h(nullptr), _lastAdded(0), _stampR(0)
+      _frontEnd(nullptr), _deviceFrontEnd(false), _fastThreshold(20), _h(nullptr), _lastAdded(0), _stampR(0)
 {
     std::memset(&_info, 0, sizeof(_info));
     std::memset(&_mapResult, 0, sizeof(_mapResult));
@@ -283,9 +283,43 @@ int EKF::addNewFeatures(int wanted, bool useDeviceMask)
     return k;
 }
 
+// The frame's front-end output: either from the host FrontEnd object (uploaded with ekfb_set_keypoints) or detected and
+// described on the device from the image (then only copied back for the new-feature selection).
+bool EKF::acquireKeypoints(const cv::Mat& image)
+{
+    if (!_deviceFrontEnd) {
+        _frontEnd->detectAndDescribe(image, _kps, _desc);
+        std::vector<float> xy(_kps.size() * 2);
+        for (size_t i = 0; i < _kps.size(); ++i) { xy[2 * i] = _kps[i].x; xy[2 * i + 1] = _kps[i].y; }
+        return ekfb_set_keypoints(_h, 0, xy.data(), _desc.data(), (int)_kps.size()) == EKFB_OK;
+    }
+    const int W = _cfg.params.pixels_x, H = _cfg.params.pixels_y;
+    if (image.empty() || image.cols != W || image.rows != H) {
+        std::cerr << "EKF: the device front end needs a " << W << "x" << H << " frame" << std::endl;
+        return false;
+    }
+    const int cn = (int)(image.elemSize());
+    const unsigned char* src = image.data;
+    int stride = (int)image.step;
+    if (cn != 1) {   // cv::cvtColor(BGR2GRAY / BGRA2GRAY) for 8-bit: (B 1868 + G 9617 + R 4899 + 2^13) >> 14
+        _gray.resize((size_t)W * H);
+        for (int y = 0; y < H; ++y) {
+            const unsigned char* r = image.data + (size_t)y * image.step;
+            for (int x = 0; x < W; ++x, r += cn) _gray[(size_t)y * W + x] = (unsigned char)((r[0] * 1868 + r[1] * 9617 + r[2] * 4899 + 8192) >> 14);
+        }
+        src = _gray.data();
+        stride = W;
+    }
+    int32_t n = 0;
+    if (ekfb_set_image(_h, 0, src, stride) != EKFB_OK || ekfb_detect_keypoints(_h, 0, _fastThreshold, &n) != EKFB_OK) return false;
+    _kps.resize(n);
+    _desc.resize((size_t)n * 32);
+    return ekfb_get_keypoints(_h, 0, reinterpret_cast<float*>(_kps.data()), _desc.data()) == EKFB_OK;
+}
+
 void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
 {
-    if (!_configOk || !_frontEnd) {
+    if (!_configOk || (!_frontEnd && !_deviceFrontEnd)) {
         std::cerr << "EKF::init: no configuration or no front end" << std::endl;
         return;
     }
@@ -308,7 +342,10 @@ void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
         return;
     }
     // detectNewImageFeatures(image, noPredictions, MinMatchesPerImage) + addFeaturesToStateAndCovariance, on the device
-    _frontEnd->detectAndDescribe(image, _kps, _desc);
+    if (!acquireKeypoints(image)) {
+        std::cerr << "EKF::init: " << ekfb_last_error() << std::endl;
+        return;
+    }
     _predXY.clear();
     _lastAdded = addNewFeatures(_cfg.policy.min_matches_per_image, false);
     mirrorLayout();
@@ -317,15 +354,12 @@ void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
 
 void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
 {
-    if (!_h || !_frontEnd) {
+    if (!_h || (!_frontEnd && !_deviceFrontEnd)) {
         std::cerr << "EKF::step: filter not initialised" << std::endl;
         return;
     }
     _ekfSteps++;
-    _frontEnd->detectAndDescribe(image, _kps, _desc);
-    std::vector<float> xy(_kps.size() * 2);
-    for (size_t i = 0; i < _kps.size(); ++i) { xy[2 * i] = _kps[i].x; xy[2 * i + 1] = _kps[i].y; }
-    bool ok = ekfb_set_keypoints(_h, 0, xy.data(), _desc.data(), (int)_kps.size()) == EKFB_OK;
+    bool ok = acquireKeypoints(image);
     float ms[8] = {0};
     if (ok && _trace.isOpen()) {
         // phase by phase with device timers, the seven intervals the reference writes (E/EKF.cpp:291 ... 618)
@@ -419,3 +453,42 @@ void EKF::syncCovariance()
     for (int i = 0; i < n; ++i) std::memcpy(stateCovarianceMatrix[i], &P[(size_t)i * n], sizeof(double) * n);
 }
 
+
+// ---- flat C binding of the class: what a JNI / ctypes / cgo layer binds (android/EKFMonoSlam/jni/EKFNative.cpp:79-218 keeps an
+// EKF* in a Java long and calls init / step with the camera frame, then reads state.position / orientation) ----
+extern "C" void* ekfb_host_ekf_create(const char* config, const char* outputPath, int device, int fastThreshold)
+{
+    EKF* e = new EKF(config, outputPath);
+    e->setDevice(device);
+    if (fastThreshold > 0) e->useDeviceFrontEnd(fastThreshold);
+    return e;
+}
+extern "C" void ekfb_host_ekf_destroy(void* e) { delete (EKF*)e; }
+// frames: 8-bit, `channels` = 1 (grey), 3 (BGR) or 4 (BGRA), tightly packed rows
+extern "C" int ekfb_host_ekf_init(void* e, const unsigned char* frame, int width, int height, int channels)
+{
+    cv::Mat img(height, width, channels == 1 ? CV_8UC1 : channels == 3 ? CV_8UC3 : CV_8UC4, const_cast<unsigned char*>(frame));
+    ((EKF*)e)->init(img);
+    return ((EKF*)e)->ok() ? 0 : 1;
+}
+extern "C" int ekfb_host_ekf_step(void* e, const unsigned char* frame, int width, int height, int channels)
+{
+    cv::Mat img(height, width, channels == 1 ? CV_8UC1 : channels == 3 ? CV_8UC3 : CV_8UC4, const_cast<unsigned char*>(frame));
+    ((EKF*)e)->step(img);
+    return ((EKF*)e)->ok() ? 0 : 1;
+}
+// x13 = r, q, v, omega; counts = {map features, state dimension, matches, inliers, rescued, removed, converted (-1 none), added}
+extern "C" void ekfb_host_ekf_get(void* ep, double* x13, int* counts8)
+{
+    EKF* e = (EKF*)ep;
+    const State& s = e->state;
+    for (int i = 0; i < 3; ++i) { x13[i] = s.position[i]; x13[7 + i] = s.linearVelocity[i]; x13[10 + i] = s.angularVelocity[i]; }
+    for (int i = 0; i < 4; ++i) x13[3 + i] = s.orientation[i];
+    int32_t n = 0, N = 0;
+    if (e->handle()) ekfb_get_dims(e->handle(), 0, &n, &N);
+    const ekfb_frame_info& fi = e->lastFrameInfo();
+    const ekfb_map_result& mr = e->lastMapResult();
+    const int c[8] = {(int)s.mapFeatures.size(), n, fi.n_matches, fi.n_inliers, fi.n_rescued, mr.n_removed_bad + mr.n_removed_unseen,
+                      mr.converted, e->lastNewFeatures()};
+    for (int i = 0; i < 8; ++i) counts8[i] = c[i];
+}

@@ -106,3 +106,41 @@ def test_gpu_frame_to_frame_from_device_keypoints():
         gpu.step()
         info = gpu.frame_info(0)
         assert info["status"] == 0 and info["n_matches"] >= 40 and info["n_inliers"] >= 25, info
+
+
+@pytest.mark.gpu
+def test_gpu_drop_in_class_with_device_front_end(tmp_path):
+    """The C++ EKF class through its flat C binding (what the Android JNI layer binds): BGR frames in, detector + descriptor,
+    matching, RANSAC, updates and map management on the device, state out."""
+    import ctypes
+    from openekfmonoslam_b200 import build
+    from openekfmonoslam_b200.params import synthetic_params, write_config
+    build.build_host()
+    host = ctypes.CDLL(build.HOST_OUT)
+    host.ekfb_host_ekf_create.restype = ctypes.c_void_p
+    W, H = 640, 480
+    cfg = str(tmp_path / "config.yml")
+    write_config(cfg, synthetic_params(W, H), 60, max_map_size=600,
+                 extra={"MapManagementFrequency": 1, "GoodFeatureMatchingPercent": 0.5, "InverseDepthLinearityIndexThreshold": 0.1,
+                        "DetectNewFeaturesImageAreasDivideTimes": 2, "DetectNewFeaturesImageMaskEllipseSize": 10})
+    world = np.tile(images()[2][1], (3, 3))[:600, :800]
+    e = ctypes.c_void_p(host.ekfb_host_ekf_create(cfg.encode(), b"", 0, 12))
+
+    def frame(t, channels):
+        g = np.ascontiguousarray(world[40:40 + H, 60 + t:60 + t + W])
+        return g if channels == 1 else np.ascontiguousarray(np.repeat(g[:, :, None], channels, axis=2))
+
+    f0 = frame(0, 3)
+    assert host.ekfb_host_ekf_init(e, f0.ctypes.data_as(ctypes.c_void_p), W, H, 3) == 0
+    x = np.zeros(13); c = np.zeros(8, np.int32)
+    host.ekfb_host_ekf_get(e, x.ctypes.data_as(ctypes.c_void_p), c.ctypes.data_as(ctypes.c_void_p))
+    assert c[0] == 60 and c[1] == 13 + 6 * 60 and x[3] == 1.0
+    for t in range(1, 6):
+        ch = (3, 4, 1)[t % 3]
+        ft = frame(t, ch)
+        assert host.ekfb_host_ekf_step(e, ft.ctypes.data_as(ctypes.c_void_p), W, H, ch) == 0
+        host.ekfb_host_ekf_get(e, x.ctypes.data_as(ctypes.c_void_p), c.ctypes.data_as(ctypes.c_void_p))
+        assert c[2] >= 40 and c[3] >= 25, (t, c)
+        assert abs(np.linalg.norm(x[3:7]) - 1.0) < 1e-12
+    assert c[0] >= 55
+    host.ekfb_host_ekf_destroy(e)
