@@ -85,6 +85,7 @@ struct ekfb_ctx {
     // r01_downdate_sweep.txt) that variant wins at every k and n tried (16 resident warps hide the tile read-modify-write
     // and the operand ring better than 8 warps of one 128x128 CTA), so it is the default for all k; option 4 lowers it.
     int downdate_small_k = 1 << 30;
+    int trsm_stages = 4;      // upper limit of the slab TRSM's operand ring depth (option 5)
     int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches
     bool dd_timing = false;
     std::vector<cudaEvent_t> dd_ev;   // pairs
@@ -245,8 +246,11 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     CK(cudaFuncSetAttribute(k_schain_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, kSTrailSmem));
     CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
     CK(cudaFuncSetAttribute(k_schain_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem));
-    CK(cudaFuncSetAttribute(k_trsm_slab<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(k_trsm_slab<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_trsm_slab<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_trsm_slab<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_trsm_slab<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_ransac_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             std::min<int>(227 * 1024 - 2048, c->ld * (int)sizeof(double))));
     const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
@@ -650,15 +654,23 @@ static int run_update(ekfb_ctx* c, int which)
     {
         GroupScope gs(c, G_CHOL);
         const int steps = cdiv(k, kNB);
-        const size_t smem24 = trsm_smem_bytes(k, 24), smem16 = trsm_smem_bytes(k, 16);
+        const size_t smem16 = trsm_smem_bytes(k, 16);
         const size_t smemMax = 227 * 1024;
         if (smem16 <= smemMax && !c->force_generic) {
             // fast path: S-only chain, diagonal-block inverses, slab TRSM
             { int rcC = launch_schain(c, k); if (rcC != EKFB_OK) return rcC; }
-            if (smem24 <= smemMax)
-                CK(launch_pdl(k_trsm_slab<24>, dim3(cdiv(n, 24), c->F), dim3(256), smem24, c->stream, v));
+            // widest slab that fits, then the deepest operand ring beside it (4, 3 or 2 stages of 32 rows)
+            const int maxStages = c->trsm_stages;
+            if (trsm_smem_bytes(k, 24, 4) <= smemMax && maxStages >= 4)
+                CK(launch_pdl(k_trsm_slab<24, 4>, dim3(cdiv(n, 24), c->F), dim3(256), trsm_smem_bytes(k, 24, 4), c->stream, v));
+            else if (trsm_smem_bytes(k, 24, 3) <= smemMax && maxStages >= 3)
+                CK(launch_pdl(k_trsm_slab<24, 3>, dim3(cdiv(n, 24), c->F), dim3(256), trsm_smem_bytes(k, 24, 3), c->stream, v));
+            else if (trsm_smem_bytes(k, 24, 2) <= smemMax)
+                CK(launch_pdl(k_trsm_slab<24, 2>, dim3(cdiv(n, 24), c->F), dim3(256), trsm_smem_bytes(k, 24, 2), c->stream, v));
+            else if (trsm_smem_bytes(k, 16, 4) <= smemMax && maxStages >= 4)
+                CK(launch_pdl(k_trsm_slab<16, 4>, dim3(cdiv(n, 16), c->F), dim3(256), trsm_smem_bytes(k, 16, 4), c->stream, v));
             else
-                CK(launch_pdl(k_trsm_slab<16>, dim3(cdiv(n, 16), c->F), dim3(256), smem16, c->stream, v));
+                CK(launch_pdl(k_trsm_slab<16, 2>, dim3(cdiv(n, 16), c->F), dim3(256), smem16, c->stream, v));
             count_launch(c);
         } else {
             // generic path (very large k): right-looking over the whole augmented matrix
@@ -1300,8 +1312,9 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_DOWNDATE_SMALL_K, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_TRSM_STAGES, "unknown option");
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
+    if (option == EKFB_OPT_TRSM_STAGES) { c->trsm_stages = value; return EKFB_OK; }
     if (option == EKFB_OPT_FORCE_GENERIC_FACTOR) c->force_generic = value != 0;
     else if (option == EKFB_OPT_SCHAIN_VARIANT) c->schain_variant = value;
     else c->downdate_variant = value;

@@ -894,13 +894,16 @@ __global__ void __launch_bounds__(128) k_schain_trail(DevView v, int J)
 template <int SW>
 __host__ __device__ constexpr int trsm_pitch() { return SW + 4; }
 
-inline size_t trsm_smem_bytes(int k, int SW)
+inline size_t trsm_smem_bytes(int k, int SW, int stages = 2)
 {
     const int kpad = (k + kNB - 1) / kNB * kNB;
-    return sizeof(double) * ((size_t)kpad * (SW + 4) + 2 * 32 * 68 + (size_t)kNB * (SW + 4) + 8 * SW);
+    return sizeof(double) * ((size_t)kpad * (SW + 4) + (size_t)stages * 32 * 68 + (size_t)kNB * (SW + 4) + 8 * SW);
 }
 
-template <int SW>
+// NS = depth of the cp.async ring of 32-row operand chunks.  A chunk feeds only 8 x SW/8 DMMAs per warp, far less than
+// the L2 round trip of its load, so the kernel's time is (number of chunks) x (load latency / chunks in flight): NS - 1
+// chunks are kept in flight, as many as the shared memory left beside the slab allows (run_update picks NS).
+template <int SW, int NS>
 __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
 {
     constexpr int SWP = SW + 4, NT = SW / 8;
@@ -913,8 +916,8 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
     if (c0 >= n) return;
     const int kpad = (k + kNB - 1) / kNB * kNB, steps = kpad / kNB;
     double* Xs = tsm;
-    double* Us = Xs + (size_t)kpad * SWP;   // 2 stages x [32][68]
-    double* Ts = Us + 2 * 32 * 68;          // [64][SWP]
+    double* Us = Xs + (size_t)kpad * SWP;   // NS stages x [32][68]
+    double* Ts = Us + NS * 32 * 68;         // [64][SWP]
     double* red = Ts + kNB * SWP;           // [8][SW]
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -943,8 +946,17 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
         }
     };
     int J = 0, ch = 0, stage = 0;
-    issue(0, 0, 0);
-    cp_async_commit();
+    int Ji = 0, chi = 0, stagei = 0;   // issue position: NS - 1 chunks ahead of the consume position (J, ch, stage)
+    auto issue_next = [&]() {
+        if (Ji < steps) {
+            issue(Ji, chi, stagei);
+            if (++chi == (Ji * kNB) / 32 + 2) { ++Ji; chi = 0; }
+            stagei = (stagei + 1 == NS) ? 0 : stagei + 1;
+        }
+        cp_async_commit();   // one group per slot, empty past the end of the stream: keeps wait_group's count uniform
+    };
+#pragma unroll
+    for (int p = 0; p < NS - 1; ++p) issue_next();
     double acc[NT][2];
     while (J < steps) {
         const int J0 = J * kNB, nU = J0 / 32, nCh = nU + 2;
@@ -953,12 +965,11 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
 #pragma unroll
             for (int b = 0; b < NT; ++b) acc[b][0] = acc[b][1] = 0.0;
         }
-        // prefetch the next chunk of the stream
         int Jn = J, chn = ch + 1;
         if (chn == nCh) { Jn = J + 1; chn = 0; }
-        if (Jn < steps) issue(Jn, chn, stage ^ 1);
-        cp_async_commit();
-        cp_async_wait<1>();
+        // prefetch: the slot being refilled was consumed in the previous iteration (barrier at its end)
+        issue_next();
+        cp_async_wait<NS - 1>();
         __syncthreads();
         const double* Uc = Us + stage * 32 * 68;
         if (ch == nU) {
@@ -991,7 +1002,7 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
                 }
         }
         __syncthreads();  // stage buffer and Ts / Xs hazards before the next chunk
-        stage ^= 1;
+        stage = (stage + 1 == NS) ? 0 : stage + 1;
         J = Jn;
         ch = chn;
     }
