@@ -58,6 +58,9 @@ struct ekfb_ctx {
     std::vector<void*> allocs;
     std::vector<int> hn, hN, hKp;  // host copies of per-filter sizes
     int* h_dims = nullptr;          // pinned mirror of v.dims
+    int* h_dims_zc = nullptr;       // mapped pinned memory the counter-publishing kernels write (publish_dims)
+    volatile int* h_flag_zc = nullptr;
+    int dims_seq = 0;
     float* d_kpxy = nullptr;        // staging for ekfb_set_keypoints
     uint8_t* d_kpdesc = nullptr;
     const float** h_kpxy_ptr = nullptr;  // pinned
@@ -223,6 +226,17 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     v.kpxy = c->d_kpxy_ptr;
     v.kpdesc = c->d_kpdesc_ptr;
     CK(cudaMallocHost(&c->h_dims, F * D_STRIDE * sizeof(int)));
+    {
+        int* zc = nullptr;
+        CK(cudaHostAlloc(&zc, (F * D_STRIDE + F) * sizeof(int), cudaHostAllocMapped));
+        std::memset(zc, 0, (F * D_STRIDE + F) * sizeof(int));
+        c->h_dims_zc = zc;
+        c->h_flag_zc = zc + F * D_STRIDE;
+        int* dzc = nullptr;
+        CK(cudaHostGetDevicePointer(&dzc, zc, 0));
+        v.hostDims = dzc;
+        v.hostFlag = dzc + F * D_STRIDE;
+    }
     CK(cudaMallocHost(&c->h_kpxy_ptr, F * sizeof(void*)));
     CK(cudaMallocHost(&c->h_kpdesc_ptr, F * sizeof(void*)));
     CK(cudaMallocHost(&c->h_rec, F * sizeof(RecordDev)));
@@ -273,6 +287,7 @@ extern "C" int ekfb_destroy(ekfb_handle c)
     if (c->flush_buf) cudaFree(c->flush_buf);
     for (cudaEvent_t e : c->dd_ev) cudaEventDestroy(e);
     cudaFreeHost(c->h_dims);
+    if (c->h_dims_zc) cudaFreeHost(c->h_dims_zc);
     cudaFreeHost(c->h_kpxy_ptr);
     cudaFreeHost(c->h_kpdesc_ptr);
     cudaFreeHost(c->h_rec);
@@ -463,6 +478,29 @@ static int read_dims(ekfb_ctx* c)
     return EKFB_OK;
 }
 
+// Wait for the counters a publishing kernel (publish_dims) launched with sequence number `seq` wrote into mapped host
+// memory.  Falls back to the copy + synchronise path if the stream drains without the flags (a failed launch).
+static int wait_published_dims(ekfb_ctx* c, int seq)
+{
+    const int F = c->F;
+    for (unsigned spin = 1;; ++spin) {
+        bool all = true;
+        for (int f = 0; f < F; ++f) all = all && c->h_flag_zc[f] == seq;
+        if (all) break;
+        if ((spin & 0x3ff) == 0) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaErrorNotReady) continue;
+            CK(q);
+            all = true;
+            for (int f = 0; f < F; ++f) all = all && c->h_flag_zc[f] == seq;
+            if (all) break;
+            return read_dims(c);
+        }
+    }
+    std::memcpy(c->h_dims, c->h_dims_zc, (size_t)F * D_STRIDE * sizeof(int));
+    return EKFB_OK;
+}
+
 extern "C" int ekfb_predict(ekfb_handle c)
 {
     REQUIRE(c, "null handle");
@@ -470,9 +508,8 @@ extern "C" int ekfb_predict(ekfb_handle c)
     GroupScope gs(c, G_PREDICT);
     const int n = max_of(c->hn);
     dim3 grid(1 + cdiv(std::max(n - 13, 0), 256), c->F);
-    k_predict_cov<<<grid, 256, 0, c->stream>>>(c->v);
-    k_predict_state<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->v);
-    count_launch(c, 2);
+    k_predict_cov<<<grid, 256, 0, c->stream>>>(c->v);   // + the state prediction, by the block that finishes last
+    count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
 }
@@ -531,10 +568,11 @@ extern "C" int ekfb_ransac(ekfb_handle c)
     (void)n;
     for (int chunk0 = 0; chunk0 < std::max(N, 1); chunk0 += CH) {
         k_ransac_hyp<<<dim3(CH, c->F, cdiv(c->Nmax, kHypFeat)), 416, 0, c->stream>>>(c->v, chunk0);
-        k_ransac_select<<<c->F, 256, 0, c->stream>>>(c->v, chunk0, CH);
+        const int seq = ++c->dims_seq;
+        k_ransac_select<<<c->F, 256, 0, c->stream>>>(c->v, chunk0, CH, seq);
         count_launch(c, 2);
         CK(cudaGetLastError());
-        int rc = read_dims(c);
+        int rc = wait_published_dims(c, seq);
         if (rc != EKFB_OK) return rc;
         bool all = true;
         for (int f = 0; f < c->F; ++f) all = all && c->h_dims[(size_t)f * D_STRIDE + D_RANSAC_DONE];
@@ -687,9 +725,8 @@ static int run_update(ekfb_ctx* c, int which)
                 }
             }
         }
-        k_state_apply<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
-        k_quat_norm<<<cdiv(c->F, 128), 128, 0, c->stream>>>(v);
-        count_launch(c, 2);
+        k_state_apply<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);   // + quaternion normalisation (block 0)
+        count_launch(c);
     }
     {
         GroupScope gs(c, G_DOWNDATE);
@@ -717,10 +754,11 @@ extern "C" int ekfb_rescue(ekfb_handle c)
     GroupScope gs(c, G_RESCUE);
     int rc = launch_measure(c, 1);
     if (rc != EKFB_OK) return rc;
-    k_rescue_gate<<<c->F, 256, 0, c->stream>>>(c->v);
+    const int seq = ++c->dims_seq;
+    k_rescue_gate<<<c->F, 256, 0, c->stream>>>(c->v, seq);
     count_launch(c);
     CK(cudaGetLastError());
-    return read_dims(c);
+    return wait_published_dims(c, seq);
 }
 
 extern "C" int ekfb_update_map_features(ekfb_handle c)

@@ -26,7 +26,8 @@ enum DimSlot {
     D_BEST_COUNT = 14, D_ULIST = 15, D_N_PRED2 = 16,
     // map management plan (ekf_map.cuh)
     D_MAP_CHANGED = 17, D_MAP_NEW_N = 18, D_MAP_NEW_NF = 19, D_MAP_CONVERT = 20, D_MAP_NEEDED = 21, D_MAP_NBAD = 22,
-    D_MAP_NUNSEEN = 23, D_MAP_CONV_OLDOFF = 24, D_MAP_CONV_NEWOFF = 25, D_STRIDE = 32
+    D_MAP_NUNSEEN = 23, D_MAP_CONV_OLDOFF = 24, D_MAP_CONV_NEWOFF = 25,
+    D_PRED_TICKET = 26 /* blocks of k_predict_cov that have finished (reset by the last one) */, D_STRIDE = 32
 };
 
 struct DevView {
@@ -46,9 +47,26 @@ struct DevView {
     // new row -> old row table, per-feature removal flags, conversion Jacobian, add-feature staging
     double* P2; double* x2; int* ftype2; int* foff2; uint8_t* desc2; int* tpred2; int* tmatch2;
     int* rowsrc; uint8_t* mapflag; double* convJ; double* addJ; double* adduv; uint8_t* adddesc;
+    // zero-copy readback of the per-filter counters (mapped pinned host memory): hostDims[F][D_STRIDE], hostFlag[F]
+    int* hostDims; volatile int* hostFlag;
 };
 
 __device__ __forceinline__ int* fdims(const DevView& v, int f) { return v.dims + (size_t)f * D_STRIDE; }
+
+// The two kernels whose counters size the next launches (k_ransac_select, k_rescue_gate) end by writing the filter's counter
+// block straight into mapped host memory and then a sequence number the host spins on: the host learns the counts a few
+// microseconds after the kernel's last store instead of after a copy + stream synchronisation.  Call from all threads.
+__device__ __forceinline__ void publish_dims(const DevView& v, int f, int seq)
+{
+    __syncthreads();
+    if (threadIdx.x != 0 || v.hostDims == nullptr) return;
+    const int* dm = fdims(v, f);
+    int* hd = v.hostDims + (size_t)f * D_STRIDE;
+#pragma unroll
+    for (int i = 0; i < D_STRIDE; ++i) hd[i] = dm[i];
+    __threadfence_system();
+    v.hostFlag[f] = seq;
+}
 
 // ---------------------------------------------------------------------------------------------
 // P1: P <- F P F^T + G Q G^T on the 13 camera rows / columns (E/StateAndCovariancePrediction.cpp:154-240).
@@ -104,6 +122,17 @@ __global__ void __launch_bounds__(256) k_predict_cov(DevView v)
             }
         }
     }
+    // P2, fused: x <- f(x) AFTER the covariance prediction (E/StateAndCovariancePrediction.cpp:43-65,252).  Every block read
+    // the pre-prediction state before it took its ticket, so the block that draws the last ticket may overwrite it.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* dmw = fdims(v, f);
+        __threadfence();
+        if (atomicAdd(&dmw[D_PRED_TICKET], 1) == (int)gridDim.x - 1) {
+            dmw[D_PRED_TICKET] = 0;
+            motion_predict(v.x + (size_t)f * v.ld);
+        }
+    }
 }
 
 // Establishes the device invariant "P is exactly symmetric" at upload: P <- 0.5 P + 0.5 P^T, which is
@@ -117,14 +146,6 @@ __global__ void k_symmetrize(DevView v, int f)
     const double a = 0.5 * P[(size_t)i * v.ld + j] + 0.5 * P[(size_t)j * v.ld + i];
     P[(size_t)i * v.ld + j] = a;
     P[(size_t)j * v.ld + i] = a;
-}
-
-// P2: x <- f(x), after P1 (E/StateAndCovariancePrediction.cpp:43-65,252)
-__global__ void k_predict_state(DevView v)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= v.F) return;
-    motion_predict(v.x + (size_t)f * v.ld);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -514,7 +535,7 @@ __global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0)
 // Sequential replay of the acceptance / adaptive-cap rule over one evaluated chunk
 // (E/1PointRansac.cpp:125-186), then -- once the loop has ended -- the inlier/outlier split in
 // match order (:201-227) and the inlier list for the low-innovation update.
-__global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, int chunkLen)
+__global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, int chunkLen, int seq)
 {
     const int f = blockIdx.x;
     int* dm = fdims(v, f);
@@ -566,7 +587,10 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
         }
     }
     __syncthreads();
-    if (!finished) return;
+    if (!finished) {
+        publish_dims(v, f, seq);
+        return;
+    }
     const int bestHyp = dm[D_BEST_HYP];
     const uint32_t* sup = v.hypsup + ((size_t)f * v.Nmax + (bestHyp < 0 ? 0 : bestHyp)) * v.supWords;
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
@@ -582,13 +606,14 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
         dm[D_N_OUT] = m - ni;
         dm[D_ULIST] = ni;
     }
+    publish_dims(v, f, seq);
 }
 
 // ---------------------------------------------------------------------------------------------
 // X1: chi-square gate on the re-predicted outliers (E/EKF.cpp:477-506 + :68-119), then the
 // rescued list for the high-innovation update.  One CTA per filter.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rescue_gate(DevView v)
+__global__ void __launch_bounds__(256) k_rescue_gate(DevView v, int seq)
 {
     const int f = blockIdx.x;
     int* dm = fdims(v, f);
@@ -621,6 +646,7 @@ __global__ void __launch_bounds__(256) k_rescue_gate(DevView v)
         dm[D_ULIST] = nr;
         dm[D_N_PRED2] = npred2;
     }
+    publish_dims(v, f, seq);
 }
 
 // updateMapFeatures (E/MapManagement.cpp:77-113): hit counters and descriptor refresh of inliers + rescued

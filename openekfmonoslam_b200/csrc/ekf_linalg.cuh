@@ -1199,18 +1199,16 @@ __global__ void __launch_bounds__(256) k_state_apply(DevView v)
     if (dm[D_ULIST] == 0) return;
     const int n = dm[D_N_STATE];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double d = v.dx[(size_t)f * v.ld + i];
-    if (fabs(d) > kDelta) v.x[(size_t)f * v.ld + i] += d;
-}
-
-// U4 (a): J = d(q/|q|)/dq at the un-normalised q, then q <- q/|q| (E/Update.cpp:45-60,309-317)
-__global__ void k_quat_norm(DevView v)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= v.F) return;
-    if (fdims(v, f)[D_ULIST] == 0) return;
     double* x = v.x + (size_t)f * v.ld;
+    if (i < n) {
+        const double d = v.dx[(size_t)f * v.ld + i];
+        if (fabs(d) > kDelta) x[i] += d;
+    }
+    if (blockIdx.x != 0) return;
+    // U4 (a), fused: J = d(q/|q|)/dq at the un-normalised q, then q <- q/|q| (E/Update.cpp:45-60,309-317).  The quaternion
+    // (elements 3..6) belongs to this block.
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     const double r = x[3], a = x[4], b = x[5], c = x[6];
     const double nrm = sqrt(r * r + a * a + b * b + c * c);
     const double s = 1.0 / (nrm * nrm * nrm);
