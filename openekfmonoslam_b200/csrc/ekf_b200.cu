@@ -88,6 +88,8 @@ struct ekfb_ctx {
     // r01_downdate_sweep.txt) that variant wins at every k and n tried (16 resident warps hide the tile read-modify-write
     // and the operand ring better than 8 warps of one 128x128 CTA), so it is the default for all k; option 4 lowers it.
     int downdate_small_k = 1 << 30;
+    int trsm_pair = 1;        // batched filters: slab footprint that fits two CTAs per SM when possible (option 6)
+    int ransac_chunk = 0;     // hypotheses evaluated per round; 0 = 16 for a single filter, 4 for batches (option 7)
     int trsm_stages = 4;      // upper limit of the slab TRSM's operand ring depth (option 5)
     int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches
     bool dd_timing = false;
@@ -563,7 +565,9 @@ extern "C" int ekfb_ransac(ekfb_handle c)
     REQUIRE(c, "null handle");
     CK(cudaSetDevice(c->device));
     GroupScope gs(c, G_RANSAC);
-    const int CH = 16;
+    // hypotheses per round: the adaptive cap of the reference's rule collapses to 2-5 once a majority hypothesis is seen, so
+    // batches (where surplus hypotheses cost real throughput) go four at a time, a single filter (latency) sixteen
+    const int CH = c->ransac_chunk > 0 ? std::min(c->ransac_chunk, 64) : (c->F >= 8 ? 4 : 16);
     const int n = max_of(c->hn), N = max_of(c->hN);
     (void)n;
     for (int chunk0 = 0; chunk0 < std::max(N, 1); chunk0 += CH) {
@@ -699,7 +703,13 @@ static int run_update(ekfb_ctx* c, int which)
             { int rcC = launch_schain(c, k); if (rcC != EKFB_OK) return rcC; }
             // widest slab that fits, then the deepest operand ring beside it (4, 3 or 2 stages of 32 rows)
             const int maxStages = c->trsm_stages;
-            if (trsm_smem_bytes(k, 24, 4) <= smemMax && maxStages >= 4)
+            // batched filters: many slabs per SM, so prefer a footprint that lets two CTAs share an SM (their barrier
+            // stalls overlap) over the widest slab
+            if (c->F > 1 && c->trsm_pair && 2 * trsm_smem_bytes(k, 24, 2) <= smemMax)
+                CK(launch_pdl(k_trsm_slab<24, 2>, dim3(cdiv(n, 24), c->F), dim3(256), trsm_smem_bytes(k, 24, 2), c->stream, v));
+            else if (c->F > 1 && c->trsm_pair && 2 * trsm_smem_bytes(k, 16, 2) <= smemMax)
+                CK(launch_pdl(k_trsm_slab<16, 2>, dim3(cdiv(n, 16), c->F), dim3(256), trsm_smem_bytes(k, 16, 2), c->stream, v));
+            else if (trsm_smem_bytes(k, 24, 4) <= smemMax && maxStages >= 4)
                 CK(launch_pdl(k_trsm_slab<24, 4>, dim3(cdiv(n, 24), c->F), dim3(256), trsm_smem_bytes(k, 24, 4), c->stream, v));
             else if (trsm_smem_bytes(k, 24, 3) <= smemMax && maxStages >= 3)
                 CK(launch_pdl(k_trsm_slab<24, 3>, dim3(cdiv(n, 24), c->F), dim3(256), trsm_smem_bytes(k, 24, 3), c->stream, v));
@@ -1350,9 +1360,11 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_TRSM_STAGES, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_RANSAC_CHUNK, "unknown option");
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
     if (option == EKFB_OPT_TRSM_STAGES) { c->trsm_stages = value; return EKFB_OK; }
+    if (option == EKFB_OPT_TRSM_PAIR) { c->trsm_pair = value; return EKFB_OK; }
+    if (option == EKFB_OPT_RANSAC_CHUNK) { c->ransac_chunk = value; return EKFB_OK; }
     if (option == EKFB_OPT_FORCE_GENERIC_FACTOR) c->force_generic = value != 0;
     else if (option == EKFB_OPT_SCHAIN_VARIANT) c->schain_variant = value;
     else c->downdate_variant = value;

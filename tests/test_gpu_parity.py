@@ -112,6 +112,20 @@ def test_generic_factorisation_path():
         phase_by_phase(sc, orc, gpu, t)
 
 
+def test_ransac_in_small_rounds_and_legacy_tile_options():
+    """RANSAC hypotheses two per round (batches use four; the sequential accept / adaptive-cap replay must not depend on the
+    round size), the 128x128 downdate tiles and the shallow TRSM ring, all against the oracle."""
+    sc, orc, gpu = make_pair(640, 480, 100)
+    gpu.set_option(7, 2)      # EKFB_OPT_RANSAC_CHUNK
+    gpu.set_option(4, 64)     # EKFB_OPT_DOWNDATE_SMALL_K: updates with more than 64 rows use the 128x128 kernel
+    gpu.set_option(5, 2)      # EKFB_OPT_TRSM_STAGES
+    hyps = []
+    for t in range(1, 5):
+        phase_by_phase(sc, orc, gpu, t)
+        hyps.append(gpu.frame_info(0)["n_hypotheses"])
+    assert max(hyps) > 2, hyps     # at least one frame needed a second round
+
+
 def test_downdate_variant_128x64():
     """The alternative downdate kernel (128x64 tiles, transposed mirror store) against the oracle."""
     sc, orc, gpu = make_pair(640, 480, 100, warm=3)
