@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f
     }
     __syncthreads();
     int phase = 0;
-    double finalScore = -2.0;
     bool first = true;
     for (int l = lev; l >= 0; --l) {
         const int Wl = nv.W[l], Hl = nv.H[l];
@@ -186,7 +185,6 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f
         __syncthreads();
         if (!sBest[2]) return;   // no valid candidate at this level
         if (l == 0) {
-            finalScore = wbest[0].s;   // only used by thread 0 below through nv.score
             cx = sBest[0];
             cy = sBest[1];
         } else {
@@ -197,7 +195,6 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f
         }
         __syncthreads();   // window and wbest are rewritten by the next level
     }
-    (void)finalScore;
     if (tid == 0 && nv.score[j] >= nv.ncc_min) {
         v.mflag[fj] = 1;
         v.z[fj * 2] = (double)cx;
