@@ -23,6 +23,7 @@ def images():
         n = np.apply_along_axis(lambda r: np.convolve(r, k, "same"), 1, n)
     n = n[8:-8, 8:-8]
     out.append(("blurred noise", np.clip(128 + 400 * n, 0, 255).astype(np.uint8)))
+    out.append(("odd size", np.ascontiguousarray(out[-1][1][3:3 + 187, 5:5 + 251])))   # width not a multiple of 16: row pitch != width
     return out
 
 

@@ -107,3 +107,16 @@ def test_gpu_ncc_search_equals_oracle(W, H, N, pscale):
     assert info["status"] == 0 and info["n_inliers"] > N // 3
     Pg = gpu.get_state(0)[1]
     assert np.array_equal(Pg, Pg.T)
+
+
+@pytest.mark.gpu
+def test_gpu_pyramid_of_an_odd_sized_image():
+    """251 x 187: the device rows are padded to a 16-byte pitch, the levels are floor(W/2) x floor(H/2)"""
+    from openekfmonoslam_b200.capi import EkfBatch
+    from openekfmonoslam_b200.params import synthetic_params
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (187, 251), dtype=np.uint8)
+    gpu = EkfBatch(synthetic_params(251, 187), 1, 4, 64)
+    gpu.ncc_set_image(0, img)
+    for l, ref in enumerate(ncc_oracle.pyramid(img)):
+        assert np.array_equal(gpu.ncc_level(0, l), ref), l
