@@ -132,6 +132,7 @@ public:
 private:
     void downloadState();
     void mirrorLayout();
+    void refreshMirror(bool layout);
     bool acquireKeypoints(const cv::Mat& image);
     int addNewFeatures(int wanted, bool useDeviceMask);
     int _ekfSteps;
@@ -146,11 +147,10 @@ private:
     ekfb_handle _h;
     ekfb_frame_info _info;
     ekfb_map_result _mapResult;
-    int _lastAdded;
+    int _lastAdded, _featuresBefore;
     std::vector<EkfKeyPoint> _kps;
     std::vector<unsigned char> _desc;
     std::vector<unsigned char> _mask, _stamp;
-    std::vector<double> _predXY;   // predicted pixels of the frame (zone occupancy of the new-feature search)
     int _stampR;
     EkfbTraceWriter _trace;
 };

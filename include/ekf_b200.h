@@ -153,6 +153,15 @@ int ekfb_set_hit_counters(ekfb_handle h, int filter, const int32_t* times_predic
 /* buildImageMask (E/DetectNewImageFeatures.cpp:101-122): 255 everywhere, 0 inside the gate ellipse of every feature predicted
  * in this frame; built by the last ekfb_map_management when a filter asked for new features (pixels_y x pixels_x bytes) */
 int ekfb_get_new_feature_mask(ekfb_handle h, int filter, uint8_t* mask);
+/* the inputs of the host's new-feature selection in one round trip: predicted flags and pixels of this frame's measurement
+ * (n_features_before = the feature count before ekfb_map_management; either may be NULL) and the new-feature mask (or NULL) */
+int ekfb_get_new_feature_inputs(ekfb_handle h, int filter, int n_features_before, uint8_t* predicted, double* hpred, uint8_t* mask);
+/* the host mirror of one filter in one round trip (any pointer may be NULL): state vector (n), feature type / covarianceMatrixPos /
+ * descriptor / timesPredicted / timesMatched (N each), and the result record */
+int ekfb_get_map_snapshot(ekfb_handle h, int filter, double* x, int32_t* type, int32_t* off, uint8_t* desc, int32_t* times_predicted,
+                          int32_t* times_matched, ekfb_record* record);
+/* the last frame's counters from the host mirror, no device round trip (valid right after ekfb_step / ekfb_map_management) */
+int ekfb_peek_frame_info(ekfb_handle h, int filter, ekfb_frame_info* info);
 /* one drawUncertaintyEllipse2D(img, (cx,cy), S, max_axes, value, filled) (Gui/Draw.cpp:42-64) into a host W x H byte image;
  * the host side uses it once for the stamp of E/DetectNewImageFeatures.cpp:283-288, tests pin the rasteriser with it */
 int ekfb_raster_ellipse(ekfb_handle h, int W, int H, double cx, double cy, const double* S, int max_axes, int value,

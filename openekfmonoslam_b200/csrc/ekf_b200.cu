@@ -784,6 +784,8 @@ extern "C" int ekfb_update_map_features(ekfb_handle c)
     return EKFB_OK;
 }
 
+static void fill_info(const int* d, ekfb_frame_info* o);
+
 // ---- map management (kernels in ekf_map.cuh) ----------------------------------------------
 static int ensure_map_buffers(ekfb_ctx* c)
 {
@@ -922,6 +924,63 @@ extern "C" int ekfb_set_hit_counters(ekfb_handle c, int f, const int32_t* tp, co
     CK(cudaMemcpyAsync(c->v.tpred + (size_t)f * c->Nmax, tp, sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->v.tmatch + (size_t)f * c->Nmax, tm, sizeof(int) * N, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+// what the host's new-feature selection reads, in one round trip: the predictions of this frame's measurement (indexed by
+// the feature numbering BEFORE ekfb_map_management, which leaves these arrays alone) and the new-feature mask
+extern "C" int ekfb_get_new_feature_inputs(ekfb_handle c, int f, int n_features_before, uint8_t* predicted, double* hpred, uint8_t* mask)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F && n_features_before >= 0 && n_features_before <= c->Nmax, "bad filter index or count");
+    REQUIRE(!mask || (c->map_ready && c->mask2_valid), "no new-feature mask: the last ekfb_map_management asked for no new features");
+    CK(cudaSetDevice(c->device));
+    const size_t fo = (size_t)f * c->Nmax, wh = (size_t)c->v.W * c->v.H;
+    if (predicted && n_features_before)
+        CK(cudaMemcpyAsync(predicted, c->v.vis + fo, n_features_before, cudaMemcpyDeviceToHost, c->stream));
+    if (hpred && n_features_before)
+        CK(cudaMemcpyAsync(hpred, c->v.h + fo * 2, sizeof(double) * 2 * n_features_before, cudaMemcpyDeviceToHost, c->stream));
+    if (mask) CK(cudaMemcpyAsync(mask, c->mask2 + (size_t)f * wh, wh, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+// the host mirror of one filter in one round trip: state vector, feature layout, descriptors, hit counters, result record
+extern "C" int ekfb_get_map_snapshot(ekfb_handle c, int f, double* x, int32_t* type, int32_t* off, uint8_t* desc, int32_t* tp,
+                                     int32_t* tm, ekfb_record* rec)
+{
+    REQUIRE(c, "null handle");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    CK(cudaSetDevice(c->device));
+    const int n = c->hn[f], N = c->hN[f];
+    const size_t fo = (size_t)f * c->Nmax;
+    if (rec) {
+        k_write_records<<<c->F, 192, 0, c->stream>>>(c->v, c->d_rec);
+        count_launch(c);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_rec + f, c->d_rec + f, sizeof(RecordDev), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (x) CK(cudaMemcpyAsync(x, c->v.x + (size_t)f * c->ld, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (N > 0) {
+        if (type) CK(cudaMemcpyAsync(type, c->v.ftype + fo, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+        if (off) CK(cudaMemcpyAsync(off, c->v.foff + fo, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+        if (desc) CK(cudaMemcpyAsync(desc, c->v.desc + fo * 32, (size_t)N * 32, cudaMemcpyDeviceToHost, c->stream));
+        if (tp) CK(cudaMemcpyAsync(tp, c->v.tpred + fo, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+        if (tm) CK(cudaMemcpyAsync(tm, c->v.tmatch + fo, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (rec) std::memcpy(rec, c->h_rec + f, sizeof(ekfb_record));
+    return EKFB_OK;
+}
+
+// the counters of the last frame from the host mirror, without a device round trip: valid right after a call that
+// synchronised them (ekfb_step / ekfb_rescue / ekfb_map_management / ekfb_get_frame_info); `status` may lag behind the
+// high-innovation update (ekfb_get_frame_info reads it from the device)
+extern "C" int ekfb_peek_frame_info(ekfb_handle c, int f, ekfb_frame_info* info)
+{
+    REQUIRE(c && info, "null argument");
+    REQUIRE(f >= 0 && f < c->F, "bad filter index");
+    fill_info(c->h_dims + (size_t)f * D_STRIDE, info);
     return EKFB_OK;
 }
 

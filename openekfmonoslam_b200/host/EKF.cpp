@@ -159,53 +159,54 @@ EKF::~EKF()
     if (_h) ekfb_destroy(_h);
 }
 
-void EKF::downloadState()
+// Bring the host mirror in line with the device in ONE round trip (ekfb_get_map_snapshot): camera state and every feature's
+// position, the 13x13 block, and -- after features were removed, converted or added -- the feature list itself (what
+// State::removeFeatures / addFeature / convertToDepth do to the reference's vectors: E/State.cpp:142-206,
+// E/MapManagement.cpp:457-496).  MapFeature objects are reused by index; surplus ones are deleted.
+void EKF::downloadState() { refreshMirror(false); }
+void EKF::mirrorLayout() { refreshMirror(true); }
+
+void EKF::refreshMirror(bool layout)
 {
     int32_t n = 0, N = 0;
     ekfb_get_dims(_h, 0, &n, &N);
     std::vector<double> x(n);
-    if (ekfb_get_state(_h, 0, x.data(), nullptr, 0) != EKFB_OK) { std::cerr << "EKF: " << ekfb_last_error() << std::endl; return; }
+    const int M = N > 0 ? N : 1;
+    std::vector<int32_t> type, off, tp, tm;
+    std::vector<unsigned char> desc;
+    if (layout) { type.resize(M); off.resize(M); tp.resize(M); tm.resize(M); desc.resize((size_t)M * 32); }
+    ekfb_record rec;
+    if (ekfb_get_map_snapshot(_h, 0, x.data(), layout ? type.data() : nullptr, layout ? off.data() : nullptr,
+                              layout ? desc.data() : nullptr, layout ? tp.data() : nullptr, layout ? tm.data() : nullptr, &rec) != EKFB_OK) {
+        std::cerr << "EKF: " << ekfb_last_error() << std::endl;
+        return;
+    }
+    if (layout) {
+        while ((int)state.mapFeatures.size() > N) { delete state.mapFeatures.back(); state.mapFeatures.pop_back(); }
+        while ((int)state.mapFeatures.size() < N) state.mapFeatures.push_back(new MapFeature());
+        state.mapFeaturesDepth.clear();
+        state.mapFeaturesInvDepth.clear();
+        for (int i = 0; i < N; ++i) {
+            MapFeature* f = state.mapFeatures[i];
+            f->featureType = (MapFeatureType)type[i];
+            f->positionDimension = type[i] == MAPFEATURE_TYPE_INVERSE_DEPTH ? 6 : 3;
+            f->covarianceMatrixPos = off[i];
+            f->timesPredicted = (unsigned)tp[i];
+            f->timesMatched = (unsigned)tm[i];
+            std::memcpy(f->descriptor, &desc[(size_t)i * 32], 32);
+            (type[i] == MAPFEATURE_TYPE_INVERSE_DEPTH ? state.mapFeaturesInvDepth : state.mapFeaturesDepth).push_back(f);
+        }
+    }
     for (int i = 0; i < 3; ++i) { state.position[i] = x[i]; state.linearVelocity[i] = x[7 + i]; state.angularVelocity[i] = x[10 + i]; }
     state.setOrientation(&x[3]);
     for (int i = 0; i < N && i < (int)state.mapFeatures.size(); ++i) {
         MapFeature* f = state.mapFeatures[i];
         for (int j = 0; j < f->positionDimension; ++j) f->position[j] = x[f->covarianceMatrixPos + j];
     }
-    ekfb_record rec;
-    if (ekfb_get_records(_h, &rec) == EKFB_OK) {
-        if (stateCovarianceMatrix.rows < 13) stateCovarianceMatrix = Matd(13, 13);
-        for (int i = 0; i < 13; ++i)
-            for (int j = 0; j < 13; ++j) stateCovarianceMatrix[i][j] = rec.P_cam[i * 13 + j];
-    }
-}
-
-// bring the host mirror of the map (State::mapFeatures and the two per-type lists) in line with the device's layout
-// after features were removed, converted or added (what State::removeFeatures / addFeature / convertToDepth do to the
-// reference's vectors: E/State.cpp:142-206, E/MapManagement.cpp:457-496)
-void EKF::mirrorLayout()
-{
-    int32_t n = 0, N = 0;
-    ekfb_get_dims(_h, 0, &n, &N);
-    std::vector<int32_t> type(N > 0 ? N : 1), off(N > 0 ? N : 1), tp(N > 0 ? N : 1), tm(N > 0 ? N : 1);
-    std::vector<unsigned char> desc((size_t)(N > 0 ? N : 1) * 32);
-    if (ekfb_get_feature_layout(_h, 0, type.data(), off.data()) != EKFB_OK ||
-        ekfb_get_descriptors(_h, 0, desc.data(), tp.data(), tm.data()) != EKFB_OK) {
-        std::cerr << "EKF: " << ekfb_last_error() << std::endl;
-        return;
-    }
-    while ((int)state.mapFeatures.size() < N) state.mapFeatures.push_back(new MapFeature());
-    state.mapFeaturesDepth.clear();
-    state.mapFeaturesInvDepth.clear();
-    for (int i = 0; i < N; ++i) {
-        MapFeature* f = state.mapFeatures[i];
-        f->featureType = (MapFeatureType)type[i];
-        f->positionDimension = type[i] == MAPFEATURE_TYPE_INVERSE_DEPTH ? 6 : 3;
-        f->covarianceMatrixPos = off[i];
-        f->timesPredicted = (unsigned)tp[i];
-        f->timesMatched = (unsigned)tm[i];
-        std::memcpy(f->descriptor, &desc[(size_t)i * 32], 32);
-        (type[i] == MAPFEATURE_TYPE_INVERSE_DEPTH ? state.mapFeaturesInvDepth : state.mapFeaturesDepth).push_back(f);
-    }
+    if (stateCovarianceMatrix.rows < 13) stateCovarianceMatrix = Matd(13, 13);
+    for (int i = 0; i < 13; ++i)
+        for (int j = 0; j < 13; ++j) stateCovarianceMatrix[i][j] = rec.P_cam[i * 13 + j];
+    _info.status = rec.info.status;   // the record is read after the high-innovation update
 }
 
 namespace {
@@ -244,11 +245,16 @@ int EKF::addNewFeatures(int wanted, bool useDeviceMask)
     _mask.assign((size_t)W * H, 255);
     std::vector<double> pred;
     if (useDeviceMask) {
-        if (ekfb_get_new_feature_mask(_h, 0, _mask.data()) != EKFB_OK) {
+        // one round trip: this frame's predictions (zone occupancy; indexed by the numbering before the map changed) + the mask
+        const int nb = _featuresBefore;
+        std::vector<unsigned char> vis(nb > 0 ? nb : 1);
+        std::vector<double> h(2 * (size_t)(nb > 0 ? nb : 1));
+        if (ekfb_get_new_feature_inputs(_h, 0, nb, vis.data(), h.data(), _mask.data()) != EKFB_OK) {
             std::cerr << "EKF: " << ekfb_last_error() << std::endl;
             return 0;
         }
-        pred = _predXY;
+        for (int i = 0; i < nb; ++i)
+            if (vis[i]) { pred.push_back(h[2 * i]); pred.push_back(h[2 * i + 1]); }
     }
     if (_stamp.empty()) {   // the ellipse of E/DetectNewImageFeatures.cpp:221-223, rasterised once by the device
         const double es = _cfg.detectNewFeaturesImageMaskEllipseSize;
@@ -346,10 +352,8 @@ void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
         std::cerr << "EKF::init: " << ekfb_last_error() << std::endl;
         return;
     }
-    _predXY.clear();
     _lastAdded = addNewFeatures(_cfg.policy.min_matches_per_image, false);
-    mirrorLayout();
-    downloadState();
+    refreshMirror(true);
 }
 
 void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
@@ -384,40 +388,19 @@ void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
         std::cerr << "EKF::step: " << ekfb_last_error() << std::endl;
         return;
     }
-    ekfb_get_frame_info(_h, 0, &_info);
+    ekfb_peek_frame_info(_h, 0, &_info);   // the counters ekfb_step synchronised; status is refreshed from the record below
     // map management (E/EKF.cpp:572-612): bad / unseen features out, one conversion, new features in
     std::memset(&_mapResult, 0, sizeof(_mapResult));
     _mapResult.converted = -1;
     _lastAdded = 0;
     bool layoutChanged = false;
     if (_cfg.mapManagementFrequency > 0 && _ekfSteps % _cfg.mapManagementFrequency == 0) {
-        const int nBefore = (int)state.mapFeatures.size();
-        if (_cfg.policy.min_matches_per_image - (_info.n_inliers + _info.n_rescued) > 0) {
-            // the zone occupancy of detectNewImageFeatures counts this frame's predictions: fetch them before the map changes
-            std::vector<unsigned char> vis(nBefore > 0 ? nBefore : 1);
-            std::vector<double> h(2 * (size_t)(nBefore > 0 ? nBefore : 1));
-            _predXY.clear();
-            if (ekfb_get_feature_results(_h, 0, vis.data(), h.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                         nullptr, nullptr, nullptr) == EKFB_OK)
-                for (int i = 0; i < nBefore; ++i)
-                    if (vis[i]) { _predXY.push_back(h[2 * i]); _predXY.push_back(h[2 * i + 1]); }
-        }
+        _featuresBefore = (int)state.mapFeatures.size();
         if (ekfb_map_management(_h, &_cfg.policy, &_mapResult) != EKFB_OK) {
             std::cerr << "EKF::step: " << ekfb_last_error() << std::endl;
             return;
         }
-        if (_mapResult.n_removed_bad + _mapResult.n_removed_unseen > 0) {
-            std::vector<unsigned char> flags(nBefore > 0 ? nBefore : 1);
-            if (ekfb_get_removed_flags(_h, 0, nBefore, flags.data()) == EKFB_OK) {
-                VectorMapFeature keep;
-                for (int i = 0; i < nBefore; ++i) {
-                    if (flags[i]) delete state.mapFeatures[i];
-                    else keep.push_back(state.mapFeatures[i]);
-                }
-                state.mapFeatures.swap(keep);
-            }
-            layoutChanged = true;
-        }
+        if (_mapResult.n_removed_bad + _mapResult.n_removed_unseen > 0) layoutChanged = true;
         if (_mapResult.converted >= 0) layoutChanged = true;
         if (_mapResult.new_features_needed > 0) {
             _lastAdded = addNewFeatures(_mapResult.new_features_needed, true);
@@ -425,8 +408,7 @@ void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
         }
     }
     if (_trace.isOpen()) ekfb_timer_record(_h, 7);
-    if (layoutChanged) mirrorLayout();
-    downloadState();
+    refreshMirror(layoutChanged);
     if (_trace.isOpen()) {
         for (int i = 0; i < 7; ++i) ekfb_timer_elapsed_ms(_h, i, i + 1, &ms[i]);
         EkfbFrameTrace t;
