@@ -120,3 +120,29 @@ def test_gpu_pyramid_of_an_odd_sized_image():
     gpu.ncc_set_image(0, img)
     for l, ref in enumerate(ncc_oracle.pyramid(img)):
         assert np.array_equal(gpu.ncc_level(0, l), ref), l
+
+
+@pytest.mark.gpu
+def test_gpu_ncc_search_two_filters_of_one_handle():
+    """per-filter images, templates and results: filter 1 sees a different frame of the same scene than filter 0"""
+    from openekfmonoslam_b200.capi import EkfBatch
+    W, H, N = 320, 240, 40
+    sc, orc0, (x, P, ft, fo, desc), tex, tmpl = ncc_case(N, W, H)
+    orc1 = OracleFilter(sc.params); orc1.set_state(x, P, ft, fo, desc)
+    gpu = EkfBatch(sc.params, 2, N, 4 * N + 64)
+    for f in (0, 1):
+        gpu.set_state(f, x, P, ft, fo, desc)
+        gpu.ncc_set_templates(f, 0, tmpl)
+    imgs = [render(W, H, feature_pixels(sc, 1), tex, 21), render(W, H, feature_pixels(sc, 2), tex, 22)]
+    for f in (0, 1):
+        gpu.ncc_set_image(f, imgs[f])
+    gpu.predict(); gpu.measure(); gpu.match_ncc(0.8)
+    for f, orc in ((0, orc0), (1, orc1)):
+        orc.predict(); orc.measure()
+        mo = orc.get_measure()
+        matched, z, score, level = ncc_oracle.search(ncc_oracle.pyramid(imgs[f]), tmpl, mo["vis"], mo["h"], mo["ell"][:, :2], mo["ell"][:, 2])
+        r = gpu.feature_results(f)
+        gs, gl = gpu.ncc_scores(f)
+        assert np.array_equal(gs, score) and np.array_equal(gl, level) and np.array_equal(r["matched"], matched)
+        assert np.array_equal(r["z"][matched.astype(bool)], z[matched.astype(bool)])
+    assert gpu.frame_info(0)["n_matches"] != gpu.frame_info(1)["n_matches"] or not np.array_equal(gpu.ncc_scores(0)[0], gpu.ncc_scores(1)[0])
