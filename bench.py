@@ -283,10 +283,9 @@ def main():
             gpu.flush_l2()
         gpu.sync()
         t0 = time.perf_counter()
-        for i in range(F):
-            xy, ds = pin[i][s]
-            gpu.set_keypoints_raw(i, xy.data_ptr(), ds.data_ptr(), xy.shape[0])
-            h2d += xy.numel() * 4 + ds.numel()
+        cur = [pin[i][s] for i in range(F)]
+        gpu.set_keypoints_batch_raw([xy.data_ptr() for xy, _ in cur], [ds.data_ptr() for _, ds in cur], [xy.shape[0] for xy, _ in cur])
+        h2d += sum(xy.numel() * 4 + ds.numel() for xy, ds in cur)
         gpu.step()
         recs = gpu.records()                           # D2H + sync
         e2e_s += time.perf_counter() - t0

@@ -99,6 +99,8 @@ int ekfb_get_dims(ekfb_handle h, int filter, int32_t* n, int32_t* n_features);
 /* ---- front-end output (what detector->detect + extractor->compute return, E/Matching.cpp:204-215) */
 /* host buffers: xy = n_kp x 2 float32 pixel coordinates, desc = n_kp x 32 bytes; copied to the device */
 int ekfb_set_keypoints(ekfb_handle h, int filter, const float* xy, const uint8_t* desc, int n_kp);
+/* the same for all filters of the handle in one call (xy[f], desc[f], n_kp[f] per filter): one pointer-table / count update */
+int ekfb_set_keypoints_batch(ekfb_handle h, const float* const* xy, const uint8_t* const* desc, const int32_t* n_kp);
 /* device-resident sequences: upload all frames once, then select a frame with no host traffic.
  * kp_offset has n_frames+1 entries (prefix sums of per-frame keypoint counts). */
 int ekfb_load_sequence(ekfb_handle h, int filter, int n_frames, const int32_t* kp_offset, const float* xy,

@@ -127,6 +127,12 @@ class EkfBatch:
         self._ck(self.L.ekfb_set_keypoints(self.h, ctypes.c_int(f), ctypes.c_void_p(xy_ptr), ctypes.c_void_p(desc_ptr),
                                            ctypes.c_int(n_kp)))
 
+    def set_keypoints_batch_raw(self, xy_ptrs, desc_ptrs, counts):
+        """all filters in one call: lists of host pointers (ints) and counts"""
+        F = self.n_filters
+        a = (ctypes.c_void_p * F)(*xy_ptrs); b = (ctypes.c_void_p * F)(*desc_ptrs); n = (ctypes.c_int32 * F)(*counts)
+        self._ck(self.L.ekfb_set_keypoints_batch(self.h, a, b, n))
+
     def load_sequence(self, f, frames):
         """frames: list of (xy, desc) per frame; uploads them all to device memory."""
         off = np.zeros(len(frames) + 1, np.int32)

@@ -67,6 +67,8 @@ struct ekfb_ctx {
     const uint8_t** h_kpdesc_ptr = nullptr;
     const float** d_kpxy_ptr = nullptr;
     const uint8_t** d_kpdesc_ptr = nullptr;
+    int* h_kpcount = nullptr;       // pinned
+    int* d_kpcount = nullptr;
     std::vector<SeqDev> seq;
     RecordDev* d_rec = nullptr;
     RecordDev* h_rec = nullptr;  // pinned
@@ -223,7 +225,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     ALLOC(v.hypcount, F * N); ALLOC(v.hypsup, F * N * c->supWords);
     ALLOC(v.Bu, F * c->kmax * c->ld); ALLOC(v.S, F * c->kmax * c->ldS); ALLOC(v.Sf, F * c->kmax * c->ldS); ALLOC(v.dx, F * c->ld); ALLOC(v.dbg, 64); ALLOC(v.Uinv, F * (c->kmax / kNB) * kNB * kNB); ALLOC(v.Jq, F * 16);
     ALLOC(c->d_kpxy, F * c->Kpmax * 2); ALLOC(c->d_kpdesc, F * c->Kpmax * 32);
-    ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F);
+    ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F); ALLOC(c->d_kpcount, F);
     ALLOC(c->d_rec, F);
     v.kpxy = c->d_kpxy_ptr;
     v.kpdesc = c->d_kpdesc_ptr;
@@ -241,6 +243,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     }
     CK(cudaMallocHost(&c->h_kpxy_ptr, F * sizeof(void*)));
     CK(cudaMallocHost(&c->h_kpdesc_ptr, F * sizeof(void*)));
+    CK(cudaMallocHost(&c->h_kpcount, F * sizeof(int)));
     CK(cudaMallocHost(&c->h_rec, F * sizeof(RecordDev)));
     std::memset(c->h_dims, 0, F * D_STRIDE * sizeof(int));
     for (int f = 0; f < c->F; ++f) {
@@ -292,6 +295,7 @@ extern "C" int ekfb_destroy(ekfb_handle c)
     if (c->h_dims_zc) cudaFreeHost(c->h_dims_zc);
     cudaFreeHost(c->h_kpxy_ptr);
     cudaFreeHost(c->h_kpdesc_ptr);
+    cudaFreeHost(c->h_kpcount);
     cudaFreeHost(c->h_rec);
     for (int i = 0; i < 64; ++i) cudaEventDestroy(c->timers[i]);
     cudaEventDestroy(c->pe[0]);
@@ -389,13 +393,15 @@ extern "C" int ekfb_get_dims(ekfb_handle c, int f, int32_t* n, int32_t* N)
 // ---- keypoints ----------------------------------------------------------------------------------
 static int push_kp_meta(ekfb_ctx* c)
 {
+    // pointer tables and counts of all filters: three copies and one launch, whatever the number of filters
     const size_t F = c->F;
-    for (int f = 0; f < c->F; ++f) c->h_dims[(size_t)f * D_STRIDE + D_N_KP] = c->hKp[f];
+    for (int f = 0; f < c->F; ++f) c->h_dims[(size_t)f * D_STRIDE + D_N_KP] = c->h_kpcount[f] = c->hKp[f];
     CK(cudaMemcpyAsync(c->d_kpxy_ptr, c->h_kpxy_ptr, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_kpdesc_ptr, c->h_kpdesc_ptr, F * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
-    for (int f = 0; f < c->F; ++f)
-        CK(cudaMemcpyAsync(c->v.dims + (size_t)f * D_STRIDE + D_N_KP, c->h_dims + (size_t)f * D_STRIDE + D_N_KP,
-                           sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_kpcount, c->h_kpcount, F * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    k_set_kp_counts<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->v, c->d_kpcount);
+    count_launch(c);
+    CK(cudaGetLastError());
     return EKFB_OK;
 }
 
@@ -423,6 +429,32 @@ extern "C" int ekfb_set_keypoints(ekfb_handle c, int f, const float* xy, const u
     CK(cudaMemcpyAsync(c->v.dims + (size_t)f * D_STRIDE + D_N_KP, c->h_dims + (size_t)f * D_STRIDE + D_N_KP, sizeof(int),
                        cudaMemcpyHostToDevice, c->stream));
     return EKFB_OK;
+}
+
+// ekfb_set_keypoints for every filter of the handle in one call: xy[f] / desc[f] = host buffers of filter f, n_kp[f] its count
+extern "C" int ekfb_set_keypoints_batch(ekfb_handle c, const float* const* xy, const uint8_t* const* desc, const int32_t* n_kp)
+{
+    REQUIRE(c && xy && desc && n_kp, "null argument");
+    CK(cudaSetDevice(c->device));
+    for (int f = 0; f < c->F; ++f) {
+        if (n_kp[f] > c->Kpmax || n_kp[f] < 0) {
+            g_err = "keypoint count exceeds the capacity reserved by ekfb_create";
+            return EKFB_ERR_CAPACITY;
+        }
+        REQUIRE(n_kp[f] == 0 || (xy[f] && desc[f]), "null keypoint buffer");
+    }
+    for (int f = 0; f < c->F; ++f) {
+        float* dxy = c->d_kpxy + (size_t)f * c->Kpmax * 2;
+        uint8_t* dds = c->d_kpdesc + (size_t)f * c->Kpmax * 32;
+        if (n_kp[f] > 0) {
+            CK(cudaMemcpyAsync(dxy, xy[f], sizeof(float) * 2 * n_kp[f], cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(dds, desc[f], (size_t)32 * n_kp[f], cudaMemcpyHostToDevice, c->stream));
+        }
+        c->hKp[f] = n_kp[f];
+        c->h_kpxy_ptr[f] = dxy;
+        c->h_kpdesc_ptr[f] = dds;
+    }
+    return push_kp_meta(c);
 }
 
 extern "C" int ekfb_load_sequence(ekfb_handle c, int f, int n_frames, const int32_t* kp_offset, const float* xy,

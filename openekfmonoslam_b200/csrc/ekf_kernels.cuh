@@ -668,6 +668,13 @@ __global__ void k_update_map_features(DevView v)
     }
 }
 
+// keypoint counts of all filters in one launch (ekfb_select_frame / ekfb_set_keypoints_batch)
+__global__ void k_set_kp_counts(DevView v, const int* counts)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < v.F) fdims(v, f)[D_N_KP] = counts[f];
+}
+
 // fixed-size result record per filter (13-state, 13x13 covariance block, counters)
 struct RecordDev {
     double x_cam[13];

@@ -104,3 +104,26 @@ def test_capacity_and_argument_errors():
     gpu.set_state(0, x[:n], P[:n, :n], ft[:20], fo[:20], desc[:20])       # and the handle is still usable
     gpu.set_keypoints(0, kp[:50], ds[:50]); gpu.step()
     assert gpu.frame_info(0)["status"] == 0
+
+
+def test_keypoints_of_all_filters_in_one_call():
+    """ekfb_set_keypoints_batch: three filters of one handle fed different frames (one of them empty) in one call"""
+    sc = Scenario(320, 240, 30)
+    x, P, ft, fo, desc, _ = sc.init_map()
+    gpu = EkfBatch(sc.params, 3, 30, 256)
+    orcs = []
+    for f in range(3):
+        gpu.set_state(f, x, P, ft, fo, desc)
+        o = OracleFilter(sc.params); o.set_state(x, P, ft, fo, desc)
+        orcs.append(o)
+    for t in (1, 2):
+        fr = [sc.frame(t), sc.frame(t + 5), NO_KP if t == 2 else sc.frame(t + 9)]
+        keep = [(np.ascontiguousarray(k), np.ascontiguousarray(d)) for k, d in fr]
+        gpu.set_keypoints_batch_raw([k.ctypes.data for k, _ in keep], [d.ctypes.data for _, d in keep], [len(k) for k, _ in keep])
+        gpu.step()
+        for f in range(3):
+            io = orcs[f].step(*fr[f])
+            ig = gpu.frame_info(f)
+            assert (io["n_matches"], io["n_inliers"], io["n_rescued"]) == (ig["n_matches"], ig["n_inliers"], ig["n_rescued"]), (t, f)
+            xo, Po = orcs[f].get_state(); xg, Pg = gpu.get_state(f)
+            assert rel_err(xg, xo) < 1e-9 and rel_err(Pg, Po) < 1e-9
