@@ -1,7 +1,7 @@
 """On-box timing of the NCC active search alone (BASELINE.json config 5: 1280x720 pyramid, N = 100..2000 features, every
 feature searched).  Prints per-launch time, features/s, candidate evaluations/s and the shared-memory read rate they imply
 (2 x 121 byte reads per candidate) beside the window bytes fetched from HBM / L2.
-usage: ncc_bench.py [W H] [N ...]"""
+usage: python tests/bench_ncc.py [N ...]   (lives under tests/ because it takes its templates from the oracle's helpers)"""
 import json
 import os
 import sys

@@ -1,7 +1,7 @@
 """BASELINE.json config 1 on the box: the reference's bundled experiments/s3 sequence (keypoint fixture, tests/golden/
 s3_keypoints.npz) through the sample driver of the drop-in EKF class (GPU, output.yml with the seven phase timers) and
 through the reference's own EKF::init / EKF::step (oracle/_ref, CPU, 1 thread).  Prints one JSON line: parity over the
-run, GPU microseconds per phase and frame, CPU milliseconds per frame.  usage: s3_report.py [out.json]"""
+run, GPU microseconds per phase and frame, CPU milliseconds per frame.  usage: python tests/report_s3.py [out.json]   (lives under tests/ because it runs the reference arm from oracle/)"""
 import ctypes
 import json
 import os
