@@ -238,7 +238,8 @@ enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* 0: 12
        EKFB_OPT_DOWNDATE_SMALL_K = 4 /* updates with at most this many rows run the downdate as 64x64 tiles, 4 CTAs/SM (default: all); above it 128x128 tiles */,
        EKFB_OPT_TRSM_STAGES = 5 /* upper limit of the slab TRSM's operand-ring depth: 2, 3 or 4 (default 4, as shared memory allows) */,
        EKFB_OPT_TRSM_PAIR = 6 /* batched filters: 1 (default) = slab footprint that lets two CTAs share an SM when possible */,
-       EKFB_OPT_RANSAC_CHUNK = 7 /* RANSAC hypotheses evaluated per round (0 = default: 16 single filter, 4 batched) */ };
+       EKFB_OPT_RANSAC_CHUNK = 7 /* RANSAC hypotheses evaluated per round (0 = default: 16 single filter, 4 batched) */,
+       EKFB_OPT_PDL = 8 /* 1 (default): the frame's kernels are launched with programmatic stream serialisation */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

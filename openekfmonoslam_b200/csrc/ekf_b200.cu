@@ -90,6 +90,7 @@ struct ekfb_ctx {
     // r01_downdate_sweep.txt) that variant wins at every k and n tried (16 resident warps hide the tile read-modify-write
     // and the operand ring better than 8 warps of one 128x128 CTA), so it is the default for all k; option 4 lowers it.
     int downdate_small_k = 1 << 30;
+    int use_pdl = 1;          // programmatic dependent launch for the kernels of the frame (option 8)
     int trsm_pair = 1;        // batched filters: slab footprint that fits two CTAs per SM when possible (option 6)
     int ransac_chunk = 0;     // hypotheses evaluated per round; 0 = 16 for a single filter, 4 for batches (option 7)
     int trsm_stages = 4;      // upper limit of the slab TRSM's operand ring depth (option 5)
@@ -159,6 +160,31 @@ static inline void count_launch(ekfb_ctx* c, int nlaunch = 1)
     c->launches += nlaunch;
     c->prof_launch[c->cur_group] += nlaunch;
 }
+
+// launch with the programmatic-stream-serialization attribute (see grid_dependency_wait in ekf_kernels.cuh);
+// ctx->use_pdl = 0 (option 9) turns every such launch into a plain one
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// a frame kernel on the handle's stream: with PDL unless the handle's switch is off
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(ekfb_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args)
+{
+    if (c->use_pdl) return launch_pdl(kernel, grid, block, smem, c->stream, args...);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 
 extern "C" const char* ekfb_last_error(void) { return g_err.c_str(); }
 
@@ -542,7 +568,7 @@ extern "C" int ekfb_predict(ekfb_handle c)
     GroupScope gs(c, G_PREDICT);
     const int n = max_of(c->hn);
     dim3 grid(1 + cdiv(std::max(n - 13, 0), 256), c->F);
-    k_predict_cov<<<grid, 256, 0, c->stream>>>(c->v);   // + the state prediction, by the block that finishes last
+    CK(launch_k(c, k_predict_cov, grid, dim3(256), 0, c->v));   // + the state prediction, by the block that finishes last
     count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
@@ -553,7 +579,7 @@ static int launch_measure(ekfb_ctx* c, int mode)
     const int N = max_of(c->hN);
     if (N == 0) return EKFB_OK;
     dim3 grid(cdiv(N, 8), c->F);
-    k_measure<<<grid, 256, 0, c->stream>>>(c->v, mode);
+    CK(launch_k(c, k_measure, grid, dim3(256), 0, c->v, mode));
     count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
@@ -577,16 +603,16 @@ extern "C" int ekfb_match(ekfb_handle c)
     CK(cudaMemsetAsync(v.mask, 0, (size_t)c->F * v.W * v.H, c->stream));
     if (N > 0) {
         const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
-        k_mask_raster<<<dim3(cdiv(N, 4), c->F), 128, rasterSmem, c->stream>>>(v, v.mask, v.maxAxes, 255);
+        CK(launch_k(c, k_mask_raster, dim3(cdiv(N, 4), c->F), dim3(128), rasterSmem, v, v.mask, v.maxAxes, 255));
         count_launch(c);
         if (Kp > 0) {
-            k_kp_mask<<<dim3(cdiv(Kp, 256), c->F), 256, 0, c->stream>>>(v);
+            CK(launch_k(c, k_kp_mask, dim3(cdiv(Kp, 256), c->F), dim3(256), 0, v));
             count_launch(c);
         }
-        k_match<<<dim3(cdiv(N, 8), c->F), 256, 0, c->stream>>>(v);
+        CK(launch_k(c, k_match, dim3(cdiv(N, 8), c->F), dim3(256), 0, v));
         count_launch(c);
     }
-    k_after_match<<<c->F, 256, 0, c->stream>>>(v);
+    CK(launch_k(c, k_after_match, dim3(c->F), dim3(256), 0, v));
     count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
@@ -603,9 +629,9 @@ extern "C" int ekfb_ransac(ekfb_handle c)
     const int n = max_of(c->hn), N = max_of(c->hN);
     (void)n;
     for (int chunk0 = 0; chunk0 < std::max(N, 1); chunk0 += CH) {
-        k_ransac_hyp<<<dim3(CH, c->F, cdiv(c->Nmax, kHypFeat)), 416, 0, c->stream>>>(c->v, chunk0);
+        CK(launch_k(c, k_ransac_hyp, dim3(CH, c->F, cdiv(c->Nmax, kHypFeat)), dim3(416), 0, c->v, chunk0));
         const int seq = ++c->dims_seq;
-        k_ransac_select<<<c->F, 256, 0, c->stream>>>(c->v, chunk0, CH, seq);
+        CK(launch_k(c, k_ransac_select, dim3(c->F), dim3(256), 0, c->v, chunk0, CH, seq));
         count_launch(c, 2);
         CK(cudaGetLastError());
         int rc = wait_published_dims(c, seq);
@@ -630,7 +656,7 @@ static int launch_downdate(ekfb_ctx* c, int n)
         k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
     else if (kMax <= c->downdate_small_k) {
         // 64x64 tiles, four CTAs per SM (the default at every k, see downdate_small_k)
-        k_downdate64<<<dim3(nI * (nI + 1) / 2 * 4, c->F), 128, kSmallSmemBytes, c->stream>>>(v, 0);
+        CK(launch_k(c, k_downdate64, dim3(nI * (nI + 1) / 2 * 4, c->F), dim3(128), kSmallSmemBytes, v, 0));
     } else {
         // 1-D grid over the T lower 128x128 tiles.  Single filter: if T is just above a multiple of the SM
         // count, the remainder would cost a whole extra wave; it runs as 64x64 tiles on a second stream,
@@ -664,19 +690,6 @@ static int launch_downdate(ekfb_ctx* c, int n)
         }
     }
     return EKFB_OK;
-}
-
-// launch with the programmatic-stream-serialization attribute (see grid_dependency_wait in ekf_linalg.cuh)
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 // Cholesky of [S | nu] for all filters of the handle (k = the largest 2 * ulist count): factor rows into Sf, inverses of
@@ -721,8 +734,8 @@ static int run_update(ekfb_ctx* c, int which)
     const int k = 2 * ku, n = max_of(c->hn);
     {
         GroupScope gs(c, G_GAIN);
-        k_gain_rows<<<dim3(cdiv(c->ld, 256), ku, c->F), 256, 0, c->stream>>>(v, which);
-        k_build_S<<<dim3(cdiv(k, 32), cdiv(k, 32), c->F), dim3(32, 8), 0, c->stream>>>(v, which);
+        CK(launch_k(c, k_gain_rows, dim3(cdiv(c->ld, 256), ku, c->F), dim3(256), 0, v, which));
+        CK(launch_k(c, k_build_S, dim3(cdiv(k, 32), cdiv(k, 32), c->F), dim3(32, 8), 0, v, which));
         count_launch(c, 2);
     }
     {
@@ -767,14 +780,14 @@ static int run_update(ekfb_ctx* c, int which)
                 }
             }
         }
-        k_state_apply<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);   // + quaternion normalisation (block 0)
+        CK(launch_k(c, k_state_apply, dim3(cdiv(n, 256), c->F), dim3(256), 0, v));   // + quaternion normalisation (block 0)
         count_launch(c);
     }
     {
         GroupScope gs(c, G_DOWNDATE);
         int rcD = launch_downdate(c, n);
         if (rcD != EKFB_OK) return rcD;
-        k_quat_cov<<<dim3(cdiv(n, 256), c->F), 256, 0, c->stream>>>(v);
+        CK(launch_k(c, k_quat_cov, dim3(cdiv(n, 256), c->F), dim3(256), 0, v));
         count_launch(c, 2);
     }
     CK(cudaGetLastError());
@@ -797,7 +810,7 @@ extern "C" int ekfb_rescue(ekfb_handle c)
     int rc = launch_measure(c, 1);
     if (rc != EKFB_OK) return rc;
     const int seq = ++c->dims_seq;
-    k_rescue_gate<<<c->F, 256, 0, c->stream>>>(c->v, seq);
+    CK(launch_k(c, k_rescue_gate, dim3(c->F), dim3(256), 0, c->v, seq));
     count_launch(c);
     CK(cudaGetLastError());
     return wait_published_dims(c, seq);
@@ -810,7 +823,7 @@ extern "C" int ekfb_update_map_features(ekfb_handle c)
     GroupScope gs(c, G_MISC);
     const int N = max_of(c->hN);
     if (N == 0) return EKFB_OK;
-    k_update_map_features<<<dim3(cdiv(N, 256), c->F), 256, 0, c->stream>>>(c->v);
+    CK(launch_k(c, k_update_map_features, dim3(cdiv(N, 256), c->F), dim3(256), 0, c->v));
     count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
@@ -863,7 +876,7 @@ extern "C" int ekfb_map_management(ekfb_handle c, const ekfb_map_policy* pol, ek
         // here because the predictions are indexed by the feature numbering of this frame's measurement.
         CK(cudaMemsetAsync(c->mask2, 255, (size_t)c->F * v.W * v.H, c->stream));
         const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
-        k_mask_raster<<<dim3(cdiv(max_of(c->hN), 4), c->F), 128, rasterSmem, c->stream>>>(v, c->mask2, 2 * (v.W + v.H), 0);
+        CK(launch_k(c, k_mask_raster, dim3(cdiv(max_of(c->hN), 4), c->F), dim3(128), rasterSmem, v, c->mask2, 2 * (v.W + v.H), 0));
         count_launch(c);
         c->mask2_valid = true;
     } else if (needNew) {
@@ -1192,7 +1205,7 @@ extern "C" int ekfb_match_ncc(ekfb_handle c, double ncc_min)
         k_search_ncc<<<c->hN[f], 128, 0, c->stream>>>(c->v, nv, f);
         count_launch(c);
     }
-    k_after_match<<<c->F, 256, 0, c->stream>>>(c->v);
+    CK(launch_k(c, k_after_match, dim3(c->F), dim3(256), 0, c->v));
     count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
@@ -1451,10 +1464,11 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_RANSAC_CHUNK, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_PDL, "unknown option");
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
     if (option == EKFB_OPT_TRSM_STAGES) { c->trsm_stages = value; return EKFB_OK; }
     if (option == EKFB_OPT_TRSM_PAIR) { c->trsm_pair = value; return EKFB_OK; }
+    if (option == EKFB_OPT_PDL) { c->use_pdl = value; return EKFB_OK; }
     if (option == EKFB_OPT_RANSAC_CHUNK) { c->ransac_chunk = value; return EKFB_OK; }
     if (option == EKFB_OPT_FORCE_GENERIC_FACTOR) c->force_generic = value != 0;
     else if (option == EKFB_OPT_SCHAIN_VARIANT) c->schain_variant = value;

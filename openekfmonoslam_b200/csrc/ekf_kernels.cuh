@@ -53,6 +53,13 @@ struct DevView {
 
 __device__ __forceinline__ int* fdims(const DevView& v, int f) { return v.dims + (size_t)f * D_STRIDE; }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may be scheduled
+// while its predecessor in the stream is still draining; it must not touch the predecessor's output before
+// grid_dependency_wait(), which every kernel of the frame therefore executes first (a no-op for a plain launch).
+// grid_launch_dependents() lets the successor be scheduled before this grid's blocks exit.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // The two kernels whose counters size the next launches (k_ransac_select, k_rescue_gate) end by writing the filter's counter
 // block straight into mapped host memory and then a sequence number the host spins on: the host learns the counts a few
 // microseconds after the kernel's last store instead of after a copy + stream synchronisation.  Call from all threads.
@@ -76,6 +83,7 @@ __device__ __forceinline__ void publish_dims(const DevView& v, int f, int seq)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_predict_cov(DevView v)
 {
+    grid_dependency_wait();
     const int f = blockIdx.y;
     const int n = fdims(v, f)[D_N_STATE];
     __shared__ double F[169], GQG[169], Pxx[169], T[169];
@@ -157,6 +165,7 @@ __global__ void k_symmetrize(DevView v, int f)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_measure(DevView v, int mode)
 {
+    grid_dependency_wait();
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     const int N = dm[D_N_FEAT];
@@ -235,6 +244,7 @@ __global__ void __launch_bounds__(256) k_measure(DevView v, int mode)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_mask_raster(DevView v, uint8_t* maskBase, int maxAxes, int val)
 {
+    grid_dependency_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.y;
     const int N = fdims(v, f)[D_N_FEAT];
@@ -259,6 +269,7 @@ __global__ void __launch_bounds__(128) k_mask_raster(DevView v, uint8_t* maskBas
 // (cv::KeyPointsFilter::runByPixelsMask, applied inside detector->detect, E/Matching.cpp:206)
 __global__ void k_kp_mask(DevView v)
 {
+    grid_dependency_wait();
     const int f = blockIdx.y;
     const int Kp = fdims(v, f)[D_N_KP];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -277,6 +288,7 @@ __global__ void k_kp_mask(DevView v)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_match(DevView v)
 {
+    grid_dependency_wait();
     // keypoint positions and mask flags are staged in shared memory, 1024 at a time, for the eight features of the CTA
     constexpr int CHUNK = 1024;
     __shared__ float2 sxy[CHUNK];
@@ -397,6 +409,7 @@ __device__ inline int block_compact(const uint8_t* flags, int N, int* list)
 // after matching: counts, match list, RANSAC state reset (E/1PointRansac.cpp:101-125)
 __global__ void __launch_bounds__(256) k_after_match(DevView v)
 {
+    grid_dependency_wait();
     const int f = blockIdx.x;
     int* dm = fdims(v, f);
     const int N = dm[D_N_FEAT];
@@ -443,6 +456,7 @@ constexpr int kHypFeat = 64;  // features per CTA
 
 __global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0)
 {
+    grid_dependency_wait();
     __shared__ double xc[13], xs[kHypFeat * 6];
     __shared__ double sK[4], sNu[2], sHx[14], sHf[12], sR[27];
     const int f = blockIdx.y, part = blockIdx.z;
@@ -537,6 +551,7 @@ __global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0)
 // match order (:201-227) and the inlier list for the low-innovation update.
 __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, int chunkLen, int seq)
 {
+    grid_dependency_wait();
     const int f = blockIdx.x;
     int* dm = fdims(v, f);
     const size_t fo = (size_t)f * v.Nmax;
@@ -615,6 +630,7 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, int seq)
 {
+    grid_dependency_wait();
     const int f = blockIdx.x;
     int* dm = fdims(v, f);
     const size_t fo = (size_t)f * v.Nmax;
@@ -652,6 +668,7 @@ __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, int seq)
 // updateMapFeatures (E/MapManagement.cpp:77-113): hit counters and descriptor refresh of inliers + rescued
 __global__ void k_update_map_features(DevView v)
 {
+    grid_dependency_wait();
     const int f = blockIdx.y;
     const int N = fdims(v, f)[D_N_FEAT];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;

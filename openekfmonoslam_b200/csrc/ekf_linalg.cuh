@@ -42,6 +42,7 @@ __device__ __forceinline__ UpdSrc upd_src(const DevView& v, int which)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gain_rows(DevView v, int which)
 {
+    grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
     const int f = blockIdx.z, a = blockIdx.y;
     const int* dm = fdims(v, f);
     if (a >= dm[D_ULIST]) return;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) k_gain_rows(DevView v, int which)
 // out of shared memory and S is written with the lanes along rb.  grid (ceil(k/32), ceil(k/32), F), block (32, 8).
 __global__ void __launch_bounds__(256) k_build_S(DevView v, int which)
 {
+    grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
     constexpr int BP = 105;  // 7 + 16 * 6 columns, odd pitch
     __shared__ double Bs[32 * BP];
     __shared__ double Hs[32 * 13];
@@ -332,8 +334,7 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
 // while its predecessor in the stream is still running; it must not touch the predecessor's output before
 // grid_dependency_wait().  grid_launch_dependents() lets the successor be scheduled early.
-__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+// (grid_dependency_wait / grid_launch_dependents are defined in ekf_kernels.cuh)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
@@ -514,6 +515,7 @@ constexpr int kSmallSmemBytes = kStages * kKC * (68 + 68) * (int)sizeof(double);
 
 __global__ void __maxnreg__(112) k_downdate64(DevView v, int firstBig)
 {
+    grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
     extern __shared__ __align__(16) double ssm2[];
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
@@ -1194,6 +1196,7 @@ __global__ void __launch_bounds__(128, 2) k_downdate(DevView v)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_state_apply(DevView v)
 {
+    grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     if (dm[D_ULIST] == 0) return;
@@ -1223,6 +1226,7 @@ __global__ void __launch_bounds__(256) k_state_apply(DevView v)
 // and columns 3..6 change.  grid (ceil(n/256), F)
 __global__ void __launch_bounds__(256) k_quat_cov(DevView v)
 {
+    grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     if (dm[D_ULIST] == 0) return;
