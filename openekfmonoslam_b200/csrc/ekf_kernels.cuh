@@ -59,6 +59,9 @@ __device__ __forceinline__ int* fdims(const DevView& v, int f) { return v.dims +
 // grid_launch_dependents() lets the successor be scheduled before this grid's blocks exit.
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+#ifndef PDL_EARLY_TRIGGER
+#define PDL_EARLY_TRIGGER 0   /* measured: triggering the successor at kernel start is slightly slower than letting it launch as blocks exit */
+#endif
 
 // The two kernels whose counters size the next launches (k_ransac_select, k_rescue_gate) end by writing the filter's counter
 // block straight into mapped host memory and then a sequence number the host spins on: the host learns the counts a few
@@ -84,6 +87,7 @@ __device__ __forceinline__ void publish_dims(const DevView& v, int f, int seq)
 __global__ void __launch_bounds__(256) k_predict_cov(DevView v)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     const int f = blockIdx.y;
     const int n = fdims(v, f)[D_N_STATE];
     __shared__ double F[169], GQG[169], Pxx[169], T[169];
@@ -166,6 +170,7 @@ __global__ void k_symmetrize(DevView v, int f)
 __global__ void __launch_bounds__(256) k_measure(DevView v, int mode)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     const int N = dm[D_N_FEAT];
@@ -245,6 +250,7 @@ __global__ void __launch_bounds__(256) k_measure(DevView v, int mode)
 __global__ void __launch_bounds__(128) k_mask_raster(DevView v, uint8_t* maskBase, int maxAxes, int val)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.y;
     const int N = fdims(v, f)[D_N_FEAT];
@@ -270,6 +276,7 @@ __global__ void __launch_bounds__(128) k_mask_raster(DevView v, uint8_t* maskBas
 __global__ void k_kp_mask(DevView v)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     const int f = blockIdx.y;
     const int Kp = fdims(v, f)[D_N_KP];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,6 +296,7 @@ __global__ void k_kp_mask(DevView v)
 __global__ void __launch_bounds__(256) k_match(DevView v)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     // keypoint positions and mask flags are staged in shared memory, 1024 at a time, for the eight features of the CTA
     constexpr int CHUNK = 1024;
     __shared__ float2 sxy[CHUNK];
@@ -410,6 +418,7 @@ __device__ inline int block_compact(const uint8_t* flags, int N, int* list)
 __global__ void __launch_bounds__(256) k_after_match(DevView v)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     const int f = blockIdx.x;
     int* dm = fdims(v, f);
     const int N = dm[D_N_FEAT];
@@ -457,6 +466,7 @@ constexpr int kHypFeat = 64;  // features per CTA
 __global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     __shared__ double xc[13], xs[kHypFeat * 6];
     __shared__ double sK[4], sNu[2], sHx[14], sHf[12], sR[27];
     const int f = blockIdx.y, part = blockIdx.z;
@@ -552,6 +562,7 @@ __global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0)
 __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, int chunkLen, int seq)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     const int f = blockIdx.x;
     int* dm = fdims(v, f);
     const size_t fo = (size_t)f * v.Nmax;
@@ -631,6 +642,7 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
 __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, int seq)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     const int f = blockIdx.x;
     int* dm = fdims(v, f);
     const size_t fo = (size_t)f * v.Nmax;
@@ -669,6 +681,7 @@ __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, int seq)
 __global__ void k_update_map_features(DevView v)
 {
     grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     const int f = blockIdx.y;
     const int N = fdims(v, f)[D_N_FEAT];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;

@@ -43,6 +43,7 @@ __device__ __forceinline__ UpdSrc upd_src(const DevView& v, int which)
 __global__ void __launch_bounds__(256) k_gain_rows(DevView v, int which)
 {
     grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();
     const int f = blockIdx.z, a = blockIdx.y;
     const int* dm = fdims(v, f);
     if (a >= dm[D_ULIST]) return;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) k_gain_rows(DevView v, int which)
 __global__ void __launch_bounds__(256) k_build_S(DevView v, int which)
 {
     grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();
     constexpr int BP = 105;  // 7 + 16 * 6 columns, odd pitch
     __shared__ double Bs[32 * BP];
     __shared__ double Hs[32 * 13];
@@ -516,6 +518,7 @@ constexpr int kSmallSmemBytes = kStages * kKC * (68 + 68) * (int)sizeof(double);
 __global__ void __maxnreg__(112) k_downdate64(DevView v, int firstBig)
 {
     grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();
     extern __shared__ __align__(16) double ssm2[];
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
@@ -1197,6 +1200,7 @@ __global__ void __launch_bounds__(128, 2) k_downdate(DevView v)
 __global__ void __launch_bounds__(256) k_state_apply(DevView v)
 {
     grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     if (dm[D_ULIST] == 0) return;
@@ -1227,6 +1231,7 @@ __global__ void __launch_bounds__(256) k_state_apply(DevView v)
 __global__ void __launch_bounds__(256) k_quat_cov(DevView v)
 {
     grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     if (dm[D_ULIST] == 0) return;
