@@ -134,7 +134,7 @@ void State::removeAllFeatures()
 
 EKF::EKF(const char* configurationFileName, const char* outputPath)
     : _ekfSteps(0), _strOutputPath(outputPath ? outputPath : ""), _maxFeatures(0), _device(0), _configOk(false),
-      _frontEnd(nullptr), _deviceFrontEnd(false), _fastThreshold(20), _h(nullptr), _lastAdded(0), _stampR(0)
+      _frontEnd(nullptr), _deviceFrontEnd(false), _fastThreshold(20), _h(nullptr), _lastAdded(0), _featuresBefore(0), _stampR(0)
 {
     std::memset(&_info, 0, sizeof(_info));
     std::memset(&_mapResult, 0, sizeof(_mapResult));
