@@ -134,7 +134,27 @@ def cpu_oracle_sample(wl, N, budget_s=25.0, max_frames=20):
                       f"k differs slightly from the steady-state frames timed on the GPU")
     if phases:
         out["us_per_phase"] = {k: v / frames for k, v in phases.items()}
+    out["dense_products_all_cores"] = dense_products_all_cores(13 + 6 * N, min(2 * int(0.65 * N), 13 + 6 * N))
     return out
+
+
+def dense_products_all_cores(n, k):
+    """Fairness line of SURVEY 8d: the reference's single-threaded cv::gemm is not what a tuned CPU library would do, so the dense
+    products of its update (Update.cpp:92-109,214-218: P H^T, H (P H^T) + R, (P H^T) S^-1, (I - K H) P) are also timed with numpy /
+    OpenBLAS on all host cores, once, at the workload's n and its typical low-innovation k.  Not the reference, not the target."""
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(n, 16))
+    P = A @ A.T + np.eye(n)
+    H = rng.normal(size=(k, n))
+    t0 = time.perf_counter()
+    PHt = P @ H.T
+    S = H @ PHt + np.eye(k)
+    K = PHt @ np.linalg.inv(S)
+    P2 = (np.eye(n) - K @ H) @ P
+    dt = time.perf_counter() - t0
+    flops = 2.0 * n * n * k + 2.0 * n * k * k + 2.0 * n * k * k + 2.0 * k ** 3 + 2.0 * n * n * k + 2.0 * n ** 3
+    return {"seconds_per_update": dt, "gflops": flops / dt / 1e9, "n": n, "k": k, "cores": os.cpu_count(),
+            "what": "numpy/OpenBLAS, all cores, one low-innovation update in the reference's literal form", "checksum": float(P2[0, 0])}
 
 
 def measure_fp64_peak(device):
