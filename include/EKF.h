@@ -117,8 +117,8 @@ public:
     void setFrontEnd(FrontEnd* fe) { _frontEnd = fe; }
     // detector + descriptor on the GPU instead of a host FrontEnd object: FAST-9/16 (threshold) + 3x3 NMS + BRIEF-style
     // descriptor (ekfb_set_image / ekfb_detect_keypoints).  init / step then need the frame itself: CV_8UC1, CV_8UC3 (BGR,
-    // desktop: FileSequenceImageGenerator.cpp:82) or CV_8UC4 (Android: EKFNative.cpp:134-137), converted to grey like
-    // cv::cvtColor(COLOR_BGR2GRAY).
+    // desktop: FileSequenceImageGenerator.cpp:82) or CV_8UC4 (Android: EKFNative.cpp:134-137), converted to grey on the
+    // device like cv::cvtColor(COLOR_BGR2GRAY).
     void useDeviceFrontEnd(int fastThreshold) { _deviceFrontEnd = true; _fastThreshold = fastThreshold; }
     void setDevice(int device) { _device = device; }
     void syncCovariance();
@@ -143,7 +143,6 @@ private:
     FrontEnd* _frontEnd;
     bool _deviceFrontEnd;
     int _fastThreshold;
-    std::vector<unsigned char> _gray;
     ekfb_handle _h;
     ekfb_frame_info _info;
     ekfb_map_result _mapResult;

@@ -172,6 +172,9 @@ int ekfb_raster_ellipse(ekfb_handle h, int W, int H, double cx, double cy, const
 /* ---- detector + descriptor on the device (what detector->detect + extractor->compute do, E/Matching.cpp:204-215) */
 /* the frame as 8-bit grey (pixels_y rows of pixels_x bytes, `stride` bytes apart); also builds the NCC pyramid */
 int ekfb_set_image(ekfb_handle h, int filter, const uint8_t* gray, int stride);
+/* the same from an interleaved 8-bit colour frame (channels = 3: BGR, 4: BGRA; 1 = grey): converted on the device like
+ * cv::cvtColor(COLOR_BGR2GRAY) */
+int ekfb_set_image_color(ekfb_handle h, int filter, const uint8_t* pixels, int stride, int channels);
 /* FAST-9/16 corners with 3x3 non-maximum suppression (OpenCV's FastFeatureDetector(threshold, true), the "FAST" entry of the
  * reference's FeatureDetectorFactory) in raster order, keypoints closer than 18 pixels to the border dropped, each with a
  * 256-bit BRIEF-style descriptor; they replace ekfb_set_keypoints for this frame.  At most max_keypoints are kept. */

@@ -232,6 +232,12 @@ class EkfBatch:
         gray = np.ascontiguousarray(gray, np.uint8)
         self._ck(self.L.ekfb_set_image(self.h, ctypes.c_int(f), _ptr(gray), ctypes.c_int(gray.shape[1])))
 
+    def set_image_color(self, f, img):
+        """(H, W, 3) BGR or (H, W, 4) BGRA uint8"""
+        img = np.ascontiguousarray(img, np.uint8)
+        self._ck(self.L.ekfb_set_image_color(self.h, ctypes.c_int(f), _ptr(img), ctypes.c_int(img.shape[1] * img.shape[2]),
+                                             ctypes.c_int(img.shape[2])))
+
     def detect_keypoints(self, f, threshold):
         n = ctypes.c_int32()
         self._ck(self.L.ekfb_detect_keypoints(self.h, ctypes.c_int(f), ctypes.c_int(threshold), ctypes.byref(n)))

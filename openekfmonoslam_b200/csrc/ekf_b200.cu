@@ -110,6 +110,7 @@ struct ekfb_ctx {
     uint8_t* ncc_tmpl = nullptr;
     // device front end (ekf_frontend.cuh): corner-score image, per-row counts / offsets, keypoint count per filter
     uint8_t* fe_score = nullptr;
+    uint8_t* fe_color = nullptr;   // staging for a colour frame (W x H x 4)
     int* fe_rows = nullptr;   // [F][2][H]
     int* fe_count = nullptr;  // [F]
 };
@@ -1082,6 +1083,7 @@ static int ensure_ncc(ekfb_ctx* c)
     nv.ncc_min = 0.8;
     ALLOC(c->fe_score, (size_t)c->F * c->ncc_level_bytes[0]);
     ALLOC(c->fe_rows, (size_t)c->F * 2 * v.H);
+    ALLOC(c->fe_color, (size_t)v.W * v.H * 4);
     ALLOC(c->fe_count, (size_t)c->F);
     CK(cudaMemcpyToSymbolAsync(c_brief, kBriefPattern, sizeof(kBriefPattern), 0, cudaMemcpyHostToDevice, c->stream));
     c->ncc_ready = true;
@@ -1110,6 +1112,34 @@ extern "C" int ekfb_ncc_set_image(ekfb_handle c, int f, const uint8_t* gray, int
 }
 
 extern "C" int ekfb_set_image(ekfb_handle c, int f, const uint8_t* gray, int stride) { return ekfb_ncc_set_image(c, f, gray, stride); }
+
+// the frame as the callers of the reference hold it: 8-bit interleaved BGR (desktop, FileSequenceImageGenerator.cpp:82) or BGRA
+// (Android, EKFNative.cpp:134-137); converted to grey on the device, then as ekfb_set_image
+extern "C" int ekfb_set_image_color(ekfb_handle c, int f, const uint8_t* pixels, int stride, int channels)
+{
+    REQUIRE(c && pixels, "null argument");
+    REQUIRE(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+    if (channels == 1) return ekfb_ncc_set_image(c, f, pixels, stride);
+    REQUIRE(f >= 0 && f < c->F && stride >= c->v.W * channels, "bad filter index or stride");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_ncc(c);
+    if (rc != EKFB_OK) return rc;
+    NccView& nv = c->ncc;
+    const int W = nv.W[0], H = nv.H[0];
+    uint8_t* L[kNccLevels];
+    for (int l = 0; l < kNccLevels; ++l) L[l] = c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l];
+    CK(cudaMemcpy2DAsync(c->fe_color, (size_t)W * channels, pixels, stride, (size_t)W * channels, H, cudaMemcpyHostToDevice, c->stream));
+    k_bgr_to_gray<<<dim3(cdiv(W, 32), cdiv(H, 8)), dim3(32, 8), 0, c->stream>>>(c->fe_color, W * channels, channels, L[0], nv.pitch[0], W, H);
+    count_launch(c);
+    for (int l = 1; l < kNccLevels; ++l) {
+        k_pyr_down<<<dim3(cdiv(nv.W[l], 32), cdiv(nv.H[l], 8)), dim3(32, 8), 0, c->stream>>>(L[l - 1], nv.pitch[l - 1], L[l], nv.pitch[l],
+                                                                                          nv.W[l], nv.H[l]);
+        count_launch(c);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));   // the caller's frame may be pageable
+    return EKFB_OK;
+}
 
 // detector + descriptor on the device for the image of ekfb_set_image: the keypoints become the frame's front-end output
 extern "C" int ekfb_detect_keypoints(ekfb_handle c, int f, int threshold, int32_t* n_kp)

@@ -24,6 +24,16 @@ constexpr int kFastBorder = 18;   // keypoints closer than this to the border ar
 
 __device__ __constant__ signed char c_brief[256 * 4];
 
+// interleaved 8-bit BGR / BGRA -> grey like cv::cvtColor(COLOR_BGR2GRAY): (B 1868 + G 9617 + R 4899 + 2^13) >> 14
+// (what OpenCV's detectors do with a colour frame: E/Matching.cpp:206 passes the BGR image).  grid (ceil(W/32), ceil(H/8)), block (32, 8)
+__global__ void k_bgr_to_gray(const uint8_t* src, int spitch, int channels, uint8_t* dst, int dpitch, int W, int H)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const uint8_t* p = src + (size_t)y * spitch + (size_t)x * channels;
+    dst[(size_t)y * dpitch + x] = (uint8_t)((p[0] * 1868 + p[1] * 9617 + p[2] * 4899 + 8192) >> 14);
+}
+
 // grid (ceil(W/32), ceil(H/8)), block (32, 8)
 __global__ void __launch_bounds__(256) k_fast_score(const uint8_t* img, int pitch, int W, int H, int threshold, uint8_t* score)
 {

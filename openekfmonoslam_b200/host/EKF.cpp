@@ -304,20 +304,11 @@ bool EKF::acquireKeypoints(const cv::Mat& image)
         std::cerr << "EKF: the device front end needs a " << W << "x" << H << " frame" << std::endl;
         return false;
     }
-    const int cn = (int)(image.elemSize());
-    const unsigned char* src = image.data;
-    int stride = (int)image.step;
-    if (cn != 1) {   // cv::cvtColor(BGR2GRAY / BGRA2GRAY) for 8-bit: (B 1868 + G 9617 + R 4899 + 2^13) >> 14
-        _gray.resize((size_t)W * H);
-        for (int y = 0; y < H; ++y) {
-            const unsigned char* r = image.data + (size_t)y * image.step;
-            for (int x = 0; x < W; ++x, r += cn) _gray[(size_t)y * W + x] = (unsigned char)((r[0] * 1868 + r[1] * 9617 + r[2] * 4899 + 8192) >> 14);
-        }
-        src = _gray.data();
-        stride = W;
-    }
+    // the frame goes to the device as it is (grey, BGR or BGRA); the grey conversion of cv::cvtColor runs there
     int32_t n = 0;
-    if (ekfb_set_image(_h, 0, src, stride) != EKFB_OK || ekfb_detect_keypoints(_h, 0, _fastThreshold, &n) != EKFB_OK) return false;
+    if (ekfb_set_image_color(_h, 0, image.data, (int)image.step, (int)image.elemSize()) != EKFB_OK ||
+        ekfb_detect_keypoints(_h, 0, _fastThreshold, &n) != EKFB_OK)
+        return false;
     _kps.resize(n);
     _desc.resize((size_t)n * 32);
     return ekfb_get_keypoints(_h, 0, reinterpret_cast<float*>(_kps.data()), _desc.data()) == EKFB_OK;

@@ -145,3 +145,20 @@ def test_gpu_drop_in_class_with_device_front_end(tmp_path):
         assert abs(np.linalg.norm(x[3:7]) - 1.0) < 1e-12
     assert c[0] >= 55
     host.ekfb_host_ekf_destroy(e)
+
+
+@pytest.mark.gpu
+def test_gpu_colour_frame_to_grey_like_cvtcolor():
+    """ekfb_set_image_color: BGR / BGRA frames become the grey image cv::cvtColor(COLOR_BGR2GRAY) produces"""
+    cv2 = pytest.importorskip("cv2")
+    from openekfmonoslam_b200.capi import EkfBatch
+    from openekfmonoslam_b200.params import synthetic_params
+    rng = np.random.default_rng(8)
+    H, W = 187, 251
+    gpu = EkfBatch(synthetic_params(W, H), 1, 4, 64)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    gpu.set_image_color(0, bgr)
+    assert np.array_equal(gpu.ncc_level(0, 0), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    bgra = np.concatenate([bgr, rng.integers(0, 256, (H, W, 1), dtype=np.uint8)], axis=2)
+    gpu.set_image_color(0, bgra)
+    assert np.array_equal(gpu.ncc_level(0, 0), cv2.cvtColor(bgra, cv2.COLOR_BGRA2GRAY))
