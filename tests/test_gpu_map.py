@@ -143,3 +143,32 @@ def test_raster_ellipse_hook_matches_oracle():
         assert np.array_equal(a, b)
     st = gpu.raster_ellipse(np.full((64, 64), 255, np.uint8), 32, 32, np.diag([10.0, 10.0]), 1000, 0)
     assert st[32, 32] == 0 and st[0, 0] == 255
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_map_management_policy_branches(seed):
+    """Random hit counters and every branch of the removal policy (E/EKF.cpp:580-589), with and without a conversion:
+    the same script as tests/test_reference_pin.py::test_map_management_policy_branches, GPU against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    behind = tuple(sorted(rng.choice(40, size=4, replace=False)))
+    sc, orc, gpu = map_pair(40, behind)
+    for t in (1, 2):
+        phase_by_phase(sc, orc, gpu, t)
+    N = orc.dims()[1]
+    tp = rng.integers(1, 9, N).astype(np.int32)
+    tm = np.minimum(tp, rng.integers(0, 9, N)).astype(np.int32)
+    tp[list(behind)] = 0; tm[list(behind)] = 0
+    orc.set_hit_counters(tp, tm); gpu.set_hit_counters(0, tp, tm)
+    branch = seed % 4
+    pol = MapPolicy(min_matches_per_image=int(rng.integers(20, 80)),
+                    max_map_features_count=int(rng.integers(20, 45)) if branch == 1 else 0,
+                    max_map_size=int(rng.integers(150, 260)) if branch == 2 else 0,
+                    always_remove_unseen=1 if branch == 0 else 0,
+                    good_feature_matching_percent=float(rng.choice([0.3, 0.5, 0.7])),
+                    linearity_index_threshold=1e9 if seed % 2 else 0.1)
+    needed, removed, conv = orc.map_management(pol)
+    res = gpu.map_management(pol)[0]
+    assert (res["new_features_needed"], res["converted"]) == (needed, conv)
+    assert np.array_equal(gpu.removed_flags(0, N), removed)
+    same_map(orc, gpu, f"policy branch {branch}")
+    phase_by_phase(sc, orc, gpu, 3)

@@ -185,3 +185,36 @@ def test_map_management_remove_convert_add():
             assert conv == t - 3      # the first remaining inverse-depth feature each frame
     assert (o.get_features()["type"] == 1).sum() == 6
     r.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_map_management_policy_branches(seed):
+    """Random hit counters and every branch of the removal policy of E/EKF.cpp:580-589 (AlwaysRemoveUnseenMapFeatures,
+    MaxMapFeaturesCount, MaxMapSize, none), with and without a conversion, oracle against the reference's own functions."""
+    rng = np.random.default_rng(100 + seed)
+    behind = tuple(sorted(rng.choice(40, size=4, replace=False)))
+    sc, o, r, MapPolicy = map_scenario(40, behind)
+    for t in (1, 2):
+        phase_by_phase(sc, o, r, t)
+    N = o.dims()[1]
+    tp = rng.integers(1, 9, N).astype(np.int32)
+    tm = np.minimum(tp, rng.integers(0, 9, N)).astype(np.int32)
+    tp[list(behind)] = 0; tm[list(behind)] = 0          # the unseen features were never predicted (0/0 is not "bad")
+    o.set_hit_counters(tp, tm); r.set_hit_counters(tp, tm)
+    branch = seed % 4
+    pol = MapPolicy(min_matches_per_image=int(rng.integers(20, 80)),
+                    max_map_features_count=int(rng.integers(20, 45)) if branch == 1 else 0,
+                    max_map_size=int(rng.integers(150, 260)) if branch == 2 else 0,
+                    always_remove_unseen=1 if branch == 0 else 0,
+                    good_feature_matching_percent=float(rng.choice([0.3, 0.5, 0.7])),
+                    linearity_index_threshold=1e9 if seed % 2 else 0.1)
+    r.set_policy(pol)
+    needed, removed, conv = o.map_management(pol)
+    assert needed == r.map_management()
+    same_map(o, r, f"policy branch {branch}", 1e-9)
+    bad = (tm.astype(np.float32) / np.maximum(tp, 1).astype(np.float32) < pol.good_feature_matching_percent) & (tp > 0)
+    assert np.array_equal(removed == 1, bad)
+    if branch == 3:
+        assert not (removed == 2).any()
+    phase_by_phase(sc, o, r, 3, 1e-9)                  # and both keep running on the re-laid-out map
+    r.close()
