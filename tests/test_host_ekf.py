@@ -277,3 +277,33 @@ def test_sample_driver_with_map_management_follows_the_reference(tmp_path):
     assert last.getNode("UpdateLI").real() > 0
     fs.release()
     r.close()
+
+
+def test_config_reader_defaults_of_optional_keys(host, tmp_path):
+    """keys the reference treats as optional (ExtendedKalmanFilterConfiguration.cpp: MaxMapFeaturesCount, MaxMapSize,
+    AlwaysRemoveUnseenMapFeatures default to 0 / false) may be absent"""
+    cfg = str(tmp_path / "config.yml")
+    write_config(cfg, synthetic_params(320, 240), 25)
+    c = HostConfig()
+    assert host.ekfb_host_load_config_full(cfg.encode(), ctypes.byref(c)) == 0
+    pol = c.policy
+    assert (pol.min_matches_per_image, pol.max_map_size, pol.max_map_features_count, pol.always_remove_unseen) == (25, 0, 0, 0)
+    assert c.map_management_frequency == 0
+
+
+def test_new_feature_selection_takes_everything_when_few_keypoints(host):
+    """DetectNewImageFeatures.cpp:358-371: no more unmasked keypoints than requested -> all of them, in order, no rand() drawn"""
+    libc = ctypes.CDLL(None)
+    W, H = 320, 240
+    mask = np.full((H, W), 255, np.uint8)
+    mask[:, :100] = 0                                   # left part masked
+    kp = np.array([[50, 50], [150, 60], [200, 100], [99.6, 10], [310, 230]], np.float32)   # (99.6 + 0.5) -> column 100: kept
+    stamp = np.zeros((1, 1), np.uint8)
+    out = np.zeros(8, np.int32)
+    libc.srand(7); a = libc.rand(); libc.srand(7)
+    k = host.ekfb_host_select_new_features(W, H, 2, mask.ctypes.data_as(ctypes.c_void_p), stamp.ctypes.data_as(ctypes.c_void_p), 0,
+                                           kp.ctypes.data_as(ctypes.c_void_p), len(kp), None, 0, 8, out.ctypes.data_as(ctypes.c_void_p))
+    assert k == 4 and list(out[:4]) == [1, 2, 3, 4]
+    assert libc.rand() == a                              # the random stream was not touched
+    assert host.ekfb_host_select_new_features(W, H, 2, mask.ctypes.data_as(ctypes.c_void_p), stamp.ctypes.data_as(ctypes.c_void_p), 0,
+                                              kp.ctypes.data_as(ctypes.c_void_p), len(kp), None, 0, 0, out.ctypes.data_as(ctypes.c_void_p)) == 0
