@@ -172,3 +172,38 @@ def test_map_management_policy_branches(seed):
     assert np.array_equal(gpu.removed_flags(0, N), removed)
     same_map(orc, gpu, f"policy branch {branch}")
     phase_by_phase(sc, orc, gpu, 3)
+
+
+def test_map_management_large_map():
+    """N = 300 (n = 1813): the plan kernel's ordered scan runs over more than one block-wide chunk, the gather moves a
+    3-MB covariance, 50 features are added in one batch."""
+    rng = np.random.default_rng(5)
+    behind = tuple(sorted(rng.choice(300, size=25, replace=False)))
+    sc, orc, gpu = map_pair(300, behind, cap=360, W=640, H=480)
+    kp, ds = sc.frame(1)
+    orc.step(kp, ds)
+    gpu.set_keypoints(0, kp, ds); gpu.step()
+    N = orc.dims()[1]
+    tp = rng.integers(1, 9, N).astype(np.int32)
+    tm = np.minimum(tp, rng.integers(0, 9, N)).astype(np.int32)
+    tp[list(behind)] = 0; tm[list(behind)] = 0
+    orc.set_hit_counters(tp, tm); gpu.set_hit_counters(0, tp, tm)
+    pol = MapPolicy(min_matches_per_image=400, max_map_features_count=0, max_map_size=0, always_remove_unseen=1,
+                    good_feature_matching_percent=0.5, linearity_index_threshold=1e9)
+    needed, removed, conv = orc.map_management(pol)
+    res = gpu.map_management(pol)[0]
+    assert (res["new_features_needed"], res["converted"]) == (needed, conv) and conv >= 0
+    assert np.array_equal(gpu.removed_flags(0, N), removed) and (removed == 1).sum() > 50 and (removed == 2).sum() == 25
+    same_map(orc, gpu, "large map after removal + conversion")
+    uv = np.stack([rng.uniform(30, 600, 50).round(), rng.uniform(30, 450, 50).round()], 1)
+    dd = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    for a in range(50):
+        orc.add_feature(uv[a], dd[a])
+    gpu.add_features(0, uv, dd)
+    same_map(orc, gpu, "large map after a batch of 50 new features")
+    kp, ds = sc.frame(2)
+    io = orc.step(kp, ds)
+    gpu.set_keypoints(0, kp, ds); gpu.step()
+    ig = gpu.frame_info(0)
+    assert (io["n_matches"], io["n_inliers"], io["n_rescued"]) == (ig["n_matches"], ig["n_inliers"], ig["n_rescued"])
+    compare_state(orc, gpu, "large map, next frame")
