@@ -108,8 +108,10 @@ public:
     void init(const cv::Mat& image);
     void step(const cv::Mat& image);
 
-    // Attributes (E/EKF.h:50-51).  After every step(): state (camera + all feature positions) and the 13x13 camera
-    // block of stateCovarianceMatrix are current; syncCovariance() downloads the full matrix when a caller needs it.
+    // Attributes (E/EKF.h:50-51).  After every step(): state (camera, every feature's position, type, covarianceMatrixPos,
+    // descriptor, timesPredicted / timesMatched) and the 13x13 camera block of stateCovarianceMatrix are current.
+    // DIFFERENCE FROM THE REFERENCE: the rest of stateCovarianceMatrix lives on the GPU; syncCovariance() downloads the
+    // full n x n matrix when a caller needs it (the two shipped callers read only the camera block).
     Matd stateCovarianceMatrix;
     State state;
 
@@ -124,7 +126,16 @@ public:
     void syncCovariance();
     const ekfb_frame_info& lastFrameInfo() const { return _info; }
     ekfb_handle handle() const { return _h; }
-    bool ok() const { return _h != nullptr; }
+    // healthy: a device handle exists and the last init / step completed without an error (lastStatus() == EKFB_OK)
+    bool ok() const { return _h != nullptr && _lastStatus == 0; }
+    // ekfb status of the last init / step: EKFB_OK, or the code of the call that failed (CUDA error, capacity, wrong frame
+    // size ...), or EKFB_ERR_NUMERIC when an innovation covariance of the frame was not positive definite.  A failed frame
+    // leaves the step counter where it was and skips map management.
+    int lastStatus() const { return _lastStatus; }
+    // test hook: after every step() append the frame's per-feature results (numbering before map management) to a binary
+    // file: int32 N, then matched[N], inlier[N], rescued[N] (uint8), keypoint index[N] (int32), z[N][2] (double)
+    bool dumpFrameSetsTo(const char* path);
+    int capacityFeatures() const { return _maxFeatures; }
 
     const ekfb_map_result& lastMapResult() const { return _mapResult; }
     int lastNewFeatures() const { return _lastAdded; }
@@ -135,6 +146,9 @@ private:
     void refreshMirror(bool layout);
     bool acquireKeypoints(const cv::Mat& image);
     int addNewFeatures(int wanted, bool useDeviceMask);
+    bool growCapacity(int minFeatures);
+    void fail(int status, const char* where);
+    void dumpFrameSets();
     int _ekfSteps;
     std::string _strOutputPath;
     EkfHostConfig _cfg;
@@ -152,6 +166,8 @@ private:
     std::vector<unsigned char> _mask, _stamp;
     int _stampR;
     EkfbTraceWriter _trace;
+    int _lastStatus;
+    void* _setDump;   // FILE*
 };
 
 // reads the reference's YAML 1.0 configuration (experiments/s3/config.yml, kalmanFilter/samples/EKF/config.yml)

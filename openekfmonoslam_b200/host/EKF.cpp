@@ -3,7 +3,9 @@
 // mathematics is on the GPU, the host keeps the reference's public state object in sync.
 #include "../../include/EKF.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <iostream>
 
@@ -134,14 +136,17 @@ void State::removeAllFeatures()
 
 EKF::EKF(const char* configurationFileName, const char* outputPath)
     : _ekfSteps(0), _strOutputPath(outputPath ? outputPath : ""), _maxFeatures(0), _device(0), _configOk(false),
-      _frontEnd(nullptr), _deviceFrontEnd(false), _fastThreshold(20), _h(nullptr), _lastAdded(0), _featuresBefore(0), _stampR(0)
+      _frontEnd(nullptr), _deviceFrontEnd(false), _fastThreshold(20), _h(nullptr), _lastAdded(0), _featuresBefore(0), _stampR(0),
+      _lastStatus(0), _setDump(nullptr)
 {
     std::memset(&_info, 0, sizeof(_info));
     std::memset(&_mapResult, 0, sizeof(_mapResult));
     _configOk = ekfbLoadConfigFull(configurationFileName, &_cfg);
     if (!_configOk) std::cerr << "EKF: could not load configuration " << configurationFileName << std::endl;
-    // capacity in features: MaxMapSize is in rows of the state (E/EKF.cpp:582-584) and a frame may add up to
-    // MinMatchesPerImage features on top of it before the next removal; without a limit allow 4x the target
+    // INITIAL capacity in features: MaxMapSize is in rows of the state (E/EKF.cpp:582-584) and a frame may add up to
+    // MinMatchesPerImage features on top of it before the next removal; without a limit start at 4x the target.  The
+    // reference's map has no upper bound (E/EKF.cpp:594-611 adds every feature it asked for), so when a frame's new
+    // features do not fit the handle is re-created with a larger capacity (growCapacity) -- never truncated.
     const int minM = _cfg.policy.min_matches_per_image > 0 ? _cfg.policy.min_matches_per_image : 64;
     if (_cfg.policy.max_map_features_count > 0) _maxFeatures = _cfg.policy.max_map_features_count + minM;
     else if (_cfg.policy.max_map_size > 13) _maxFeatures = (_cfg.policy.max_map_size - 13) / 3 + minM;
@@ -157,6 +162,67 @@ EKF::EKF(const char* configurationFileName, const char* outputPath)
 EKF::~EKF()
 {
     if (_h) ekfb_destroy(_h);
+    if (_setDump) std::fclose((FILE*)_setDump);
+}
+
+void EKF::fail(int status, const char* where)
+{
+    _lastStatus = status ? status : EKFB_ERR_ARG;
+    std::cerr << where << ": " << ekfb_last_error() << std::endl;
+}
+
+bool EKF::dumpFrameSetsTo(const char* path)
+{
+    if (_setDump) std::fclose((FILE*)_setDump);
+    _setDump = path ? (void*)std::fopen(path, "wb") : nullptr;
+    return _setDump != nullptr;
+}
+
+void EKF::dumpFrameSets()
+{
+    int32_t n = 0, N = 0;
+    ekfb_get_dims(_h, 0, &n, &N);
+    const int M = N > 0 ? N : 1;
+    std::vector<unsigned char> matched(M), inl(M), resc(M);
+    std::vector<int32_t> kp(M);
+    std::vector<double> z(2 * (size_t)M);
+    if (ekfb_get_feature_results(_h, 0, nullptr, nullptr, nullptr, nullptr, nullptr, matched.data(), z.data(), kp.data(), nullptr,
+                                 inl.data(), nullptr, resc.data()) != EKFB_OK)
+        return;
+    FILE* f = (FILE*)_setDump;
+    std::fwrite(&N, 4, 1, f);
+    std::fwrite(matched.data(), 1, N, f); std::fwrite(inl.data(), 1, N, f); std::fwrite(resc.data(), 1, N, f);
+    std::fwrite(kp.data(), 4, N, f); std::fwrite(z.data(), 8, 2 * (size_t)N, f);
+    std::fflush(f);
+}
+
+// The reference's map grows without bound; the device handle has a fixed capacity.  Re-create it with room for at least
+// minFeatures features and carry the whole filter over (state, covariance, layout, descriptors, hit counters).
+bool EKF::growCapacity(int minFeatures)
+{
+    int32_t n = 0, N = 0;
+    ekfb_get_dims(_h, 0, &n, &N);
+    const int newMax = std::max(minFeatures, 2 * _maxFeatures);
+    std::vector<double> x(n), P((size_t)n * n);
+    const int M = N > 0 ? N : 1;
+    std::vector<int32_t> type(M), off(M), tp(M), tm(M);
+    std::vector<unsigned char> desc((size_t)M * 32);
+    int rc = ekfb_get_state(_h, 0, x.data(), P.data(), 0);
+    if (rc == EKFB_OK) rc = ekfb_get_map_snapshot(_h, 0, nullptr, type.data(), off.data(), desc.data(), tp.data(), tm.data(), nullptr);
+    ekfb_handle h2 = nullptr;
+    if (rc == EKFB_OK) rc = ekfb_create(&_cfg.params, _device, 1, newMax, 16384, &h2);
+    if (rc == EKFB_OK) rc = ekfb_set_state(h2, 0, n, N, x.data(), type.data(), off.data(), P.data(), desc.data());
+    if (rc == EKFB_OK && N > 0) rc = ekfb_set_hit_counters(h2, 0, tp.data(), tm.data());
+    if (rc != EKFB_OK) {
+        if (h2) ekfb_destroy(h2);
+        fail(rc, "EKF: could not grow the map capacity");
+        return false;
+    }
+    std::cerr << "EKF: map capacity grown from " << _maxFeatures << " to " << newMax << " features" << std::endl;
+    ekfb_destroy(_h);
+    _h = h2;
+    _maxFeatures = newMax;
+    return true;
 }
 
 // Bring the host mirror in line with the device in ONE round trip (ekfb_get_map_snapshot): camera state and every feature's
@@ -240,7 +306,6 @@ int EKF::addNewFeatures(int wanted, bool useDeviceMask)
     const int W = _cfg.params.pixels_x, H = _cfg.params.pixels_y;
     int32_t n = 0, N = 0;
     ekfb_get_dims(_h, 0, &n, &N);
-    if (wanted > _maxFeatures - N) wanted = _maxFeatures - N;
     if (wanted <= 0 || _kps.empty()) return 0;
     _mask.assign((size_t)W * H, 255);
     std::vector<double> pred;
@@ -282,8 +347,10 @@ int EKF::addNewFeatures(int wanted, bool useDeviceMask)
         uv[2 * a + 1] = _kps[idx[a]].y;
         std::memcpy(&dd[(size_t)32 * a], &_desc[(size_t)32 * idx[a]], 32);
     }
-    if (ekfb_add_features(_h, 0, k, uv.data(), dd.data()) != EKFB_OK) {
-        std::cerr << "EKF: " << ekfb_last_error() << std::endl;
+    if (N + k > _maxFeatures && !growCapacity(N + k + std::max(_cfg.policy.min_matches_per_image, 16))) return 0;
+    const int rcAdd = ekfb_add_features(_h, 0, k, uv.data(), dd.data());
+    if (rcAdd != EKFB_OK) {
+        fail(rcAdd, "EKF: ekfb_add_features");
         return 0;
     }
     return k;
@@ -316,13 +383,16 @@ bool EKF::acquireKeypoints(const cv::Mat& image)
 
 void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
 {
+    _lastStatus = EKFB_OK;
     if (!_configOk || (!_frontEnd && !_deviceFrontEnd)) {
         std::cerr << "EKF::init: no configuration or no front end" << std::endl;
+        _lastStatus = EKFB_ERR_ARG;
         return;
     }
-    if (!_h && ekfb_create(&_cfg.params, _device, 1, _maxFeatures, 16384, &_h) != EKFB_OK) {
-        std::cerr << "EKF::init: " << ekfb_last_error() << std::endl;
+    int rc = EKFB_OK;
+    if (!_h && (rc = ekfb_create(&_cfg.params, _device, 1, _maxFeatures, 16384, &_h)) != EKFB_OK) {
         _h = nullptr;
+        fail(rc, "EKF::init");
         return;
     }
     // initState / initCovariance (E/CommonFunctions.cpp:39-80)
@@ -334,13 +404,13 @@ void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
         P[(10 + i) * 13 + 10 + i] = _cfg.params.init_angular_accel_sd * _cfg.params.init_angular_accel_sd;
     }
     state.removeAllFeatures();
-    if (ekfb_set_state(_h, 0, 13, 0, x.data(), nullptr, nullptr, P.data(), nullptr) != EKFB_OK) {
-        std::cerr << "EKF::init: " << ekfb_last_error() << std::endl;
+    if ((rc = ekfb_set_state(_h, 0, 13, 0, x.data(), nullptr, nullptr, P.data(), nullptr)) != EKFB_OK) {
+        fail(rc, "EKF::init");
         return;
     }
     // detectNewImageFeatures(image, noPredictions, MinMatchesPerImage) + addFeaturesToStateAndCovariance, on the device
     if (!acquireKeypoints(image)) {
-        std::cerr << "EKF::init: " << ekfb_last_error() << std::endl;
+        fail(EKFB_ERR_ARG, "EKF::init (front end)");
         return;
     }
     _lastAdded = addNewFeatures(_cfg.policy.min_matches_per_image, false);
@@ -351,55 +421,67 @@ void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
 {
     if (!_h || (!_frontEnd && !_deviceFrontEnd)) {
         std::cerr << "EKF::step: filter not initialised" << std::endl;
+        _lastStatus = EKFB_ERR_ARG;
         return;
     }
-    _ekfSteps++;
-    bool ok = acquireKeypoints(image);
+    _lastStatus = EKFB_OK;
+    if (!acquireKeypoints(image)) {
+        fail(EKFB_ERR_ARG, "EKF::step (front end)");
+        return;
+    }
+    int rc = EKFB_OK;
     float ms[8] = {0};
-    if (ok && _trace.isOpen()) {
+    if (_trace.isOpen()) {
         // phase by phase with device timers, the seven intervals the reference writes (E/EKF.cpp:291 ... 618)
         ekfb_timer_record(_h, 0);
-        ok = ekfb_predict(_h) == EKFB_OK && ekfb_measure(_h) == EKFB_OK;
+        if ((rc = ekfb_predict(_h)) == EKFB_OK) rc = ekfb_measure(_h);
         ekfb_timer_record(_h, 1);
-        ok = ok && ekfb_match(_h) == EKFB_OK;
+        if (rc == EKFB_OK) rc = ekfb_match(_h);
         ekfb_timer_record(_h, 2);
-        ok = ok && ekfb_ransac(_h) == EKFB_OK;
+        if (rc == EKFB_OK) rc = ekfb_ransac(_h);
         ekfb_timer_record(_h, 3);
-        ok = ok && ekfb_update(_h, 0) == EKFB_OK;
+        if (rc == EKFB_OK) rc = ekfb_update(_h, 0);
         ekfb_timer_record(_h, 4);
-        ok = ok && ekfb_rescue(_h) == EKFB_OK;
+        if (rc == EKFB_OK) rc = ekfb_rescue(_h);
         ekfb_timer_record(_h, 5);
-        ok = ok && ekfb_update(_h, 1) == EKFB_OK;
+        if (rc == EKFB_OK) rc = ekfb_update(_h, 1);
         ekfb_timer_record(_h, 6);
-        ok = ok && ekfb_update_map_features(_h) == EKFB_OK;
-    } else if (ok) {
-        ok = ekfb_step(_h) == EKFB_OK;
+        if (rc == EKFB_OK) rc = ekfb_update_map_features(_h);
+    } else {
+        rc = ekfb_step(_h);
     }
-    if (!ok) {
-        std::cerr << "EKF::step: " << ekfb_last_error() << std::endl;
+    if (rc != EKFB_OK) {
+        fail(rc, "EKF::step");
         return;
     }
+    _ekfSteps++;   // a failed frame does not count (the reference has no failure path: E/EKF.cpp:242)
     ekfb_peek_frame_info(_h, 0, &_info);   // the counters ekfb_step synchronised; status is refreshed from the record below
+    if (_setDump) dumpFrameSets();
     // map management (E/EKF.cpp:572-612): bad / unseen features out, one conversion, new features in
     std::memset(&_mapResult, 0, sizeof(_mapResult));
     _mapResult.converted = -1;
     _lastAdded = 0;
-    bool layoutChanged = false;
+    int numericStatus = 0;
     if (_cfg.mapManagementFrequency > 0 && _ekfSteps % _cfg.mapManagementFrequency == 0) {
         _featuresBefore = (int)state.mapFeatures.size();
-        if (ekfb_map_management(_h, &_cfg.policy, &_mapResult) != EKFB_OK) {
-            std::cerr << "EKF::step: " << ekfb_last_error() << std::endl;
+        if ((rc = ekfb_map_management(_h, &_cfg.policy, &_mapResult)) != EKFB_OK) {
+            fail(rc, "EKF::step (map management)");
             return;
         }
-        if (_mapResult.n_removed_bad + _mapResult.n_removed_unseen > 0) layoutChanged = true;
-        if (_mapResult.converted >= 0) layoutChanged = true;
-        if (_mapResult.new_features_needed > 0) {
-            _lastAdded = addNewFeatures(_mapResult.new_features_needed, true);
-            layoutChanged = layoutChanged || _lastAdded > 0;
-        }
+        ekfb_frame_info now;
+        ekfb_peek_frame_info(_h, 0, &now);     // ekfb_map_management synchronised the counters: status covers both updates
+        numericStatus = now.status;
+        if (_mapResult.new_features_needed > 0) _lastAdded = addNewFeatures(_mapResult.new_features_needed, true);
+        if (_lastStatus != EKFB_OK) return;
     }
     if (_trace.isOpen()) ekfb_timer_record(_h, 7);
-    refreshMirror(layoutChanged);
+    refreshMirror(true);
+    if (numericStatus) _info.status = numericStatus;
+    if (_info.status != 0) {
+        _lastStatus = _info.status;
+        std::cerr << "EKF::step: frame " << _ekfSteps << " finished with status " << _info.status
+                  << " (innovation covariance not positive definite: that update was skipped)" << std::endl;
+    }
     if (_trace.isOpen()) {
         for (int i = 0; i < 7; ++i) ekfb_timer_elapsed_ms(_h, i, i + 1, &ms[i]);
         EkfbFrameTrace t;
@@ -437,18 +519,19 @@ extern "C" void* ekfb_host_ekf_create(const char* config, const char* outputPath
     return e;
 }
 extern "C" void ekfb_host_ekf_destroy(void* e) { delete (EKF*)e; }
-// frames: 8-bit, `channels` = 1 (grey), 3 (BGR) or 4 (BGRA), tightly packed rows
+// frames: 8-bit, `channels` = 1 (grey), 3 (BGR) or 4 (BGRA), tightly packed rows.  Both return the ekfb status of the call
+// (EKFB_OK = 0; a failed frame reports the code of the failing device call, EKFB_ERR_NUMERIC a non-positive-definite update)
 extern "C" int ekfb_host_ekf_init(void* e, const unsigned char* frame, int width, int height, int channels)
 {
     cv::Mat img(height, width, channels == 1 ? CV_8UC1 : channels == 3 ? CV_8UC3 : CV_8UC4, const_cast<unsigned char*>(frame));
     ((EKF*)e)->init(img);
-    return ((EKF*)e)->ok() ? 0 : 1;
+    return ((EKF*)e)->handle() ? ((EKF*)e)->lastStatus() : EKFB_ERR_CUDA;
 }
 extern "C" int ekfb_host_ekf_step(void* e, const unsigned char* frame, int width, int height, int channels)
 {
     cv::Mat img(height, width, channels == 1 ? CV_8UC1 : channels == 3 ? CV_8UC3 : CV_8UC4, const_cast<unsigned char*>(frame));
     ((EKF*)e)->step(img);
-    return ((EKF*)e)->ok() ? 0 : 1;
+    return ((EKF*)e)->handle() ? ((EKF*)e)->lastStatus() : EKFB_ERR_CUDA;
 }
 // x13 = r, q, v, omega; counts = {map features, state dimension, matches, inliers, rescued, removed, converted (-1 none), added}
 extern "C" void ekfb_host_ekf_get(void* ep, double* x13, int* counts8)

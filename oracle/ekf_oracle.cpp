@@ -47,6 +47,26 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // minimal row-major double matrix (stands in for cv::Mat_<double>, Core/Base.h:66-67)
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Decision margins: every floating-point threshold decision of the frame records how far it was from
+// flipping.  The sets the decisions produce are compared exactly against the GPU; the margins show how much numerical
+// slack those comparisons had.  Test infrastructure: a process-wide recorder read through orc_margins_get().
+// ---------------------------------------------------------------------------------------------
+enum MarginClass { MG_FOV = 0, MG_FRAME, MG_GATE, MG_RATIO, MG_RANSAC, MG_CHI2, MG_DEADBAND, MG_COUNT };
+struct MarginLog {
+    double minAbs[MG_COUNT];
+    int64_t count[MG_COUNT];
+    int64_t zero[MG_COUNT];   // decisions whose operand was exactly on the threshold / exactly zero
+};
+MarginLog g_margins = {{1e300, 1e300, 1e300, 1e300, 1e300, 1e300, 1e300}, {0}, {0}};
+inline void markMargin(int cls, double margin)
+{
+    g_margins.count[cls]++;
+    const double a = fabs(margin);
+    if (a == 0.0) g_margins.zero[cls]++;
+    else if (a < g_margins.minAbs[cls]) g_margins.minAbs[cls] = a;
+}
+
 struct Mat {
     int r = 0, c = 0;
     std::vector<double> d;
@@ -549,6 +569,7 @@ bool pointIsInsideEllipse(float px, float py, float cx, float cy, int aw, int ah
     }
     double a1x = px - f1x, a1y = py - f1y, a2x = px - f2x, a2y = py - f2y;
     double norm_sum = sqrt(a1x * a1x + a1y * a1y) + sqrt(a2x * a2x + a2y * a2y);
+    markMargin(MG_GATE, norm_sum - 2 * majorAxis);
     return norm_sum <= 2 * majorAxis;
 }
 
@@ -857,12 +878,14 @@ bool isInFrontOfCamera(const orc_params& c, const double* f)  // :162-171
 {
     double atanxz = RAD_TO_DEG(atan2(f[0], f[2]));
     double atanyz = RAD_TO_DEG(atan2(f[1], f[2]));
+    markMargin(MG_FOV, std::min(c.angular_vision_x - fabs(atanxz), c.angular_vision_y - fabs(atanyz)));
     return -c.angular_vision_x < atanxz && atanxz < c.angular_vision_x && -c.angular_vision_y < atanyz &&
            atanyz < c.angular_vision_y;
 }
 
 bool isVisibleInImageFrame(const orc_params& c, const double* p)  // :176-181
 {
+    markMargin(MG_FRAME, std::min(std::min(p[0], c.pixels_x - p[0]), std::min(p[1], c.pixels_y - p[1])));
     return (p[0] > 0 && p[0] < c.pixels_x && p[1] > 0 && p[1] < c.pixels_y);
 }
 
@@ -1217,6 +1240,7 @@ void matchPredictedFeatures(orc_filter* f, const float* kpxy, const uint8_t* kpd
         // matchICDescriptors :148-177
         std::list<DMatch> best;
         findBestNMatches(2, feat.desc, desc.data(), nk, m.data(), best);
+        if (best.size() >= 2) markMargin(MG_RATIO, (double)best.front().distance - (double)best.back().distance * c.matching_coef);
         if (best.size() == 1 ||
             (best.size() >= 2 && best.front().distance <= best.back().distance * c.matching_coef)) {
             const DMatch& bm = best.front();
@@ -1256,9 +1280,12 @@ void stateUpdate(const Mat& K, const std::vector<const Match*>& ms, const std::v
         double dy = ms[i]->z[1] - ps[i]->h[1];
         nu(2 * i, 0) = fabs(dx) > DELTA ? dx : 0.0L;
         nu(2 * i + 1, 0) = fabs(dy) > DELTA ? dy : 0.0L;
+        markMargin(MG_DEADBAND, dx == 0.0 ? 0.0 : fabs(dx) - DELTA);
+        markMargin(MG_DEADBAND, dy == 0.0 ? 0.0 : fabs(dy) - DELTA);
     }
     Mat kd = mul(K, nu);
     const double* v = kd.d.data();
+    for (int i = 0; i < kd.r; ++i) markMargin(MG_DEADBAND, v[i] == 0.0 ? 0.0 : fabs(v[i]) - DELTA);
     for (int i = 0; i < 3; ++i)
         if (fabs(v[i]) > DELTA) s.position[i] += v[i];
     for (int i = 0; i < 4; ++i)
@@ -1346,6 +1373,7 @@ void matchesBelowAThreshold(const std::vector<Match>& matches, const std::vector
                 double xd = m.z[0] - p.h[0];
                 double yd = m.z[1] - p.h[1];
                 double dist = sqrt(xd * xd + yd * yd);
+                markMargin(MG_RANSAC, dist - thr);
                 if (dist < thr) support.push_back((int)mi);
                 found = true;
             }
@@ -1454,6 +1482,7 @@ void rescue(orc_filter* f)  // EKF.cpp:448-506 + rescueOutliers :68-119
         double t0 = d0 * Si[0] + d1 * Si[2];
         double t1 = d0 * Si[1] + d1 * Si[3];
         double chi = t0 * d0 + t1 * d1;
+        markMargin(MG_CHI2, chi - f->p.ransac_chi2);
         if (chi < f->p.ransac_chi2) {
             f->rescuedIdx.push_back(f->outlierMatchesKept[i]);
             f->rescuedPred.push_back((int)i);
@@ -2012,6 +2041,18 @@ void orc_get_mask(const orc_filter* f, uint8_t* mask, uint8_t* kpok)
 {
     if (mask && !f->mask.empty()) std::memcpy(mask, f->mask.data(), f->mask.size());
     if (kpok && !f->kpOk.empty()) std::memcpy(kpok, f->kpOk.data(), f->kpOk.size());
+}
+
+// decision margins since the last reset: 7 classes (field of view [deg], in-frame [px], foci gate [px], 2-best ratio
+// [Hamming], RANSAC support distance [px], rescue chi-square, dead-band [state units]): smallest non-zero |margin|, number of
+// decisions, number of decisions with an operand exactly on the threshold (dead-band: exactly zero)
+void orc_margins_reset()
+{
+    for (int i = 0; i < MG_COUNT; ++i) { g_margins.minAbs[i] = 1e300; g_margins.count[i] = 0; g_margins.zero[i] = 0; }
+}
+void orc_margins_get(double* minAbs, int64_t* count, int64_t* zero)
+{
+    for (int i = 0; i < MG_COUNT; ++i) { minAbs[i] = g_margins.minAbs[i]; count[i] = g_margins.count[i]; zero[i] = g_margins.zero[i]; }
 }
 
 void orc_eigen2x2(const double* A, double* ev, double* V) { eigen2x2(A, ev, V); }

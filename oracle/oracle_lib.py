@@ -191,6 +191,22 @@ class OracleFilter:
         return mask, ok[:self.n_kp]
 
 
+# ---- decision margins ----
+MARGIN_CLASSES = ("field_of_view_deg", "in_frame_px", "foci_gate_px", "ratio_test_hamming", "ransac_distance_px",
+                  "rescue_chi2", "dead_band")
+
+
+def margins_reset():
+    lib().orc_margins_reset()
+
+
+def margins():
+    """{class: (smallest non-zero |margin| since the reset, number of decisions, decisions exactly on the threshold)}"""
+    m = np.zeros(7); c = np.zeros(7, np.int64); z = np.zeros(7, np.int64)
+    lib().orc_margins_get(_p(m), _p(c), _p(z))
+    return {k: (float(m[i]) if c[i] > z[i] else None, int(c[i]), int(z[i])) for i, k in enumerate(MARGIN_CLASSES)}
+
+
 # ---- OpenCV-primitive restatements (pinned against cv2 fixtures) ----
 def eigen2x2(A):
     A = np.ascontiguousarray(A, dtype=np.float64)

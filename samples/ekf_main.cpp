@@ -5,6 +5,7 @@
 // i.e. the front-end output stored on disk -- the same seam as the reference's HandMatching.cpp.  Frame 0 initialises
 // the filter (EKF::init), every further frame is one EKF::step; the 13-state is printed per frame.
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <vector>
@@ -53,6 +54,7 @@ int main(int argc, const char* argv[])
     }
     EKF extendedKalmanFilter(argv[1], argc > 3 ? argv[3] : "");
     extendedKalmanFilter.setFrontEnd(&frames);
+    if (const char* dump = std::getenv("EKFB_DUMP_SETS")) extendedKalmanFilter.dumpFrameSetsTo(dump);   // parity tests
     cv::Mat image;  // frames carry no pixels here; the filter only needs the front-end output
     if (!frames.next()) {
         std::cout << "No se puede iniciar Kalman Filter dado que no hay imagenes disponibles." << std::endl;
@@ -63,6 +65,10 @@ int main(int argc, const char* argv[])
     int stepCount = 0;
     while (frames.next()) {
         extendedKalmanFilter.step(image);
+        if (extendedKalmanFilter.lastStatus() != 0) {
+            std::cerr << "frame " << stepCount + 1 << ": status " << extendedKalmanFilter.lastStatus() << std::endl;
+            if (!extendedKalmanFilter.handle() || extendedKalmanFilter.lastStatus() != EKFB_ERR_NUMERIC) return 1;
+        }
         const State& s = extendedKalmanFilter.state;
         const ekfb_frame_info& fi = extendedKalmanFilter.lastFrameInfo();
         int32_t nNow = 0, NNow = 0;   // state dimension after this frame's map management

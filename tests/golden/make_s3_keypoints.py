@@ -18,7 +18,7 @@ from openekfmonoslam_b200.params import load_config  # noqa: E402
 
 SEQ = "/root/reference/experiments/s3/costado_recto1"
 CFG = "/root/reference/experiments/s3/config.yml"
-FIRST, COUNT, NFEAT = 90, 121, 300
+FIRST, COUNT, NFEAT = 90, 631, 300
 
 
 def main():

@@ -312,3 +312,43 @@ def test_full_size_properties_c3():
         assert abs(np.linalg.norm(xg[3:7]) - 1.0) < 1e-12
         assert np.trace(Pg) <= np.trace(Pprior) * (1 + 1e-12)
         assert np.linalg.eigvalsh(Pg[:13, :13]).min() > -1e-15
+
+
+def test_decision_margins_of_a_sequence():
+    """every floating-point threshold decision of the oracle (field of view, in-frame, foci gate, 2-best ratio,
+    RANSAC support distance, rescue chi-square, dead-bands) logs its margin.  The GPU must reproduce every decision -- the
+    sets those decisions produce are compared exactly, frame by frame -- and the smallest margin of the sequence must be far
+    above the GPU-vs-CPU arithmetic difference (~1e-12 in a predicted pixel), i.e. no decision was decided by rounding.
+    (Frame 1 is left out of the margin statistics: the map was initialised ON the integer keypoint positions of frame 0 and the
+    camera has not moved, so its predicted pixels are integers +- 1 ulp and keypoints that moved by exactly one pixel sit at
+    |distance - 1.0| ~ 1e-14 from the RANSAC threshold -- a degenerate tie of the synthetic scenario, which the cold-frame
+    parity tests show both sides resolve identically.)"""
+    from oracle import oracle_lib
+    sc, orc, gpu = make_pair(640, 480, 100, warm=1)
+    oracle_lib.margins_reset()
+    worst = 0.0
+    for t in range(2, 32):
+        kp, ds = sc.frame(t)
+        orc.step(kp, ds)
+        gpu.set_keypoints(0, kp, ds); gpu.step()
+        r, mo = gpu.feature_results(0), orc.get_measure()
+        assert np.array_equal(mo["vis"], r["vis"])                                            # field of view + in-frame
+        v = mo["vis"].astype(bool)
+        worst = max(worst, float(np.abs(r["h"][v] - mo["h"][v]).max()))
+        ma, ro = orc.get_match(), orc.get_ransac()
+        assert np.array_equal(ma["matched"], r["matched"])                                    # foci gate + ratio test
+        mm = ma["matched"].astype(bool)
+        assert np.array_equal(ma["kp"][mm], r["kp"][mm])
+        assert np.array_equal(ro["inlier"], r["inlier"]) and np.array_equal(ro["outlier"], r["outlier"])   # RANSAC distance
+        assert np.array_equal(orc.get_rescue(), r["rescued"])                                 # chi-square gate
+        compare_state(orc, gpu, f"frame {t}")                                                 # dead-bands (state)
+    mg = oracle_lib.margins()
+    print("decision margins over 30 frames (smallest non-zero |margin|, decisions, exactly on threshold):")
+    for k, (m, c, z) in mg.items():
+        print(f"  {k:22s} {m if m is None else format(m, '.3e')}  n={c}  on-threshold={z}")
+    print(f"  largest GPU-vs-oracle difference of a predicted pixel: {worst:.2e}")
+    for k in ("field_of_view_deg", "in_frame_px", "foci_gate_px", "ransac_distance_px", "rescue_chi2"):
+        m, c, z = mg[k]
+        assert c > 0 and z == 0 and m > 1e4 * max(worst, 1e-13), (k, mg[k], worst)
+    # the ratio test compares integer Hamming distances (exact on both sides); dead-bands: a value exactly 0 stays 0
+    assert mg["ratio_test_hamming"][1] > 0 and mg["dead_band"][1] > 0
