@@ -60,8 +60,9 @@ typedef struct ekfb_frame_info {
     int32_t n_inliers;    /* liInliers                                  */
     int32_t n_outliers;
     int32_t n_rescued;    /* hiInliers                                  */
-    int32_t status;       /* 0, or EKFB_ERR_NUMERIC if a Cholesky pivot was not positive */
-    int32_t reserved;
+    int32_t status;       /* THIS frame: 0, or EKFB_ERR_NUMERIC if an innovation covariance was not positive definite (that update
+                             and the rest of the frame's updates were skipped: x and P are left as they were) */
+    int32_t reserved;     /* OR of `status` over all frames since ekfb_set_state (0 = no frame ever failed) */
 } ekfb_frame_info;
 
 /* fixed-size per-filter result record (what callers read back: main.cpp:91,137,141 read
@@ -101,6 +102,10 @@ int ekfb_get_dims(ekfb_handle h, int filter, int32_t* n, int32_t* n_features);
 int ekfb_set_keypoints(ekfb_handle h, int filter, const float* xy, const uint8_t* desc, int n_kp);
 /* the same for all filters of the handle in one call (xy[f], desc[f], n_kp[f] per filter): one pointer-table / count update */
 int ekfb_set_keypoints_batch(ekfb_handle h, const float* const* xy, const uint8_t* const* desc, const int32_t* n_kp);
+/* all filters from ONE packed host buffer pair: filter f's keypoints are entries kp_offset[f] .. kp_offset[f+1]-1 of xy / desc
+ * (n_filters + 1 offsets).  Two host->device copies per call whatever the number of filters (pinned buffers make them
+ * asynchronous); the batch form above issues two per filter. */
+int ekfb_set_keypoints_packed(ekfb_handle h, const float* xy, const uint8_t* desc, const int32_t* kp_offset);
 /* device-resident sequences: upload all frames once, then select a frame with no host traffic.
  * kp_offset has n_frames+1 entries (prefix sums of per-frame keypoint counts). */
 int ekfb_load_sequence(ekfb_handle h, int filter, int n_frames, const int32_t* kp_offset, const float* xy,
@@ -237,12 +242,14 @@ int64_t ekfb_kernel_launches(ekfb_handle h);     /* kernels launched by this han
 /* tuning / test switches.  EKFB_OPT_FORCE_GENERIC_FACTOR = 1 forces the right-looking factorisation over
  * the whole augmented matrix (the path used when k is too large for the shared-memory slab TRSM). */
 enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* 0: 128x128 tiles (default), 1: 128x64 tiles, 2 CTAs/SM */,
-       EKFB_OPT_SCHAIN_VARIANT = 3 /* factorisation of S: 0 = one fused launch per 64-row step (default), 1 = panel + trail launches */,
+       EKFB_OPT_SCHAIN_VARIANT = 3 /* factorisation of S: 0 = one fused launch per 64-row step, 1 = panel + trail launches,
+                                      3 = the whole chain in one launch (tile dataflow, ekf_chain.cuh) */,
        EKFB_OPT_DOWNDATE_SMALL_K = 4 /* updates with at most this many rows run the downdate as 64x64 tiles, 4 CTAs/SM (default: all); above it 128x128 tiles */,
        EKFB_OPT_TRSM_STAGES = 5 /* upper limit of the slab TRSM's operand-ring depth: 2, 3 or 4 (default 4, as shared memory allows) */,
        EKFB_OPT_TRSM_PAIR = 6 /* batched filters: 1 (default) = slab footprint that lets two CTAs share an SM when possible */,
        EKFB_OPT_RANSAC_CHUNK = 7 /* RANSAC hypotheses evaluated per round (0 = default: 16 single filter, 4 batched) */,
-       EKFB_OPT_PDL = 8 /* 1 (default): the frame's kernels are launched with programmatic stream serialisation */ };
+       EKFB_OPT_PDL = 8 /* 1 (default): the frame's kernels are launched with programmatic stream serialisation */,
+       EKFB_OPT_FAULT_INJECT = 9 /* test hook: 1 = the next factorisations report a non-positive pivot (EKFB_ERR_NUMERIC path) */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

@@ -133,6 +133,11 @@ class EkfBatch:
         a = (ctypes.c_void_p * F)(*xy_ptrs); b = (ctypes.c_void_p * F)(*desc_ptrs); n = (ctypes.c_int32 * F)(*counts)
         self._ck(self.L.ekfb_set_keypoints_batch(self.h, a, b, n))
 
+    def set_keypoints_packed_raw(self, xy_ptr, desc_ptr, offsets):
+        """all filters from one packed (pinned) host buffer pair; offsets: int32 numpy array of n_filters + 1 entries"""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        self._ck(self.L.ekfb_set_keypoints_packed(self.h, ctypes.c_void_p(xy_ptr), ctypes.c_void_p(desc_ptr), _ptr(offsets)))
+
     def load_sequence(self, f, frames):
         """frames: list of (xy, desc) per frame; uploads them all to device memory."""
         off = np.zeros(len(frames) + 1, np.int32)

@@ -13,6 +13,7 @@
 
 #include "ekf_linalg.cuh"
 #include "ekf_schain.cuh"
+#include "ekf_chain.cuh"
 #include "ekf_map.cuh"
 #include "ekf_ncc.cuh"
 #include "ekf_frontend.cuh"
@@ -94,7 +95,10 @@ struct ekfb_ctx {
     int trsm_pair = 1;        // batched filters: slab footprint that fits two CTAs per SM when possible (option 6)
     int ransac_chunk = 0;     // hypotheses evaluated per round; 0 = 16 for a single filter, 4 for batches (option 7)
     int trsm_stages = 4;      // upper limit of the slab TRSM's operand ring depth (option 5)
-    int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches
+    int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches,
+                              // 3 = the whole chain in one launch (ekf_chain.cuh)
+    int* chainCtl = nullptr;  // per-filter control blocks of the one-launch chain (generation, queue, flags)
+    int nbMax = 0;
     bool dd_timing = false;
     std::vector<cudaEvent_t> dd_ev;   // pairs
     size_t dd_used = 0;               // events used
@@ -254,6 +258,8 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     ALLOC(c->d_kpxy, F * c->Kpmax * 2); ALLOC(c->d_kpdesc, F * c->Kpmax * 32);
     ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F); ALLOC(c->d_kpcount, F);
     ALLOC(c->d_rec, F);
+    c->nbMax = c->kmax / kNB + 1;
+    ALLOC(c->chainCtl, F * (size_t)chain_ctl_ints(c->nbMax));
     v.kpxy = c->d_kpxy_ptr;
     v.kpdesc = c->d_kpdesc_ptr;
     CK(cudaMallocHost(&c->h_dims, F * D_STRIDE * sizeof(int)));
@@ -292,6 +298,7 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     CK(cudaFuncSetAttribute(k_schain_trail, cudaFuncAttributeMaxDynamicSharedMemorySize, kSTrailSmem));
     CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
     CK(cudaFuncSetAttribute(k_schain_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem));
+    CK(cudaFuncSetAttribute(k_schain_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -480,6 +487,32 @@ extern "C" int ekfb_set_keypoints_batch(ekfb_handle c, const float* const* xy, c
         c->hKp[f] = n_kp[f];
         c->h_kpxy_ptr[f] = dxy;
         c->h_kpdesc_ptr[f] = dds;
+    }
+    return push_kp_meta(c);
+}
+
+extern "C" int ekfb_set_keypoints_packed(ekfb_handle c, const float* xy, const uint8_t* desc, const int32_t* kp_offset)
+{
+    REQUIRE(c && kp_offset, "null argument");
+    CK(cudaSetDevice(c->device));
+    const int total = kp_offset[c->F];
+    REQUIRE(kp_offset[0] == 0 && (total == 0 || (xy && desc)), "bad offsets or null keypoint buffer");
+    for (int f = 0; f < c->F; ++f) {
+        const int n = kp_offset[f + 1] - kp_offset[f];
+        if (n < 0 || n > c->Kpmax) {
+            g_err = "keypoint count exceeds the capacity reserved by ekfb_create";
+            return EKFB_ERR_CAPACITY;
+        }
+    }
+    // the staging area holds F * Kpmax keypoints, so the packed frame always fits; filter f reads it at its offset
+    if (total > 0) {
+        CK(cudaMemcpyAsync(c->d_kpxy, xy, sizeof(float) * 2 * (size_t)total, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_kpdesc, desc, (size_t)32 * total, cudaMemcpyHostToDevice, c->stream));
+    }
+    for (int f = 0; f < c->F; ++f) {
+        c->hKp[f] = kp_offset[f + 1] - kp_offset[f];
+        c->h_kpxy_ptr[f] = c->d_kpxy + (size_t)kp_offset[f] * 2;
+        c->h_kpdesc_ptr[f] = c->d_kpdesc + (size_t)kp_offset[f] * 32;
     }
     return push_kp_meta(c);
 }
@@ -712,6 +745,14 @@ static int launch_schain(ekfb_ctx* c, int k)
             }
         }
         CK(cudaMemcpyAsync(v.Sf, v.S, sizeof(double) * (size_t)c->F * c->kmax * c->ldS, cudaMemcpyDeviceToDevice, c->stream));
+    } else if (c->schain_variant == 3) {
+        // the whole chain in one launch: G CTAs per filter (one critical CTA + queue workers).  Grid sized from the handle's
+        // capacity, not from this frame's k: surplus CTAs find the queue empty and exit.
+        const int nbR = c->kmax / kNB, nbC = nbR + 1;
+        const int tasks = nbR * (nbC - 1) - nbR * (nbR - 1) / 2 + std::max(nbR - 2, 0);
+        const int G = (c->F == 1) ? std::min(c->smCount, tasks + 1) : std::max(1, std::min(tasks + 1, c->smCount / c->F));
+        CK(launch_pdl(k_schain_fused, dim3(G, c->F), dim3(256), (size_t)kChainSmem, c->stream, v, c->chainCtl, c->nbMax));
+        count_launch(c);
     } else {
         // one launch per block step; step J needs a launch while a tile row J+1 (or the lone nu column tile) exists
         const int nbR = steps, nbC = (k + kNB) / kNB;
@@ -766,6 +807,10 @@ static int run_update(ekfb_ctx* c, int which)
             else
                 CK(launch_pdl(k_trsm_slab<16, 2>, dim3(cdiv(n, 16), c->F), dim3(256), smem16, c->stream, v));
             count_launch(c);
+            if (c->schain_variant == 3) {   // next generation of the chain's flags (after everything that follows the chain)
+                k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
+                count_launch(c);
+            }
         } else {
             // generic path (very large k): right-looking over the whole augmented matrix
             for (int J = 0; J < steps; ++J) {
@@ -1273,7 +1318,7 @@ static void fill_info(const int* d, ekfb_frame_info* o)
     o->n = d[D_N_STATE]; o->n_features = d[D_N_FEAT]; o->n_keypoints = d[D_N_KP]; o->n_predicted = d[D_N_PRED];
     o->n_matches = d[D_N_MATCH]; o->n_hypotheses = d[D_N_HYP]; o->best_hypothesis = d[D_BEST_HYP];
     o->n_inliers = d[D_N_INL]; o->n_outliers = d[D_N_OUT]; o->n_rescued = d[D_N_RESC]; o->status = d[D_STATUS];
-    o->reserved = 0;
+    o->reserved = d[D_STATUS_EVER] | d[D_STATUS];   /* any non-zero status since ekfb_set_state */
 }
 
 extern "C" int ekfb_get_frame_info(ekfb_handle c, int f, ekfb_frame_info* info)
@@ -1409,6 +1454,7 @@ extern "C" int ekfb_test_factor(ekfb_handle c, int k, const double* S_in, double
     CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
     int rc = launch_schain(c, k);
     if (rc != EKFB_OK) return rc;
+    if (c->schain_variant == 3) k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(U_out, sizeof(double) * (k + 1), v.Sf, sizeof(double) * c->ldS, sizeof(double) * (k + 1), k,
                          cudaMemcpyDeviceToHost, c->stream));
@@ -1494,7 +1540,8 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_PDL, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_FAULT_INJECT, "unknown option");
+    if (option == EKFB_OPT_FAULT_INJECT) { c->v.faultInject = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
     if (option == EKFB_OPT_TRSM_STAGES) { c->trsm_stages = value; return EKFB_OK; }
     if (option == EKFB_OPT_TRSM_PAIR) { c->trsm_pair = value; return EKFB_OK; }

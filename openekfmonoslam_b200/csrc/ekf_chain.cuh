@@ -1,0 +1,418 @@
+// ekf_chain.cuh -- the S-chain as ONE launch: blocked Cholesky  S = U^T U  of the innovation covariance [S | nu]
+// (k x (k+1)) with the inverses of the 64x64 diagonal blocks, for the slab TRSM (reference: E/Update.cpp:105-108 inverts S by
+// LU; here neither the inverse nor K is ever formed).  Replaces the per-block-step launches of ekf_schain.cuh (12 launches of
+// ~17 us each at the C3 size, 27 % of the frame at 1.2 % of the FP64 peak): the steps were bound by launch + reload latency,
+// not by work, so the whole factorisation now runs as a dataflow of 64x64 tile tasks inside one resident grid that
+// hand tiles to each other through global memory (L2) and acquire / release flags.  k comes from device memory; the grid is
+// sized for the largest k of the handle and surplus CTAs exit at once (nothing here is sized on the host per frame).
+//
+// Tile (I, C), I <= C, of the upper triangle of [S | nu]; X(I, C) = U(I, C) is a final factor tile (in the factor buffer Sf).
+//   D(I)      critical chain, one CTA per filter:   X(I-1, I) = Uinv_{I-1}^T T(I-1, I)   (Uinv_{I-1} is still in its shared memory)
+//                                                   T(I, I)   = T'(I, I) - X(I-1, I)^T X(I-1, I);  factor -> U_II, Uinv_I
+//   A(I, C)   off-diagonal tile, left-looking:      T(I, C)   = S(I, C) - sum_{r < I} X(r, I)^T X(r, C)   as the rows arrive;
+//             C == I+1: T handed to D(I+1);  else   X(I, C)   = Uinv_I^T T(I, C)
+//   PD(C)     partial diagonal:                     T'(C, C)  = S(C, C) - sum_{r <= C-2} X(r, C)^T X(r, C)
+// Per step the critical CTA does two 64^3 products and one 64x64 factorisation on tiles that are ready before it needs them;
+// everything else runs beside it on other SMs.  Tasks are taken from a per-filter queue in row-major order (atomic counter),
+// so a task only ever waits for tasks taken earlier by CTAs that are already running: no co-residency assumption, no
+// dependence on block dispatch order.  All products on the FP64 tensor pipe (DMMA m8n8k4).
+#pragma once
+
+#include "ekf_schain.cuh"
+
+namespace ekf {
+
+// per-filter control block in global memory (ints): generation, ticket and queue counters, then the flags.  A flag is "set" when
+// it holds the current generation, so nothing is cleared between launches; k_chain_finish advances the generation.
+constexpr int CH_GEN = 0, CH_TICKET = 1, CH_QUEUE = 2, CH_FLAGS = 4;
+__host__ __device__ inline int chain_ctl_ints(int nbMax) { return CH_FLAGS + 3 * (nbMax + 1) + (nbMax + 1) * (nbMax + 1); }
+
+struct ChainCtl {
+    int* base;
+    int nbMax;
+    __device__ __forceinline__ int* fdone(int I) const { return base + CH_FLAGS + I; }                     // U_II, Uinv_I published
+    __device__ __forceinline__ int* tready(int I) const { return base + CH_FLAGS + (nbMax + 1) + I; }      // T(I, I+1) in S
+    __device__ __forceinline__ int* pdready(int C) const { return base + CH_FLAGS + 2 * (nbMax + 1) + C; } // T'(C, C) in S
+    __device__ __forceinline__ int* xready(int I, int C) const { return base + CH_FLAGS + 3 * (nbMax + 1) + I * (nbMax + 1) + C; }
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+constexpr int kChainTimeoutStatus = 5;   // EKFB_ERR_INTERNAL: a flag did not arrive within ~1 s (never observed; bounds a hang)
+
+// all threads: wait until *flag == gen (thread 0 polls).  Returns with the data published before the flag visible to the CTA.
+__device__ __forceinline__ void chain_wait(const int* flag, int gen, int* status)
+{
+    if (threadIdx.x == 0) {
+        if (ld_acquire(flag) != gen) {
+            const long long t0 = clock64();
+            while (ld_acquire(flag) != gen) {
+                if (clock64() - t0 > (1ll << 31)) { atomicExch(status, kChainTimeoutStatus); break; }
+            }
+        }
+    }
+    __syncthreads();
+}
+// all threads: the CTA's global stores so far become visible, then the flag is raised
+__device__ __forceinline__ void chain_signal(int* flag, int gen)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(flag, gen);
+}
+
+constexpr int kChainSmem = (4 * kNB * kSS + 2 * kNB) * (int)sizeof(double);
+
+struct ChainCtx {
+    double *Ws, *As, *Bs, *Ts, *nu;     // shared-memory tiles (pitch kSS)
+    double *Sg, *Sf, *UinvG;            // this filter's S, factor buffer, diagonal-block inverses
+    ChainCtl ctl;
+    int* dm;
+    int k, nbR, nbC, ldS, gen, faultInject;
+    int wsBlock;                         // which Uinv block Ws holds (-1: none)
+};
+
+// acc += A^T B for two K-major 64x64 tiles in shared memory; warp (p, nh) owns rows 16p.., columns 32nh..
+__device__ __forceinline__ void tile_mma_full(const double* As, const double* Bs, int p, int nh, int g, int q, double (&acc)[2][4][2])
+{
+    const int m0 = 16 * p, n0 = 32 * nh;
+#pragma unroll 2
+    for (int k4 = 0; k4 < kNB; k4 += 4) {
+        double af[2], bf[4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) af[a] = As[(k4 + q) * kSS + m0 + 8 * a + g];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = Bs[(k4 + q) * kSS + n0 + 8 * b + g];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+}
+
+// acc += A^T A restricted to the 36 upper 8x8 tiles; warp w owns tiles w, w+8, ..., (five for w < 4)
+__device__ __forceinline__ void tile_mma_upper(const double* As, int w, int g, int q, double (&acc)[5][2])
+{
+    int mi[5], ni[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+        const int id = min(w + 8 * t, 35);
+        mi[t] = 8 * kUpperTile[id][0]; ni[t] = 8 * kUpperTile[id][1];
+    }
+    const bool five = (w + 32 < 36);
+#pragma unroll 2
+    for (int k4 = 0; k4 < kNB; k4 += 4) {
+        const double* Ar = As + (k4 + q) * kSS + g;
+        double af[5], bf[5];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) { af[t] = Ar[mi[t]]; bf[t] = Ar[ni[t]]; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dmma8x8x4(acc[t][0], acc[t][1], af[t], bf[t]);
+        if (five) dmma8x8x4(acc[4][0], acc[4][1], af[4], bf[4]);
+    }
+}
+
+// Ts(upper 8x8 tiles) -= acc
+__device__ __forceinline__ void tile_sub_upper(double* Ts, int w, int g, int q, const double (&acc)[5][2])
+{
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+        if (t == 4 && !(w + 32 < 36)) break;
+        const int id = min(w + 8 * t, 35);
+        const int m = 8 * kUpperTile[id][0] + g, nn = 8 * kUpperTile[id][1] + 2 * q;
+        double2 tv = *reinterpret_cast<double2*>(Ts + m * kSS + nn);
+        tv.x -= acc[t][0]; tv.y -= acc[t][1];
+        *reinterpret_cast<double2*>(Ts + m * kSS + nn) = tv;
+    }
+}
+
+// the 64x64 tile in shared memory -> rows row0.. / columns col0.. of a global matrix, clipped to rows < rowLimit, cols <= k
+__device__ __forceinline__ void store_tile64(const double* src, double* dst, int ld, int row0, int rowLimit, int col0, int k, int tid)
+{
+    for (int e = tid; e < kNB * 32; e += 256) {
+        const int r = e >> 5, c2 = (e & 31) * 2;
+        if (row0 + r >= rowLimit) continue;
+        double* d = dst + (size_t)(row0 + r) * ld + col0 + c2;
+        const double2 t = *reinterpret_cast<const double2*>(src + r * kSS + c2);
+        if (col0 + c2 + 1 <= k) *reinterpret_cast<double2*>(d) = t;
+        else if (col0 + c2 <= k) d[0] = t.x;
+    }
+}
+
+__device__ __forceinline__ void load_uinv(ChainCtx& cx, int I, int tid)
+{
+#pragma unroll 4
+    for (int e = tid; e < kNB * 32; e += 256) {
+        const int r = e >> 5, c2 = (e & 31) * 2;
+        cp_async16(cx.Ws + r * kSS + c2, cx.UinvG + (size_t)I * kNB * kNB + r * kNB + c2);
+    }
+    cx.wsBlock = I;
+}
+
+// X (registers, x_gemm layout) -> Sf rows row0.., columns C0.. and optionally into a shared-memory tile
+__device__ __forceinline__ void store_x(const ChainCtx& cx, const double (&x)[2][4][2], int row0, int C0, double* smemTile, int p, int nh, int g,
+                                        int q)
+{
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int m = (a == 0 ? 8 * p : 8 * (7 - p)) + g, nn = 32 * nh + 8 * b + 2 * q;
+            if (smemTile) *reinterpret_cast<double2*>(smemTile + m * kSS + nn) = make_double2(x[a][b][0], x[a][b][1]);
+            double* dst = cx.Sf + (size_t)(row0 + m) * cx.ldS + C0 + nn;
+            if (C0 + nn + 1 <= cx.k) *reinterpret_cast<double2*>(dst) = make_double2(x[a][b][0], x[a][b][1]);
+            else if (C0 + nn <= cx.k) dst[0] = x[a][b][0];
+        }
+}
+
+// ---- A(I, C): off-diagonal tile -------------------------------------------------------------------------------------
+__device__ void chain_task_offdiag(ChainCtx& cx, int I, int C)
+{
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, q = lane & 3, p = w & 3, nh = w >> 2;
+    const int I0 = I * kNB, C0 = C * kNB, k = cx.k;
+    load_tile64(cx.Ts, cx.Sg, cx.ldS, I0, k, C0, k + 1, tid);
+    cp_async_commit();
+    double acc[2][4][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int r = 0; r < I; ++r) {
+        chain_wait(cx.ctl.xready(r, I), cx.gen, cx.dm + D_STATUS);
+        chain_wait(cx.ctl.xready(r, C), cx.gen, cx.dm + D_STATUS);
+        load_tile64(cx.As, cx.Sf, cx.ldS, r * kNB, k, I0, k + 1, tid);
+        load_tile64(cx.Bs, cx.Sf, cx.ldS, r * kNB, k, C0, k + 1, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        tile_mma_full(cx.As, cx.Bs, p, nh, g, q, acc);
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // T = S(I, C) - acc, in place in Ts
+    {
+        const int m0 = 16 * p, n0 = 32 * nh;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int m = m0 + 8 * a + g, nn = n0 + 8 * b + 2 * q;
+                double2 t = *reinterpret_cast<double2*>(cx.Ts + m * kSS + nn);
+                t.x -= acc[a][b][0]; t.y -= acc[a][b][1];
+                *reinterpret_cast<double2*>(cx.Ts + m * kSS + nn) = t;
+            }
+    }
+    __syncthreads();
+    if (C == I + 1 && C < cx.nbR) {   // handed to the critical chain: D(C) multiplies by Uinv_I^T itself
+        store_tile64(cx.Ts, cx.Sg, cx.ldS, I0, k, C0, k, tid);
+        chain_signal(cx.ctl.tready(I), cx.gen);
+        return;
+    }
+    chain_wait(cx.ctl.fdone(I), cx.gen, cx.dm + D_STATUS);
+    if (cx.wsBlock != I) {
+        load_uinv(cx, I, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+    double x[2][4][2], xd[2][4][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) x[a][b][0] = x[a][b][1] = 0.0;
+    x_gemm<false>(cx.Ws, cx.Ts, cx.Ts, p, nh, g, q, x, xd);
+    store_x(cx, x, I0, C0, nullptr, p, nh, g, q);
+    chain_signal(cx.ctl.xready(I, C), cx.gen);
+}
+
+// ---- PD(C): diagonal tile minus the contributions of block rows 0 .. C-2 -----------------------------------------------
+__device__ void chain_task_partial_diag(ChainCtx& cx, int C)
+{
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int C0 = C * kNB, k = cx.k;
+    load_tile64(cx.Ts, cx.Sg, cx.ldS, C0, k, C0, k + 1, tid);
+    cp_async_commit();
+    double acc[5][2];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int r = 0; r + 2 <= C; ++r) {
+        chain_wait(cx.ctl.xready(r, C), cx.gen, cx.dm + D_STATUS);
+        load_tile64(cx.As, cx.Sf, cx.ldS, r * kNB, k, C0, k + 1, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        tile_mma_upper(cx.As, w, g, q, acc);
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    tile_sub_upper(cx.Ts, w, g, q, acc);
+    __syncthreads();
+    store_tile64(cx.Ts, cx.Sg, cx.ldS, C0, k, C0, k, tid);   // (entries below the diagonal are never read by anyone)
+    chain_signal(cx.ctl.pdready(C), cx.gen);
+}
+
+// ---- D(I): the critical chain ---------------------------------------------------------------------------------------
+__device__ void chain_task_diag(ChainCtx& cx, int I, int* bad)
+{
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, q = lane & 3, p = w & 3, nh = w >> 2;
+    const int I0 = I * kNB, k = cx.k;
+    if (I > 0) {
+        chain_wait(cx.ctl.tready(I - 1), cx.gen, cx.dm + D_STATUS);
+        if (I >= 2) chain_wait(cx.ctl.pdready(I), cx.gen, cx.dm + D_STATUS);
+        if (cx.wsBlock != I - 1) load_uinv(cx, I - 1, tid);
+        load_tile64(cx.As, cx.Sg, cx.ldS, I0 - kNB, k, I0, k + 1, tid);
+    }
+    load_tile64(cx.Ts, cx.Sg, cx.ldS, I0, k, I0, k + 1, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (I > 0) {
+        double x[2][4][2], xd[2][4][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x[a][b][0] = x[a][b][1] = 0.0;
+        x_gemm<false>(cx.Ws, cx.As, cx.As, p, nh, g, q, x, xd);
+        __syncthreads();
+        store_x(cx, x, I0 - kNB, I0, cx.As, p, nh, g, q);     // X(I-1, I): to the factor buffer and, K-major, into As
+        chain_signal(cx.ctl.xready(I - 1, I), cx.gen);        // (its __syncthreads also orders the writes to As)
+        double acc[5][2];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) acc[t][0] = acc[t][1] = 0.0;
+        tile_mma_upper(cx.As, w, g, q, acc);
+        tile_sub_upper(cx.Ts, w, g, q, acc);
+        __syncthreads();
+    }
+    // factor the diagonal tile: U_II, Uinv_I and (if nu lies in this tile) y_I
+    const int kb = min(kNB, k - I0);
+    const bool hasNu = (k - I0) < kNB;
+    if (hasNu && tid < kNB) cx.nu[tid] = (tid < kb) ? cx.Ts[tid * kSS + kb] : 0.0;
+    __syncthreads();
+    for (int e = tid; e < kNB * 32; e += 256) {   // identity outside the valid part; W starts at zero
+        const int i = e >> 5, j = (e & 31) * 2;
+        if (i >= kb || j + 1 >= kb) {
+            if (i >= kb || j >= kb) cx.Ts[i * kSS + j] = (i == j) ? 1.0 : 0.0;
+            cx.Ts[i * kSS + j + 1] = (i == j + 1) ? 1.0 : 0.0;
+        }
+        *reinterpret_cast<double2*>(cx.Ws + i * kSS + j) = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    factor_tile64(cx.Ts, cx.Ws, tid, bad, nullptr);
+    __syncthreads();
+    cx.wsBlock = I;
+    if (tid == 0 && (*bad || cx.faultInject)) cx.dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
+    for (int e = tid; e < kNB * 32; e += 256) {
+        const int i = e >> 5, j = (e & 31) * 2;
+        *reinterpret_cast<double2*>(cx.UinvG + (size_t)I * kNB * kNB + i * kNB + j) = *reinterpret_cast<const double2*>(cx.Ws + i * kSS + j);
+        if (i < kb && j + 1 >= i) {
+            double* dst = cx.Sf + (size_t)(I0 + i) * cx.ldS + I0 + j;
+            if (j >= i && j < kb) dst[0] = cx.Ts[i * kSS + j];
+            if (j + 1 < kb) dst[1] = cx.Ts[i * kSS + j + 1];
+        }
+    }
+    if (hasNu && tid < kb) {
+        double s = 0.0;
+        for (int pp = 0; pp <= tid; ++pp) s += cx.Ws[pp * kSS + tid] * cx.nu[pp];
+        cx.Sf[(size_t)(I0 + tid) * cx.ldS + k] = s;
+    }
+    chain_signal(cx.ctl.fdone(I), cx.gen);
+}
+
+// Position p of the per-filter task queue (row-major; the D tasks are not in it): row I holds A(I, I+1) .. A(I, nbC-1), then
+// PD(I+1) when I + 1 >= 2 and I + 1 < nbR.  Returns false past the end.
+__device__ __forceinline__ bool chain_task_at(int pos, int nbR, int nbC, int& kind, int& I, int& C)
+{
+    for (int r = 0; r < nbR; ++r) {
+        const int nA = nbC - r - 1, nP = (r + 1 >= 2 && r + 1 < nbR) ? 1 : 0;
+        if (pos < nA) { kind = 0; I = r; C = r + 1 + pos; return true; }
+        pos -= nA;
+        if (pos < nP) { kind = 1; I = r; C = r + 1; return true; }
+        pos -= nP;
+    }
+    return false;
+}
+
+// grid (G, F): G CTAs per filter.  The first CTA of a filter to arrive runs the critical chain, the others serve the task queue.
+// With G == 1 the single CTA runs everything in dependency order.
+__global__ void __launch_bounds__(256, 1) k_schain_fused(DevView v, int* ctlBase, int nbMax)
+{
+    extern __shared__ __align__(16) double csm[];
+    __shared__ int sTicket, sPos, bad;
+    const int f = blockIdx.y, tid = threadIdx.x;
+    grid_launch_dependents();   // the slab TRSM may be scheduled (it loads its slab of B first); it waits for this grid's completion
+    grid_dependency_wait();
+    int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST];
+    if (k == 0) return;
+    ChainCtx cx;
+    cx.Ws = csm; cx.As = cx.Ws + kNB * kSS; cx.Bs = cx.As + kNB * kSS; cx.Ts = cx.Bs + kNB * kSS; cx.nu = cx.Ts + kNB * kSS;
+    cx.Sg = v.S + (size_t)f * v.kmax * v.ldS;
+    cx.Sf = v.Sf + (size_t)f * v.kmax * v.ldS;
+    cx.UinvG = v.Uinv + (size_t)f * (v.kmax / kNB) * kNB * kNB;
+    cx.ctl.base = ctlBase + (size_t)f * chain_ctl_ints(nbMax);
+    cx.ctl.nbMax = nbMax;
+    cx.dm = dm; cx.k = k; cx.ldS = v.ldS; cx.faultInject = v.faultInject;
+    cx.nbR = (k + kNB - 1) / kNB; cx.nbC = (k + kNB) / kNB;
+    cx.wsBlock = -1;
+    if (tid == 0) {
+        sTicket = atomicAdd(cx.ctl.base + CH_TICKET, 1);
+        bad = 0;
+    }
+    __syncthreads();
+    cx.gen = ld_acquire(cx.ctl.base + CH_GEN) + 1;   // flags of this launch carry generation + 1 (k_chain_finish stores it back)
+    const int ticket = sTicket;
+    const int G = gridDim.x;
+    if (ticket == 0) {
+        if (G > 1) {
+            for (int I = 0; I < cx.nbR; ++I) chain_task_diag(cx, I, &bad);
+            return;
+        }
+        // single CTA per filter: row by row, D(I) then the row's queue tasks
+        int pos = 0;
+        for (int I = 0; I < cx.nbR; ++I) {
+            chain_task_diag(cx, I, &bad);
+            for (;;) {
+                int kind, tI, tC;
+                if (!chain_task_at(pos, cx.nbR, cx.nbC, kind, tI, tC) || tI != I) break;
+                if (kind == 0) chain_task_offdiag(cx, tI, tC);
+                else chain_task_partial_diag(cx, tC);
+                ++pos;
+            }
+        }
+        return;
+    }
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sPos = atomicAdd(cx.ctl.base + CH_QUEUE, 1);
+        __syncthreads();
+        int kind, tI, tC;
+        if (!chain_task_at(sPos, cx.nbR, cx.nbC, kind, tI, tC)) return;
+        if (kind == 0) chain_task_offdiag(cx, tI, tC);
+        else chain_task_partial_diag(cx, tC);
+    }
+}
+
+// after the chain (and everything that reads its flags) of one update: next generation, counters back to zero
+__global__ void k_chain_finish(int* ctlBase, int nbMax, int F)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    int* c = ctlBase + (size_t)f * chain_ctl_ints(nbMax);
+    if (c[CH_TICKET] == 0) return;   // this filter's chain did not run (k == 0)
+    c[CH_GEN] += 1;
+    c[CH_TICKET] = 0;
+    c[CH_QUEUE] = 0;
+}
+
+}  // namespace ekf

@@ -27,7 +27,8 @@ enum DimSlot {
     // map management plan (ekf_map.cuh)
     D_MAP_CHANGED = 17, D_MAP_NEW_N = 18, D_MAP_NEW_NF = 19, D_MAP_CONVERT = 20, D_MAP_NEEDED = 21, D_MAP_NBAD = 22,
     D_MAP_NUNSEEN = 23, D_MAP_CONV_OLDOFF = 24, D_MAP_CONV_NEWOFF = 25,
-    D_PRED_TICKET = 26 /* blocks of k_predict_cov that have finished (reset by the last one) */, D_STRIDE = 32
+    D_PRED_TICKET = 26 /* blocks of k_predict_cov that have finished (reset by the last one) */,
+    D_STATUS_EVER = 27 /* OR of the per-frame status values since ekfb_set_state */, D_STRIDE = 32
 };
 
 struct DevView {
@@ -49,6 +50,7 @@ struct DevView {
     int* rowsrc; uint8_t* mapflag; double* convJ; double* addJ; double* adduv; uint8_t* adddesc;
     // zero-copy readback of the per-filter counters (mapped pinned host memory): hostDims[F][D_STRIDE], hostFlag[F]
     int* hostDims; volatile int* hostFlag;
+    int faultInject;   // test hook (EKFB_OPT_FAULT_INJECT): factorisations report a non-positive pivot
 };
 
 __device__ __forceinline__ int* fdims(const DevView& v, int f) { return v.dims + (size_t)f * D_STRIDE; }
@@ -449,6 +451,8 @@ __global__ void __launch_bounds__(256) k_after_match(DevView v)
         dm[D_BEST_COUNT] = 0;
         dm[D_ULIST] = 0;
         dm[D_N_PRED2] = 0;
+        dm[D_STATUS_EVER] |= dm[D_STATUS];   // D_STATUS is per frame: a failed update only skips the rest of ITS frame
+        dm[D_STATUS] = 0;
     }
 }
 
@@ -725,7 +729,7 @@ __global__ void k_write_records(DevView v, RecordDev* out)
         r->info[0] = dm[D_N_STATE];  r->info[1] = dm[D_N_FEAT];   r->info[2] = dm[D_N_KP];
         r->info[3] = dm[D_N_PRED];   r->info[4] = dm[D_N_MATCH];  r->info[5] = dm[D_N_HYP];
         r->info[6] = dm[D_BEST_HYP]; r->info[7] = dm[D_N_INL];    r->info[8] = dm[D_N_OUT];
-        r->info[9] = dm[D_N_RESC];   r->info[10] = dm[D_STATUS];  r->info[11] = 0;
+        r->info[9] = dm[D_N_RESC];   r->info[10] = dm[D_STATUS];  r->info[11] = dm[D_STATUS_EVER] | dm[D_STATUS];
     }
 }
 

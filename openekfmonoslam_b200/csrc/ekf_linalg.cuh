@@ -372,6 +372,7 @@ __global__ void __maxnreg__(KIND == 2 ? 200 : 255) k_gemm_tn(DevView v, int J)
     const int f = blockIdx.z;
     const int* dm = fdims(v, f);
     const int k = 2 * dm[D_ULIST], n = dm[D_N_STATE];
+    if (KIND >= 2 && dm[D_STATUS] != 0) return;   // a failed factorisation leaves P untouched
     const double *A, *B;
     double* C;
     int lda, ldb, ldc, mBeg, mEnd, nBeg, nEnd, K, aLim, bLim;
@@ -523,7 +524,7 @@ __global__ void __maxnreg__(112) k_downdate64(DevView v, int firstBig)
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     const int K = 2 * dm[D_ULIST], n = dm[D_N_STATE];
-    if (K == 0) return;
+    if (K == 0 || dm[D_STATUS] != 0) return;   // a failed factorisation (status != 0) leaves P untouched
     const int idx = firstBig + (blockIdx.x >> 2), sub = blockIdx.x & 3;
     int I = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
     while (I * (I + 1) / 2 > idx) --I;
@@ -937,6 +938,7 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
     // The slab of B does not depend on the S-chain: with programmatic dependent launch this CTA was scheduled while the last
     // chain step was still running; from here on the factor is read.
     grid_dependency_wait();
+    if (dm[D_STATUS] != 0) return;   // the innovation covariance was not positive definite: no W, the update is skipped
     // chunk stream: for block J: J0/32 chunks of U, then 2 chunks of Uinv_J
     auto issue = [&](int J, int ch, int stage) {
         const int J0 = J * kNB, nU = J0 / 32;
@@ -1067,7 +1069,7 @@ __global__ void __launch_bounds__(128, 2) k_downdate(DevView v)
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     const int K = 2 * dm[D_ULIST], n = dm[D_N_STATE];
-    if (K == 0) return;
+    if (K == 0 || dm[D_STATUS] != 0) return;
     // linear tile index -> (row block I, column tile j), j in [0, 2I+1]
     const int idx = blockIdx.x;
     int I = (int)((sqrtf(4.0f * idx + 1.0f) - 1.0f) * 0.5f);
@@ -1203,7 +1205,7 @@ __global__ void __launch_bounds__(256) k_state_apply(DevView v)
     if (PDL_EARLY_TRIGGER) grid_launch_dependents();
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
-    if (dm[D_ULIST] == 0) return;
+    if (dm[D_ULIST] == 0 || dm[D_STATUS] != 0) return;
     const int n = dm[D_N_STATE];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double* x = v.x + (size_t)f * v.ld;
@@ -1234,7 +1236,7 @@ __global__ void __launch_bounds__(256) k_quat_cov(DevView v)
     if (PDL_EARLY_TRIGGER) grid_launch_dependents();
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
-    if (dm[D_ULIST] == 0) return;
+    if (dm[D_ULIST] == 0 || dm[D_STATUS] != 0) return;
     const int n = dm[D_N_STATE];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;

@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256, 1) k_schain_step(DevView v, int J)
     factor_tile64(Ts, Ws, tid, &bad, dbg ? dbg + 8 : nullptr);
     __syncthreads();
     if (dbg) dbg[4] = clock64();
-    if (tid == 0 && bad) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
+    if (tid == 0 && (bad || v.faultInject)) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
     for (int e = tid; e < kNB * 32; e += 256) {
         const int i = e >> 5, j = (e & 31) * 2;
         *reinterpret_cast<double2*>(UinvG + (size_t)I * kNB * kNB + i * kNB + j) = *reinterpret_cast<const double2*>(Ws + i * kSS + j);

@@ -9,13 +9,17 @@ def assign_filters(n_filters_total, world_size, rank):
     return [f for f in range(n_filters_total) if f % world_size == rank]
 
 
-def gather_records(local_records, n_filters_total, world_size, rank, dist=None):
-    """local_records: uint8 tensor [n_local * record_bytes] on this rank's device, in the order of
-    assign_filters(...).  Returns a uint8 numpy array [n_filters_total, record_bytes] in global filter
-    order (on every rank).  Ranks may own different numbers of filters; buffers are padded to the max."""
+def gather_records(local_records, n_filters_total, world_size, rank, dist=None, rec_bytes=None):
+    """local_records: uint8 tensor [n_local * rec_bytes] on this rank's device, in the order of
+    assign_filters(...).  Returns a uint8 numpy array [n_filters_total, rec_bytes] in global filter
+    order (on every rank).  Ranks may own different numbers of filters -- also none, when there are fewer filters than
+    ranks -- so the record size is passed in (capi.RECORD_BYTES), never inferred from a possibly empty local buffer;
+    buffers are padded to the largest shard."""
     import torch
     n_local = len(assign_filters(n_filters_total, world_size, rank))
-    rec_bytes = local_records.numel() // max(n_local, 1)
+    if rec_bytes is None:
+        from .capi import RECORD_BYTES as rec_bytes
+    assert local_records.numel() == n_local * rec_bytes, "local record buffer does not match this rank's shard"
     n_max = (n_filters_total + world_size - 1) // world_size
     if world_size == 1:
         return local_records.detach().cpu().numpy().reshape(n_filters_total, rec_bytes)

@@ -106,8 +106,10 @@ def test_capacity_and_argument_errors():
     assert gpu.frame_info(0)["status"] == 0
 
 
-def test_keypoints_of_all_filters_in_one_call():
-    """ekfb_set_keypoints_batch: three filters of one handle fed different frames (one of them empty) in one call"""
+@pytest.mark.parametrize("packed", [False, True])
+def test_keypoints_of_all_filters_in_one_call(packed):
+    """ekfb_set_keypoints_batch / ekfb_set_keypoints_packed: three filters of one handle fed different frames (one of them
+    empty) in one call"""
     sc = Scenario(320, 240, 30)
     x, P, ft, fo, desc, _ = sc.init_map()
     gpu = EkfBatch(sc.params, 3, 30, 256)
@@ -119,7 +121,12 @@ def test_keypoints_of_all_filters_in_one_call():
     for t in (1, 2):
         fr = [sc.frame(t), sc.frame(t + 5), NO_KP if t == 2 else sc.frame(t + 9)]
         keep = [(np.ascontiguousarray(k), np.ascontiguousarray(d)) for k, d in fr]
-        gpu.set_keypoints_batch_raw([k.ctypes.data for k, _ in keep], [d.ctypes.data for _, d in keep], [len(k) for k, _ in keep])
+        if packed:
+            xy = np.ascontiguousarray(np.concatenate([k.reshape(-1, 2) for k, _ in keep]), np.float32)
+            dd = np.ascontiguousarray(np.concatenate([d.reshape(-1, 32) for _, d in keep]), np.uint8)
+            gpu.set_keypoints_packed_raw(xy.ctypes.data, dd.ctypes.data, np.cumsum([0] + [len(k) for k, _ in keep]))
+        else:
+            gpu.set_keypoints_batch_raw([k.ctypes.data for k, _ in keep], [d.ctypes.data for _, d in keep], [len(k) for k, _ in keep])
         gpu.step()
         for f in range(3):
             io = orcs[f].step(*fr[f])

@@ -250,12 +250,13 @@ def test_covariance_downdate_kernel(n, k, variant):
     assert np.array_equal(out, out.T)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 @pytest.mark.parametrize("k", [2, 8, 62, 64, 66, 126, 128, 130, 200, 384, 600, 640])
 def test_innovation_covariance_factorisation(k, variant):
     """The S-chain alone: S = U^T U, y = U^-T nu and the inverses of the diagonal 64x64 blocks, against numpy.  k covers
     a single ragged block, exact multiples of 64 (nu alone in the last column tile) and the C3 size.  variant 0 = one
-    fused launch per block step (default), 1 = the panel + trail launch pairs."""
+    fused launch per block step, 1 = the panel + trail launch pairs, 3 = the whole chain as one launch (tile dataflow,
+    csrc/ekf_chain.cuh); every variant twice on the same handle (the one-launch chain carries a generation counter)."""
     rng = np.random.default_rng(1000 + k)
     A = rng.normal(size=(k, k + 8))
     S = A @ A.T / k + 0.5 * np.eye(k)
@@ -264,6 +265,7 @@ def test_innovation_covariance_factorisation(k, variant):
     nu = rng.normal(size=k) * d
     gpu = EkfBatch(Scenario(320, 240, 4).params, 1, max(k // 2, 4), 64)
     gpu.set_option(3, variant)
+    gpu.test_factor(np.hstack([S, nu[:, None]]))
     U, Ui = gpu.test_factor(np.hstack([S, nu[:, None]]))
     L = np.linalg.cholesky(S)
     Uu, Lt = np.triu(U[:, :k]), L.T.copy()
@@ -271,7 +273,7 @@ def test_innovation_covariance_factorisation(k, variant):
         for J in range((k + 63) // 64):
             Uu[64 * J:64 * J + 64, 64 * J:64 * J + 64] = 0.0
             Lt[64 * J:64 * J + 64, 64 * J:64 * J + 64] = 0.0
-    if k > 64 or variant == 0:
+    if k > 64 or variant != 1:
         assert rel_err(Uu, Lt) < 1e-12
     y = np.linalg.solve(L, nu)
     assert rel_err(U[:, k], y) < 1e-11
@@ -282,12 +284,66 @@ def test_innovation_covariance_factorisation(k, variant):
         assert np.array_equal(np.tril(Ui[J, :kb, :kb], -1), np.zeros((kb, kb)))
 
 
-def test_legacy_schain_variant_whole_update():
-    """The panel + trail launch pairs (option 3 = 1) through the whole update, against the oracle."""
+@pytest.mark.parametrize("variant", [1, 3])
+def test_other_schain_variants_whole_update(variant):
+    """The panel + trail launch pairs (option 3 = 1) and the one-launch chain (3) through the whole update, against the oracle."""
     sc, orc, gpu = make_pair(640, 480, 100, warm=3)
-    gpu.set_option(3, 1)
-    for t in range(4, 6):
+    gpu.set_option(3, variant)
+    for t in range(4, 7):
         phase_by_phase(sc, orc, gpu, t)
+
+
+def test_one_launch_chain_batched_filters():
+    """the one-launch chain with several CTAs per filter (4 filters -> 37 CTAs each) and with a single CTA per filter
+    (more filters than SMs / 2 cannot be co-resident with more), against per-filter oracles"""
+    for F in (4, 80):
+        scs = [Scenario(320, 240, 40, seed_offset=f % 4) for f in range(F)]
+        gpu = EkfBatch(scs[0].params, F, 40, 256)
+        gpu.set_option(3, 3)
+        orcs = []
+        for f in range(F):
+            x, P, ft, fo, desc, _ = scs[f].init_map()
+            gpu.set_state(f, x, P, ft, fo, desc)
+            if f < 4:
+                o = OracleFilter(scs[f].params); o.set_state(x, P, ft, fo, desc)
+                orcs.append(o)
+        for t in range(1, 4):
+            for f in range(F):
+                gpu.set_keypoints(f, *scs[f].frame(t))
+            gpu.step()
+            for f in range(4):
+                orcs[f].step(*scs[f].frame(t))
+        for f in range(F):
+            xo, Po = orcs[f % 4].get_state()
+            xg, Pg = gpu.get_state(f)
+            assert rel_err(xg, xo) < TOL and rel_err(Pg, Po) < TOL, (F, f)
+            assert gpu.frame_info(f)["status"] == 0
+
+
+@pytest.mark.parametrize("variant", [0, 3])
+def test_numeric_failure_leaves_the_filter_untouched(variant):
+    """EKFB_ERR_NUMERIC: when the factorisation of an innovation covariance reports a non-positive pivot (injected here with
+    EKFB_OPT_FAULT_INJECT; the reference inverts S by LU, E/Update.cpp:108, and cannot fail this way) the frame's status is set
+    and that update -- and the rest of the frame's updates -- are skipped: state and covariance stay exactly as the
+    prediction left them.  The next frame starts clean; `reserved` keeps the sticky flag."""
+    sc, orc, gpu = make_pair(320, 240, 30)
+    gpu.set_option(3, variant)
+    gpu.set_keypoints(0, *sc.frame(1))
+    gpu.predict(); gpu.measure(); gpu.match(); gpu.ransac()
+    assert gpu.frame_info(0)["n_inliers"] > 2
+    x0, P0 = gpu.get_state(0)
+    gpu.set_option(9, 1)
+    gpu.update(0); gpu.rescue(); gpu.update(1); gpu.update_map_features()
+    info = gpu.frame_info(0)
+    assert info["status"] == 4 and info["reserved"] == 4
+    x1, P1 = gpu.get_state(0)
+    assert np.array_equal(x0, x1) and np.array_equal(P0, P1)
+    gpu.set_option(9, 0)
+    gpu.set_keypoints(0, *sc.frame(2)); gpu.step()
+    info = gpu.frame_info(0)
+    assert info["status"] == 0 and info["reserved"] == 4 and info["n_inliers"] > 2
+    x2, P2 = gpu.get_state(0)
+    assert not np.array_equal(P1, P2) and np.array_equal(P2, P2.T)
 
 
 def test_full_size_properties_c3():

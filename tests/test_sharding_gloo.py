@@ -30,13 +30,13 @@ def _worker(rank, world, port, n_total, q):
     local = torch.zeros(len(mine) * REC, dtype=torch.uint8)
     for i, f in enumerate(mine):  # record content = a function of the global filter index
         local[i * REC:(i + 1) * REC] = torch.from_numpy(((np.arange(REC) * 7 + f * 13) % 251).astype(np.uint8))
-    res = gather_records(local, n_total, world, rank, dist)
+    res = gather_records(local, n_total, world, rank, dist, rec_bytes=REC)
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_total", [5, 8])
+@pytest.mark.parametrize("n_total", [1, 5, 8])   # 1: a rank that owns no filter at all
 def test_two_rank_gather_is_in_global_filter_order(n_total):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
