@@ -243,7 +243,8 @@ int64_t ekfb_kernel_launches(ekfb_handle h);     /* kernels launched by this han
  * the whole augmented matrix (the path used when k is too large for the shared-memory slab TRSM). */
 enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* 0: 128x128 tiles (default), 1: 128x64 tiles, 2 CTAs/SM */,
        EKFB_OPT_SCHAIN_VARIANT = 3 /* factorisation of S: 0 = one fused launch per 64-row step, 1 = panel + trail launches,
-                                      3 = the whole chain in one launch (tile dataflow, ekf_chain.cuh) */,
+                                      3 = the whole chain in one launch (tile dataflow, ekf_chain.cuh),
+                                      4 = as 3, and for a single filter the slab TRSM runs inside the same launch, overlapped with the chain */,
        EKFB_OPT_DOWNDATE_SMALL_K = 4 /* updates with at most this many rows run the downdate as 64x64 tiles, 4 CTAs/SM (default: all); above it 128x128 tiles */,
        EKFB_OPT_TRSM_STAGES = 5 /* upper limit of the slab TRSM's operand-ring depth: 2, 3 or 4 (default 4, as shared memory allows) */,
        EKFB_OPT_TRSM_PAIR = 6 /* batched filters: 1 (default) = slab footprint that lets two CTAs share an SM when possible */,

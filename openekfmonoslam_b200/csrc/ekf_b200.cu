@@ -299,6 +299,8 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
     CK(cudaFuncSetAttribute(k_schain_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem));
     CK(cudaFuncSetAttribute(k_schain_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    CK(cudaFuncSetAttribute(k_update_fused<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_update_fused<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -745,7 +747,7 @@ static int launch_schain(ekfb_ctx* c, int k)
             }
         }
         CK(cudaMemcpyAsync(v.Sf, v.S, sizeof(double) * (size_t)c->F * c->kmax * c->ldS, cudaMemcpyDeviceToDevice, c->stream));
-    } else if (c->schain_variant == 3) {
+    } else if (c->schain_variant >= 3) {
         // the whole chain in one launch: G CTAs per filter (one critical CTA + queue workers).  Grid sized from the handle's
         // capacity, not from this frame's k: surplus CTAs find the queue empty and exit.
         const int nbR = c->kmax / kNB, nbC = nbR + 1;
@@ -785,7 +787,19 @@ static int run_update(ekfb_ctx* c, int which)
         const int steps = cdiv(k, kNB);
         const size_t smem16 = trsm_smem_bytes(k, 16);
         const size_t smemMax = 227 * 1024;
-        if (smem16 <= smemMax && !c->force_generic) {
+        // single filter, variant 4: chain and slab TRSM overlapped in one launch (ekf_chain.cuh), when one slab per SM fits
+        // beside the chain's CTAs; otherwise the chain (one launch) followed by the slab TRSM
+        const int fusedSlabs = cdiv(n, 24);
+        const int fusedNS = trsm_smem_bytes(k, 24, 3) <= smemMax ? 3 : (trsm_smem_bytes(k, 24, 2) <= smemMax ? 2 : 0);
+        if (c->schain_variant == 4 && c->F == 1 && !c->force_generic && fusedNS > 0 && fusedSlabs + 1 + 8 <= c->smCount) {
+            const size_t sm = std::max<size_t>(kChainSmem, trsm_smem_bytes(k, 24, fusedNS));
+            if (fusedNS == 3)
+                CK(launch_pdl(k_update_fused<24, 3>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
+            else
+                CK(launch_pdl(k_update_fused<24, 2>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
+            k_chain_finish<<<1, 32, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
+            count_launch(c, 2);
+        } else if (smem16 <= smemMax && !c->force_generic) {
             // fast path: S-only chain, diagonal-block inverses, slab TRSM
             { int rcC = launch_schain(c, k); if (rcC != EKFB_OK) return rcC; }
             // widest slab that fits, then the deepest operand ring beside it (4, 3 or 2 stages of 32 rows)
@@ -807,7 +821,7 @@ static int run_update(ekfb_ctx* c, int which)
             else
                 CK(launch_pdl(k_trsm_slab<16, 2>, dim3(cdiv(n, 16), c->F), dim3(256), smem16, c->stream, v));
             count_launch(c);
-            if (c->schain_variant == 3) {   // next generation of the chain's flags (after everything that follows the chain)
+            if (c->schain_variant >= 3) {   // next generation of the chain's flags (after everything that follows the chain)
                 k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
                 count_launch(c);
             }
@@ -1454,7 +1468,7 @@ extern "C" int ekfb_test_factor(ekfb_handle c, int k, const double* S_in, double
     CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
     int rc = launch_schain(c, k);
     if (rc != EKFB_OK) return rc;
-    if (c->schain_variant == 3) k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
+    if (c->schain_variant >= 3) k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(U_out, sizeof(double) * (k + 1), v.Sf, sizeof(double) * c->ldS, sizeof(double) * (k + 1), k,
                          cudaMemcpyDeviceToHost, c->stream));

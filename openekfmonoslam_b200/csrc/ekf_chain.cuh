@@ -415,4 +415,174 @@ __global__ void k_chain_finish(int* ctlBase, int nbMax, int F)
     c[CH_QUEUE] = 0;
 }
 
+// =====================================================================================================================
+// The chain and the slab TRSM in ONE launch (single filter): the TRSM's row block J only needs block column J of U and
+// Uinv_J, which the chain publishes when it raises fdone(J) -- so W^T = U^-T B is formed WHILE the chain runs, on the SMs the
+// chain leaves idle, instead of after it.  grid (G): ticket 0 = critical chain, tickets 1 .. H = chain queue workers,
+// tickets H+1 .. = one slab of SW columns of B each (the algorithm of k_trsm_slab, ekf_linalg.cuh, with a flag wait in
+// front of every row block).  When the chain ends only the last row block of the TRSM is left.
+// =====================================================================================================================
+template <int SW, int NS>
+__device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, ChainCtx& cx)
+{
+    constexpr int SWP = SW + 4, NT = SW / 8;
+    const int* dm = cx.dm;
+    const int k = cx.k, n = dm[D_N_STATE];
+    const int c0 = slab * SW;
+    if (c0 >= n) return;
+    const int kpad = (k + kNB - 1) / kNB * kNB, steps = kpad / kNB;
+    double* Xs = tsm;
+    double* Us = Xs + (size_t)kpad * SWP;   // NS stages x [32][68]
+    double* Ts = Us + NS * 32 * 68;         // [64][SWP]
+    double* red = Ts + kNB * SWP;           // [8][SW]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    double* Bg = v.Bu + (size_t)f * v.kmax * v.ld;
+    const double* Sg = cx.Sf;
+    const double* Uinv = cx.UinvG;
+    for (int e = tid; e < kpad * SW; e += blockDim.x) {
+        const int r = e / SW, c = e % SW;
+        Xs[(size_t)r * SWP + c] = (r < k && c0 + c < n) ? Bg[(size_t)r * v.ld + c0 + c] : 0.0;
+    }
+    auto issue = [&](int J, int ch, int stage) {
+        const int J0 = J * kNB, nU = J0 / 32;
+        double* dst = Us + stage * 32 * 68;
+        const double* src;
+        int lds;
+        if (ch < nU) { src = Sg + (size_t)(ch * 32) * v.ldS + J0; lds = v.ldS; }
+        else { src = Uinv + (size_t)J * kNB * kNB + (size_t)(ch - nU) * 32 * kNB; lds = kNB; }
+        for (int e = tid; e < 32 * 32; e += blockDim.x) {
+            const int r = e >> 5, c2 = (e & 31) * 2;
+            cp_async16(dst + r * 68 + c2, src + (size_t)r * lds + c2);
+        }
+    };
+    int J = 0, ch = 0, stage = 0;
+    int Ji = 0, chi = 0, stagei = 0;   // issue position: NS - 1 chunks ahead of the consume position (J, ch, stage)
+    auto issue_next = [&]() {
+        if (Ji < steps) {
+            if (chi == 0) chain_wait(cx.ctl.fdone(Ji), cx.gen, cx.dm + D_STATUS);   // block column Ji of U and Uinv_Ji are published
+            issue(Ji, chi, stagei);
+            if (++chi == (Ji * kNB) / 32 + 2) { ++Ji; chi = 0; }
+            stagei = (stagei + 1 == NS) ? 0 : stagei + 1;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int p = 0; p < NS - 1; ++p) issue_next();
+    double acc[NT][2];
+    while (J < steps) {
+        const int J0 = J * kNB, nU = J0 / 32, nCh = nU + 2;
+        const int kb = min(kNB, k - J0);
+        if (ch == 0) {
+#pragma unroll
+            for (int b = 0; b < NT; ++b) acc[b][0] = acc[b][1] = 0.0;
+        }
+        int Jn = J, chn = ch + 1;
+        if (chn == nCh) { Jn = J + 1; chn = 0; }
+        issue_next();
+        cp_async_wait<NS - 1>();
+        __syncthreads();
+        const double* Uc = Us + stage * 32 * 68;
+        if (ch == nU) {
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = 8 * w + g, c = 8 * b + 2 * q + e;
+                    Ts[m * SWP + c] = (m < kb) ? Xs[(size_t)(J0 + m) * SWP + c] - acc[b][e] : 0.0;
+                    acc[b][e] = 0.0;
+                }
+            __syncthreads();
+        }
+        const double* Bsrc = (ch < nU) ? Xs + (size_t)(ch * 32) * SWP : Ts + (size_t)((ch - nU) * 32) * SWP;
+#pragma unroll
+        for (int k4 = 0; k4 < 32; k4 += 4) {
+            const double a = Uc[(k4 + q) * 68 + 8 * w + g];
+#pragma unroll
+            for (int b = 0; b < NT; ++b) dmma8x8x4(acc[b][0], acc[b][1], a, Bsrc[(size_t)(k4 + q) * SWP + 8 * b + g]);
+        }
+        if (ch == nCh - 1) {
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = 8 * w + g, c = 8 * b + 2 * q + e;
+                    Xs[(size_t)(J0 + m) * SWP + c] = (m < kb) ? acc[b][e] : 0.0;
+                }
+        }
+        __syncthreads();
+        stage = (stage + 1 == NS) ? 0 : stage + 1;
+        J = Jn;
+        ch = chn;
+    }
+    cp_async_wait<0>();
+    // y = U^-T nu lives in column k of the factor buffer: rows of block I < the nu column tile come from A(I, Cnu)
+    const int Cnu = cx.nbC - 1;
+    for (int I = 0; I < cx.nbR; ++I)
+        if (Cnu > I) chain_wait(cx.ctl.xready(I, Cnu), cx.gen, cx.dm + D_STATUS);
+    if (__ldcg(dm + D_STATUS) != 0) return;   // not positive definite: no W, the update is skipped
+    for (int e = tid; e < k * SW; e += blockDim.x) {
+        const int r = e / SW, c = e % SW;
+        if (c0 + c < n) Bg[(size_t)r * v.ld + c0 + c] = Xs[(size_t)r * SWP + c];
+    }
+    if (lane < SW) {
+        double s = 0.;
+        for (int r = w; r < k; r += 8) s += Xs[(size_t)r * SWP + lane] * __ldcg(Sg + (size_t)r * v.ldS + k);
+        red[w * SW + lane] = s;
+    }
+    __syncthreads();
+    if (tid < SW && c0 + tid < n) {
+        double s = 0.;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) s += red[ww * SW + tid];
+        v.dx[(size_t)f * v.ld + c0 + tid] = s;
+    }
+}
+
+template <int SW, int NS>
+__global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase, int nbMax, int nSlabs)
+{
+    extern __shared__ __align__(16) double csm[];
+    __shared__ int sTicket, sPos, bad;
+    const int f = 0, tid = threadIdx.x;
+    grid_launch_dependents();
+    grid_dependency_wait();
+    int* dm = fdims(v, f);
+    const int k = 2 * dm[D_ULIST];
+    if (k == 0) return;
+    ChainCtx cx;
+    cx.Ws = csm; cx.As = cx.Ws + kNB * kSS; cx.Bs = cx.As + kNB * kSS; cx.Ts = cx.Bs + kNB * kSS; cx.nu = cx.Ts + kNB * kSS;
+    cx.Sg = v.S; cx.Sf = v.Sf; cx.UinvG = v.Uinv;
+    cx.ctl.base = ctlBase;
+    cx.ctl.nbMax = nbMax;
+    cx.dm = dm; cx.k = k; cx.ldS = v.ldS; cx.faultInject = v.faultInject;
+    cx.nbR = (k + kNB - 1) / kNB; cx.nbC = (k + kNB) / kNB;
+    cx.wsBlock = -1;
+    if (tid == 0) {
+        sTicket = atomicAdd(cx.ctl.base + CH_TICKET, 1);
+        bad = 0;
+    }
+    __syncthreads();
+    cx.gen = ld_acquire(cx.ctl.base + CH_GEN) + 1;
+    const int ticket = sTicket;
+    const int H = (int)gridDim.x - 1 - nSlabs;   // chain queue workers
+    if (ticket == 0) {
+        for (int I = 0; I < cx.nbR; ++I) chain_task_diag(cx, I, &bad);
+        return;
+    }
+    if (ticket > H) {
+        trsm_slab_role<SW, NS>(v, f, ticket - H - 1, csm, cx);
+        return;
+    }
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sPos = atomicAdd(cx.ctl.base + CH_QUEUE, 1);
+        __syncthreads();
+        int kind, tI, tC;
+        if (!chain_task_at(sPos, cx.nbR, cx.nbC, kind, tI, tC)) return;
+        if (kind == 0) chain_task_offdiag(cx, tI, tC);
+        else chain_task_partial_diag(cx, tC);
+    }
+}
+
 }  // namespace ekf

@@ -284,9 +284,10 @@ def test_innovation_covariance_factorisation(k, variant):
         assert np.array_equal(np.tril(Ui[J, :kb, :kb], -1), np.zeros((kb, kb)))
 
 
-@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 def test_other_schain_variants_whole_update(variant):
-    """The panel + trail launch pairs (option 3 = 1) and the one-launch chain (3) through the whole update, against the oracle."""
+    """One launch per block step (option 3 = 0), the panel + trail launch pairs (1), the one-launch chain (3) and the chain
+    with the slab TRSM overlapped inside the same launch (4) through the whole update, against the oracle."""
     sc, orc, gpu = make_pair(640, 480, 100, warm=3)
     gpu.set_option(3, variant)
     for t in range(4, 7):
@@ -320,7 +321,7 @@ def test_one_launch_chain_batched_filters():
             assert gpu.frame_info(f)["status"] == 0
 
 
-@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("variant", [0, 3, 4])
 def test_numeric_failure_leaves_the_filter_untouched(variant):
     """EKFB_ERR_NUMERIC: when the factorisation of an innovation covariance reports a non-positive pivot (injected here with
     EKFB_OPT_FAULT_INJECT; the reference inverts S by LU, E/Update.cpp:108, and cannot fail this way) the frame's status is set
