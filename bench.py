@@ -293,8 +293,6 @@ class Leg:
         self.F = len(self.my_filters)
         self.scenes, self.N = make_scenarios(wl, self.my_filters, features)
         self.gpu = EkfBatch(next(iter(self.scenes.values())).params, max(self.F, 1), self.N, 2 * self.N + 256, device=local)
-        for kv in filter(None, os.environ.get("EKFB_OPTS", "").split(",")):   # developer switches (ekfb_set_option), e.g. "4=128"
-            self.gpu.set_option(*(int(x) for x in kv.split("=")))
         self.rec_dev = torch.zeros(max(self.F, 1) * RECORD_BYTES, dtype=torch.uint8, device=dev)
         self.n_max = (self.total_filters + world - 1) // world
         self.rec_pad = torch.zeros(self.n_max * RECORD_BYTES, dtype=torch.uint8, device=dev)

@@ -73,6 +73,9 @@ class EkfBatch:
         self.h = ctypes.c_void_p()
         self._ck(self.L.ekfb_create(ctypes.byref(params), ctypes.c_int(device), ctypes.c_int(n_filters),
                                     ctypes.c_int(max_features), ctypes.c_int(max_keypoints), ctypes.byref(self.h)))
+        # developer switches for every handle of the process: EKFB_OPTS="3=4,8=0" -> ekfb_set_option(3, 4), (8, 0)
+        for kv in filter(None, os.environ.get("EKFB_OPTS", "").split(",")):
+            self.set_option(*(int(x) for x in kv.split("=")))
 
     def _ck(self, rc):
         if rc != 0:

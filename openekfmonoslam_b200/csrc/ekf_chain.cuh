@@ -62,9 +62,18 @@ __device__ __forceinline__ void chain_wait(const int* flag, int gen, int* status
 // all threads: the CTA's global stores so far become visible, then the flag is raised
 __device__ __forceinline__ void chain_signal(int* flag, int gen)
 {
-    __threadfence();
+    __syncthreads();                      // every thread's stores are ordered before thread 0's fence (the pattern of a grid barrier)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release(flag, gen);
+    }
+}
+// non-blocking: is the flag already raised?  (thread 0 looks, everybody gets the answer)
+__device__ __forceinline__ bool chain_peek(const int* flagA, const int* flagB, int gen, int* sFlag)
+{
+    if (threadIdx.x == 0) *sFlag = (ld_acquire(flagA) == gen) && (flagB == nullptr || ld_acquire(flagB) == gen);
     __syncthreads();
-    if (threadIdx.x == 0) st_release(flag, gen);
+    return *sFlag != 0;
 }
 
 constexpr int kChainSmem = (4 * kNB * kSS + 2 * kNB) * (int)sizeof(double);
@@ -76,6 +85,7 @@ struct ChainCtx {
     int* dm;
     int k, nbR, nbC, ldS, gen, faultInject;
     int wsBlock;                         // which Uinv block Ws holds (-1: none)
+    int pre;                             // D(pre)'s tiles were prefetched into As / Bs (-1: none)
 };
 
 // acc += A^T B for two K-major 64x64 tiles in shared memory; warp (p, nh) owns rows 16p.., columns 32nh..
@@ -262,19 +272,27 @@ __device__ void chain_task_partial_diag(ChainCtx& cx, int C)
 }
 
 // ---- D(I): the critical chain ---------------------------------------------------------------------------------------
-__device__ void chain_task_diag(ChainCtx& cx, int I, int* bad)
+// `prefetch`: the dedicated critical CTA keeps the tile it factors in Ts and, half way through the factorisation, starts the
+// loads of its NEXT step -- T(I, I+1) into As, T'(I+1, I+1) into Bs -- if their flags are already up (they normally are: the
+// helpers run ahead); the next call then finds them in shared memory (cx.pre == I + 1) and swaps Bs / Ts.
+__device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool prefetch)
 {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3, p = w & 3, nh = w >> 2;
     const int I0 = I * kNB, k = cx.k;
-    if (I > 0) {
-        chain_wait(cx.ctl.tready(I - 1), cx.gen, cx.dm + D_STATUS);
-        if (I >= 2) chain_wait(cx.ctl.pdready(I), cx.gen, cx.dm + D_STATUS);
-        if (cx.wsBlock != I - 1) load_uinv(cx, I - 1, tid);
-        load_tile64(cx.As, cx.Sg, cx.ldS, I0 - kNB, k, I0, k + 1, tid);
+    if (cx.pre == I) {
+        double* t = cx.Ts; cx.Ts = cx.Bs; cx.Bs = t;     // T'(I, I) arrived in Bs
+    } else {
+        if (I > 0) {
+            chain_wait(cx.ctl.tready(I - 1), cx.gen, cx.dm + D_STATUS);
+            if (I >= 2) chain_wait(cx.ctl.pdready(I), cx.gen, cx.dm + D_STATUS);
+            if (cx.wsBlock != I - 1) load_uinv(cx, I - 1, tid);
+            load_tile64(cx.As, cx.Sg, cx.ldS, I0 - kNB, k, I0, k + 1, tid);
+        }
+        load_tile64(cx.Ts, cx.Sg, cx.ldS, I0, k, I0, k + 1, tid);
+        cp_async_commit();
     }
-    load_tile64(cx.Ts, cx.Sg, cx.ldS, I0, k, I0, k + 1, tid);
-    cp_async_commit();
+    cx.pre = -1;
     cp_async_wait<0>();
     __syncthreads();
     if (I > 0) {
@@ -308,7 +326,16 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad)
         *reinterpret_cast<double2*>(cx.Ws + i * kSS + j) = make_double2(0.0, 0.0);
     }
     __syncthreads();
-    factor_tile64(cx.Ts, cx.Ws, tid, bad, nullptr);
+    const bool wantNext = prefetch && (I + 1 < cx.nbR);
+    auto hook = [&]() {
+        if (!wantNext) return;
+        if (!chain_peek(cx.ctl.tready(I), (I + 1 >= 2) ? cx.ctl.pdready(I + 1) : nullptr, cx.gen, sFlag)) return;
+        load_tile64(cx.As, cx.Sg, cx.ldS, I0, k, I0 + kNB, k + 1, tid);
+        load_tile64(cx.Bs, cx.Sg, cx.ldS, I0 + kNB, k, I0 + kNB, k + 1, tid);
+        cp_async_commit();
+        cx.pre = I + 1;
+    };
+    factor_tile64(cx.Ts, cx.Ws, tid, bad, nullptr, hook);
     __syncthreads();
     cx.wsBlock = I;
     if (tid == 0 && (*bad || cx.faultInject)) cx.dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
@@ -348,7 +375,7 @@ __device__ __forceinline__ bool chain_task_at(int pos, int nbR, int nbC, int& ki
 __global__ void __launch_bounds__(256, 1) k_schain_fused(DevView v, int* ctlBase, int nbMax)
 {
     extern __shared__ __align__(16) double csm[];
-    __shared__ int sTicket, sPos, bad;
+    __shared__ int sTicket, sPos, bad, sFlag;
     const int f = blockIdx.y, tid = threadIdx.x;
     grid_launch_dependents();   // the slab TRSM may be scheduled (it loads its slab of B first); it waits for this grid's completion
     grid_dependency_wait();
@@ -364,7 +391,7 @@ __global__ void __launch_bounds__(256, 1) k_schain_fused(DevView v, int* ctlBase
     cx.ctl.nbMax = nbMax;
     cx.dm = dm; cx.k = k; cx.ldS = v.ldS; cx.faultInject = v.faultInject;
     cx.nbR = (k + kNB - 1) / kNB; cx.nbC = (k + kNB) / kNB;
-    cx.wsBlock = -1;
+    cx.wsBlock = -1; cx.pre = -1;
     if (tid == 0) {
         sTicket = atomicAdd(cx.ctl.base + CH_TICKET, 1);
         bad = 0;
@@ -375,13 +402,13 @@ __global__ void __launch_bounds__(256, 1) k_schain_fused(DevView v, int* ctlBase
     const int G = gridDim.x;
     if (ticket == 0) {
         if (G > 1) {
-            for (int I = 0; I < cx.nbR; ++I) chain_task_diag(cx, I, &bad);
+            for (int I = 0; I < cx.nbR; ++I) chain_task_diag(cx, I, &bad, &sFlag, true);
             return;
         }
         // single CTA per filter: row by row, D(I) then the row's queue tasks
         int pos = 0;
         for (int I = 0; I < cx.nbR; ++I) {
-            chain_task_diag(cx, I, &bad);
+            chain_task_diag(cx, I, &bad, &sFlag, false);
             for (;;) {
                 int kind, tI, tC;
                 if (!chain_task_at(pos, cx.nbR, cx.nbC, kind, tI, tC) || tI != I) break;
@@ -543,7 +570,7 @@ template <int SW, int NS>
 __global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase, int nbMax, int nSlabs)
 {
     extern __shared__ __align__(16) double csm[];
-    __shared__ int sTicket, sPos, bad;
+    __shared__ int sTicket, sPos, bad, sFlag;
     const int f = 0, tid = threadIdx.x;
     grid_launch_dependents();
     grid_dependency_wait();
@@ -557,7 +584,7 @@ __global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase
     cx.ctl.nbMax = nbMax;
     cx.dm = dm; cx.k = k; cx.ldS = v.ldS; cx.faultInject = v.faultInject;
     cx.nbR = (k + kNB - 1) / kNB; cx.nbC = (k + kNB) / kNB;
-    cx.wsBlock = -1;
+    cx.wsBlock = -1; cx.pre = -1;
     if (tid == 0) {
         sTicket = atomicAdd(cx.ctl.base + CH_TICKET, 1);
         bad = 0;
@@ -567,7 +594,7 @@ __global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase
     const int ticket = sTicket;
     const int H = (int)gridDim.x - 1 - nSlabs;   // chain queue workers
     if (ticket == 0) {
-        for (int I = 0; I < cx.nbR; ++I) chain_task_diag(cx, I, &bad);
+        for (int I = 0; I < cx.nbR; ++I) chain_task_diag(cx, I, &bad, &sFlag, true);
         return;
     }
     if (ticket > H) {

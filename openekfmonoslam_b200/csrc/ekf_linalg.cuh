@@ -516,7 +516,7 @@ __global__ void __maxnreg__(KIND == 2 ? 200 : 255) k_gemm_tn(DevView v, int J)
 // registers, 52 KB smem) on a second stream, co-resident with the big CTAs.  Big tile `idx` -> 4 small tiles.
 constexpr int kSmallSmemBytes = kStages * kKC * (68 + 68) * (int)sizeof(double);
 
-__global__ void __maxnreg__(128) k_downdate64(DevView v, int firstBig)
+__global__ void __maxnreg__(112) k_downdate64(DevView v, int firstBig)
 {
     grid_dependency_wait();   // launched with programmatic stream serialisation: nothing of the predecessor is read before this
     if (PDL_EARLY_TRIGGER) grid_launch_dependents();
@@ -538,14 +538,9 @@ __global__ void __maxnreg__(128) k_downdate64(DevView v, int firstBig)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
     double acc[4][4][2];
-    // executed work = algorithmic work: 8x8 sub-tiles beyond the matrix edge or strictly above the diagonal are skipped
-    const int aMax = (tm0 == tn0 && wn > wm) ? 0 : min(4, max(0, (n - (tm0 + wm * 32) + 7) / 8));
-    const int bMax = min(4, max(0, (n - (tn0 + wn * 32) + 7) / 8));
-    const bool diagWarp = (tm0 == tn0) && (wm == wn);
-    unsigned subMask = 0;
-    for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b)
-            if (a < aMax && b < bMax && (!diagWarp || b <= a)) subMask |= 1u << (a * 4 + b);
+    // warp tiles (32 x 32) that hold no element of the lower triangle inside the matrix do no arithmetic: the warp above the
+    // diagonal of a diagonal tile, and the warps beyond the ragged last block row / column of P
+    const bool warpIdle = (tm0 == tn0 && wn > wm) || (tm0 + wm * 32 >= n) || (tn0 + wn * 32 >= n);
     const int nk = (K + kKC - 1) / kKC;
     auto stA = [&](int st) { return ssm2 + (size_t)st * kKC * 136; };
     auto stB = [&](int st) { return ssm2 + (size_t)st * kKC * 136 + kKC * 68; };
@@ -596,8 +591,7 @@ __global__ void __maxnreg__(128) k_downdate64(DevView v, int firstBig)
         cp_async_commit();
         const double* As = stA(kt % kStages) + wm * 32 + g;
         const double* Bs = stB(kt % kStages) + wn * 32 + g;
-        // only the 8x8 sub-tiles that hold elements of the lower triangle inside the matrix are multiplied (warp-uniform
-        // predicates: the ragged last block row / column of P and the diagonal tile's warps skip the rest)
+        if (warpIdle) continue;
 #pragma unroll
         for (int k4 = 0; k4 < kKC; k4 += 4) {
             double af[4], bf[4];
@@ -608,8 +602,7 @@ __global__ void __maxnreg__(128) k_downdate64(DevView v, int firstBig)
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if ((subMask >> (a * 4 + b)) & 1u) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                for (int b = 0; b < 4; ++b) dmma8x8x4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
     }
     cp_async_wait<0>();

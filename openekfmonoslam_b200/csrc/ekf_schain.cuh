@@ -148,7 +148,11 @@ __device__ __forceinline__ void ll_store(const LLTile& t, const double (&c)[4])
 // valid part by identity and zeroed W): on return T holds U (upper, T = U^T U) and W holds U^-1 (upper, zeros below).
 // Called by all 256 threads: warps 0-3 do the in-register work, warps 4-7 only join the rank-8 tile updates.  *bad is set if a
 // pivot is not positive.
-__device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int* bad, long long* dbg)
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// hook(): called by all threads once, half way through (before block step 5): lets the caller start loads for its next tile
+template <typename Hook = NoHook>
+__device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int* bad, long long* dbg, Hook hook = Hook())
 {
     long long tA = 0, tB = 0, tC = 0, t0 = 0;
     const int lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -156,6 +160,7 @@ __device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int
         const int o = 8 * b;
         if (dbg) t0 = clock64();
         double R[8][8], r[8];
+        if (b == 5) hook();
         if (b > 0) {  // bring block row b of T and column block b of U^-1 up to date: one tile per warp
             const LLTile t = ll_tile(T, W, b, w, g, q);
             double ca[4] = {0.0, 0.0, 0.0, 0.0};

@@ -12,9 +12,6 @@ W, H, N, F, T = (int(a) for a in sys.argv[1:6])
 dbg = len(sys.argv) > 6
 scs = [Scenario(W, H, N, seed_offset=i) for i in range(min(F, 4))]
 gpu = EkfBatch(scs[0].params, F, N, 2 * N + 256)
-import os
-for kv in filter(None, os.environ.get("EKFB_OPTS", "").split(",")):
-    gpu.set_option(*(int(x) for x in kv.split("=")))
 t0 = time.time()
 inits = [sc.init_map() for sc in scs]
 frames = [[sc.frame(t) for t in range(1, T + 1)] for sc in scs]
