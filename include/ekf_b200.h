@@ -226,12 +226,13 @@ int ekfb_test_downdate(ekfb_handle h, int n, int k, const double* P_in, const do
  * (S = U^T U; entries below the diagonal are not written) and, in column k, y = U^-T nu.  Uinv_out receives the inverses of
  * the ceil(k/64) diagonal 64x64 blocks of U (row-major, identity-padded). */
 int ekfb_test_factor(ekfb_handle h, int k, const double* S_in, double* U_out, double* Uinv_out);
-/* Full gain + update on filter 0 from caller Jacobians: for a = 0..m-1 feature index feat[a] with
- * z (2m), using the handle's current state / P / last ekfb_measure.  Returns timings in ms. */
+/* Timing hook.  STATE-DESTRUCTIVE: applies `reps` real updates (`which` = 0 low / 1 high innovation) on the update list of the
+ * last RANSAC / rescue to the live x and P, then runs the 128x64-tile downdate kernel alone `reps` times; returns the
+ * per-repetition times in ms.  Re-upload the state with ekfb_set_state afterwards. */
 int ekfb_time_update(ekfb_handle h, int which, int reps, float* ms_total, float* ms_downdate);
 
 /* ---- device timing on the handle's stream (bench.py cannot see this stream from torch) ------------ */
-int ekfb_timer_record(ekfb_handle h, int slot);                 /* slot in [0, 64) */
+int ekfb_timer_record(ekfb_handle h, int slot);                 /* slot in [0, 62): slots 62 and 63 are used by ekfb_time_update */
 int ekfb_timer_elapsed_ms(ekfb_handle h, int slot_a, int slot_b, float* ms);
 /* enable per-kernel-group timing of ekfb_step (adds event records; off by default) */
 int ekfb_profile_enable(ekfb_handle h, int on);

@@ -41,6 +41,8 @@ static thread_local std::string g_err;
         }                           \
     } while (0)
 
+constexpr int kFusedSmemMax = 227 * 1024 - 1024;   // k_update_fused also has a few bytes of static shared memory
+
 enum ProfGroup { G_PREDICT = 0, G_MEASURE, G_MATCH, G_RANSAC, G_GAIN, G_CHOL, G_DOWNDATE, G_RESCUE, G_MISC, G_COUNT };
 
 struct SeqDev {
@@ -193,10 +195,13 @@ static cudaError_t launch_k(ekfb_ctx* c, void (*kernel)(KArgs...), dim3 grid, di
 
 extern "C" const char* ekfb_last_error(void) { return g_err.c_str(); }
 
+static int create_impl(const ekfb_params* p, int device, int n_filters, int max_features, int max_keypoints, ekfb_ctx* c);
+
 extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int max_features, int max_keypoints,
                            ekfb_handle* out)
 {
     REQUIRE(p && out, "null argument");
+    *out = nullptr;
     REQUIRE(n_filters > 0 && max_features > 0 && max_keypoints > 0, "sizes must be positive");
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
@@ -209,6 +214,24 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
         return EKFB_ERR_CUDA;
     }
     ekfb_ctx* c = new ekfb_ctx();
+    c->smCount = prop.multiProcessorCount;
+    for (int i = 0; i < 64; ++i) c->timers[i] = nullptr;
+    c->pe[0] = c->pe[1] = nullptr;
+    // any failure below (an out-of-memory on a large max_features is the realistic one) releases everything built so far
+    const int rc = create_impl(p, device, n_filters, max_features, max_keypoints, c);
+    if (rc != EKFB_OK) {
+        const std::string keep = g_err;
+        ekfb_destroy(c);
+        cudaGetLastError();
+        g_err = keep;
+        return rc;
+    }
+    *out = c;
+    return EKFB_OK;
+}
+
+static int create_impl(const ekfb_params* p, int device, int n_filters, int max_features, int max_keypoints, ekfb_ctx* c)
+{
     c->prm = *p;
     c->device = device;
     c->F = n_filters;
@@ -225,7 +248,6 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
-    c->smCount = prop.multiProcessorCount;
     for (int i = 0; i < 64; ++i) CK(cudaEventCreate(&c->timers[i]));
     CK(cudaEventCreate(&c->pe[0]));
     CK(cudaEventCreate(&c->pe[1]));
@@ -299,8 +321,8 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
     CK(cudaFuncSetAttribute(k_schain_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem));
     CK(cudaFuncSetAttribute(k_schain_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    CK(cudaFuncSetAttribute(k_update_fused<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(k_update_fused<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_update_fused<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CK(cudaFuncSetAttribute(k_update_fused<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -311,7 +333,6 @@ extern "C" int ekfb_create(const ekfb_params* p, int device, int n_filters, int 
     const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
     CK(cudaFuncSetAttribute(k_mask_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, rasterSmem));
     CK(cudaStreamSynchronize(c->stream));
-    *out = c;
     return EKFB_OK;
 }
 
@@ -319,7 +340,7 @@ extern "C" int ekfb_destroy(ekfb_handle c)
 {
     if (!c) return EKFB_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocs) cudaFree(p);
     for (SeqDev& s : c->seq) {
         if (s.xy) cudaFree(s.xy);
@@ -327,16 +348,17 @@ extern "C" int ekfb_destroy(ekfb_handle c)
     }
     if (c->flush_buf) cudaFree(c->flush_buf);
     for (cudaEvent_t e : c->dd_ev) cudaEventDestroy(e);
-    cudaFreeHost(c->h_dims);
+    if (c->h_dims) cudaFreeHost(c->h_dims);
     if (c->h_dims_zc) cudaFreeHost(c->h_dims_zc);
-    cudaFreeHost(c->h_kpxy_ptr);
-    cudaFreeHost(c->h_kpdesc_ptr);
-    cudaFreeHost(c->h_kpcount);
-    cudaFreeHost(c->h_rec);
-    for (int i = 0; i < 64; ++i) cudaEventDestroy(c->timers[i]);
-    cudaEventDestroy(c->pe[0]);
-    cudaEventDestroy(c->pe[1]);
-    cudaStreamDestroy(c->stream);
+    if (c->h_kpxy_ptr) cudaFreeHost(c->h_kpxy_ptr);
+    if (c->h_kpdesc_ptr) cudaFreeHost(c->h_kpdesc_ptr);
+    if (c->h_kpcount) cudaFreeHost(c->h_kpcount);
+    if (c->h_rec) cudaFreeHost(c->h_rec);
+    for (int i = 0; i < 64; ++i)
+        if (c->timers[i]) cudaEventDestroy(c->timers[i]);
+    if (c->pe[0]) cudaEventDestroy(c->pe[0]);
+    if (c->pe[1]) cudaEventDestroy(c->pe[1]);
+    if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
@@ -790,7 +812,7 @@ static int run_update(ekfb_ctx* c, int which)
         // single filter, variant 4: chain and slab TRSM overlapped in one launch (ekf_chain.cuh), when one slab per SM fits
         // beside the chain's CTAs; otherwise the chain (one launch) followed by the slab TRSM
         const int fusedSlabs = cdiv(n, 24);
-        const int fusedNS = trsm_smem_bytes(k, 24, 3) <= smemMax ? 3 : (trsm_smem_bytes(k, 24, 2) <= smemMax ? 2 : 0);
+        const int fusedNS = trsm_smem_bytes(k, 24, 3) <= (size_t)kFusedSmemMax ? 3 : (trsm_smem_bytes(k, 24, 2) <= (size_t)kFusedSmemMax ? 2 : 0);
         if (c->schain_variant == 4 && c->F == 1 && !c->force_generic && fusedNS > 0 && fusedSlabs + 1 + 8 <= c->smCount) {
             const size_t sm = std::max<size_t>(kChainSmem, trsm_smem_bytes(k, 24, fusedNS));
             if (fusedNS == 3)
@@ -1437,7 +1459,13 @@ extern "C" int ekfb_test_downdate(ekfb_handle c, int n, int k, const double* P_i
         c->hn[0] = n;
         int rcD = launch_downdate(c, n);
         c->hn[0] = saveN;
-        if (rcD != EKFB_OK) return rcD;
+        if (rcD != EKFB_OK) {   // leave the handle's counters as they were
+            hd[D_N_STATE] = save_n;
+            hd[D_ULIST] = save_u;
+            cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);
+            return rcD;
+        }
     }
     CK(cudaEventRecord(c->pe[1], c->stream));
     CK(cudaGetLastError());
