@@ -17,6 +17,7 @@
 #include "ekf_map.cuh"
 #include "ekf_ncc.cuh"
 #include "ekf_frontend.cuh"
+#include "ekf_downdate_tma.cuh"
 
 using namespace ekf;
 
@@ -99,6 +100,7 @@ struct ekfb_ctx {
     int trsm_stages = 4;      // upper limit of the slab TRSM's operand ring depth (option 5)
     int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches,
                               // 3 = the whole chain in one launch (ekf_chain.cuh)
+    void* tmaEncode = nullptr;   // cuTensorMapEncodeTiled (driver entry point, fetched once; no link against libcuda)
     int* chainCtl = nullptr;  // per-filter control blocks of the one-launch chain (generation, queue, flags)
     int nbMax = 0;
     bool dd_timing = false;
@@ -321,6 +323,15 @@ static int create_impl(const ekfb_params* p, int device, int n_filters, int max_
     CK(cudaFuncSetAttribute(k_schain_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSPanelSmem));
     CK(cudaFuncSetAttribute(k_schain_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem));
     CK(cudaFuncSetAttribute(k_schain_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    CK(cudaFuncSetAttribute(k_downdate_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmemBytes));
+    CK(cudaFuncSetAttribute(k_downdate_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdSmemBytes));
+    {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &c->tmaEncode, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            c->tmaEncode = nullptr;
+        cudaGetLastError();
+    }
     CK(cudaFuncSetAttribute(k_update_fused<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_fused<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -710,7 +721,31 @@ static int launch_downdate(ekfb_ctx* c, int n)
     for (int f = 0; f < c->F; ++f) kMax = std::max(kMax, 2 * c->h_dims[(size_t)f * D_STRIDE + D_ULIST]);
     const bool timeIt = c->dd_timing && c->dd_used + 2 <= c->dd_ev.size();
     if (timeIt) cudaEventRecord(c->dd_ev[c->dd_used], c->stream);
-    if (c->downdate_variant == 1)
+    if (c->downdate_variant >= 2 && c->F == 1 && c->tmaEncode && kMax > 0) {
+        // single filter: TMA-fed persistent kernel (ekf_downdate_tma.cuh).  The two tensor maps carry this launch's n and K, so
+        // the ragged edge and the rows beyond K are clipped / zero-filled by the TMA unit.
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        const bool swz = c->downdate_variant == 2;
+        TdMaps maps;
+        const cuuint64_t pd[2] = {(cuuint64_t)n, (cuuint64_t)n}, wd[2] = {(cuuint64_t)c->ld, (cuuint64_t)kMax};
+        const cuuint64_t st[1] = {(cuuint64_t)c->ld * sizeof(double)};
+        const cuuint32_t pb[2] = {swz ? 16u : 64u, 64u}, wb[2] = {swz ? 16u : 64u, 16u}, es[2] = {1, 1};
+        const CUtensorMapSwizzle sw = swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+        CUresult r1 = ((EncodeFn)c->tmaEncode)(&maps.P, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, v.P, pd, st, pb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r2 = ((EncodeFn)c->tmaEncode)(&maps.W, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, v.Bu, wd, st, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+            g_err = "cuTensorMapEncodeTiled failed for the downdate operands";
+            return EKFB_ERR_CUDA;
+        }
+        const int nT = cdiv(n, 64), tiles = nT * (nT + 1) / 2;
+        const dim3 grid(std::min(tiles, 2 * c->smCount));
+        if (swz) CK(launch_k(c, k_downdate_tma<true>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps));
+        else CK(launch_k(c, k_downdate_tma<false>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps));
+    } else if (c->downdate_variant == 1)
         k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
     else if (kMax <= c->downdate_small_k) {
         // 64x64 tiles, four CTAs per SM (the default at every k, see downdate_small_k)

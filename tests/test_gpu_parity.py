@@ -233,11 +233,12 @@ def test_device_resident_sequence_equals_host_fed():
         compare_state(orc, gpu, f"seq frame {t}")
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("n,k", [(313, 2), (313, 100), (613, 40), (1213, 120), (3013, 200)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,k", [(313, 2), (313, 100), (613, 40), (1213, 120), (3013, 200), (3013, 72), (2005, 640)])
 def test_covariance_downdate_kernel(n, k, variant):
-    """P - W W^T on the FP64 tensor pipe vs numpy, sizes of SURVEY 7.1 step 4; exactly symmetric output.
-    variant 0 = default (128x128 tiles + co-resident 64x64 remainder kernel at n = 3013), 1 = 128x64 tiles."""
+    """P - W W^T on the FP64 tensor pipe vs numpy, sizes of SURVEY 7.1 step 4 plus the C3 update sizes; exactly symmetric
+    output.  variant 0 = 64x64 tiles fed by cp.async, 1 = 128x64 tiles, 2 = persistent TMA-fed kernel (tensor-map loads and
+    stores, mbarrier ring, 128-byte swizzle), 3 = the same without swizzle."""
     rng = np.random.default_rng(n + k)
     A = rng.normal(size=(n, 64))
     P = A @ A.T / 64 + np.eye(n)

@@ -21,15 +21,16 @@ P = A @ A.T + np.eye(n)
 for k in ks:
     Wt = rng.normal(size=(k, n)) * 0.01
     res = {}
-    for small_k in (0, 1 << 20):
+    for name, small_k, variant in (("tiles128", 0, 0), ("tiles64", 1 << 20, 0), ("tma_swizzle128", 1 << 20, 2), ("tma_dense", 1 << 20, 3)):
         gpu.set_option(4, small_k)
+        gpu.set_option(2, variant)
         gpu.test_downdate(P, Wt)
         ts = []
         for _ in range(6):
             gpu.downdate_timing(True)
             gpu.test_downdate(P, Wt)
             ts.append(gpu.downdate_stats()["ms"])
-        res["tiles64" if small_k else "tiles128"] = round(min(ts) * 1e3, 1)
+        res[name] = round(min(ts) * 1e3, 1)
     best = min(res.values())
     print(json.dumps({"n": n, "k": k, "us": res, "tflops_best": round(n * (n + 1) * k / best / 1e6, 2),
                       "gbs_min_traffic_best": round(16 * n * n / best / 1e3, 1)}))
