@@ -89,7 +89,7 @@ struct ekfb_ctx {
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     bool force_generic = false;
-    int downdate_variant = 0;
+    int downdate_variant = 2;   // 2 = TMA-fed persistent kernel (default), 3 = same without swizzle, 0 = cp.async 64x64 tiles, 1 = 128x64
     // updates with at most this many rows run the downdate as 64x64 tiles, 4 CTAs per SM.  Measured on B200 (profiles/
     // r01_downdate_sweep.txt) that variant wins at every k and n tried (16 resident warps hide the tile read-modify-write
     // and the operand ring better than 8 warps of one 128x128 CTA), so it is the default for all k; option 4 lowers it.
@@ -98,8 +98,10 @@ struct ekfb_ctx {
     int trsm_pair = 1;        // batched filters: slab footprint that fits two CTAs per SM when possible (option 6)
     int ransac_chunk = 0;     // hypotheses evaluated per round; 0 = 16 for a single filter, 4 for batches (option 7)
     int trsm_stages = 4;      // upper limit of the slab TRSM's operand ring depth (option 5)
-    int schain_variant = 0;   // 0 = one fused launch per block step (ekf_schain.cuh), 1 = panel + trail launches,
-                              // 3 = the whole chain in one launch (ekf_chain.cuh)
+    int schain_variant = -1;  // -1 = automatic (single filter and k > 128: 4, else 0), 0 = one fused launch per block step
+                              // (ekf_schain.cuh), 1 = panel + trail launches, 3 = the whole chain in one launch (ekf_chain.cuh),
+                              // 4 = chain + slab TRSM in one launch (single filter)
+    int schain_eff = 0;       // the variant the current update uses
     void* tmaEncode = nullptr;   // cuTensorMapEncodeTiled (driver entry point, fetched once; no link against libcuda)
     int* chainCtl = nullptr;  // per-filter control blocks of the one-launch chain (generation, queue, flags)
     int nbMax = 0;
@@ -713,7 +715,7 @@ extern "C" int ekfb_ransac(ekfb_handle c)
 }
 
 // P -= W W^T for all filters of the handle (W^T = rows of Bu, K = 2 * ulist count per filter)
-static int launch_downdate(ekfb_ctx* c, int n)
+static int launch_downdate(ekfb_ctx* c, int n, bool allowTma = true)
 {
     DevView& v = c->v;
     const int nI = cdiv(n, kDTM);
@@ -721,30 +723,33 @@ static int launch_downdate(ekfb_ctx* c, int n)
     for (int f = 0; f < c->F; ++f) kMax = std::max(kMax, 2 * c->h_dims[(size_t)f * D_STRIDE + D_ULIST]);
     const bool timeIt = c->dd_timing && c->dd_used + 2 <= c->dd_ev.size();
     if (timeIt) cudaEventRecord(c->dd_ev[c->dd_used], c->stream);
-    if (c->downdate_variant >= 2 && c->F == 1 && c->tmaEncode && kMax > 0) {
-        // single filter: TMA-fed persistent kernel (ekf_downdate_tma.cuh).  The two tensor maps carry this launch's n and K, so
-        // the ragged edge and the rows beyond K are clipped / zero-filled by the TMA unit.
+    if (c->downdate_variant >= 2 && allowTma && c->tmaEncode && kMax > 0) {
+        // TMA-fed persistent kernel (ekf_downdate_tma.cuh): 3-D tensor maps over (column, row, filter) of P and of W^T, encoded
+        // per launch (the P buffers swap under map management).  Needs the rows of W^T between K and the end of its last 16-row
+        // chunk to be zero, which the slab TRSM guarantees (allowTma is false after the generic factorisation).
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
         const bool swz = c->downdate_variant == 2;
         TdMaps maps;
-        const cuuint64_t pd[2] = {(cuuint64_t)n, (cuuint64_t)n}, wd[2] = {(cuuint64_t)c->ld, (cuuint64_t)kMax};
-        const cuuint64_t st[1] = {(cuuint64_t)c->ld * sizeof(double)};
-        const cuuint32_t pb[2] = {swz ? 16u : 64u, 64u}, wb[2] = {swz ? 16u : 64u, 16u}, es[2] = {1, 1};
+        const cuuint64_t pd[3] = {(cuuint64_t)c->nmax, (cuuint64_t)c->nmax, (cuuint64_t)c->F};
+        const cuuint64_t wd[3] = {(cuuint64_t)c->ld, (cuuint64_t)c->kmax, (cuuint64_t)c->F};
+        const cuuint64_t pst[2] = {(cuuint64_t)c->ld * sizeof(double), (cuuint64_t)c->nmax * c->ld * sizeof(double)};
+        const cuuint64_t wst[2] = {(cuuint64_t)c->ld * sizeof(double), (cuuint64_t)c->kmax * c->ld * sizeof(double)};
+        const cuuint32_t pb[3] = {swz ? 16u : 64u, 64u, 1u}, wb[3] = {swz ? 16u : 64u, 16u, 1u}, es[3] = {1, 1, 1};
         const CUtensorMapSwizzle sw = swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
-        CUresult r1 = ((EncodeFn)c->tmaEncode)(&maps.P, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, v.P, pd, st, pb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r1 = ((EncodeFn)c->tmaEncode)(&maps.P, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, v.P, pd, pst, pb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        CUresult r2 = ((EncodeFn)c->tmaEncode)(&maps.W, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, v.Bu, wd, st, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r2 = ((EncodeFn)c->tmaEncode)(&maps.W, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, v.Bu, wd, wst, wb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
             g_err = "cuTensorMapEncodeTiled failed for the downdate operands";
             return EKFB_ERR_CUDA;
         }
-        const int nT = cdiv(n, 64), tiles = nT * (nT + 1) / 2;
-        const dim3 grid(std::min(tiles, 2 * c->smCount));
-        if (swz) CK(launch_k(c, k_downdate_tma<true>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps));
-        else CK(launch_k(c, k_downdate_tma<false>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps));
+        const int nT = cdiv(n, 64), tilesMax = nT * (nT + 1) / 2;
+        const dim3 grid((unsigned)std::min<long long>((long long)tilesMax * c->F, 2ll * c->smCount));
+        if (swz) CK(launch_k(c, k_downdate_tma<true>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps, tilesMax));
+        else CK(launch_k(c, k_downdate_tma<false>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps, tilesMax));
     } else if (c->downdate_variant == 1)
         k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
     else if (kMax <= c->downdate_small_k) {
@@ -791,7 +796,7 @@ static int launch_schain(ekfb_ctx* c, int k)
 {
     DevView& v = c->v;
     const int steps = cdiv(k, kNB);
-    if (c->schain_variant == 1) {
+    if (c->schain_eff == 1) {
         for (int J = 0; J < steps; ++J) {
             const int J0 = J * kNB, J1 = J0 + kNB;
             const int Jr = std::min(J1, k);
@@ -804,7 +809,7 @@ static int launch_schain(ekfb_ctx* c, int k)
             }
         }
         CK(cudaMemcpyAsync(v.Sf, v.S, sizeof(double) * (size_t)c->F * c->kmax * c->ldS, cudaMemcpyDeviceToDevice, c->stream));
-    } else if (c->schain_variant >= 3) {
+    } else if (c->schain_eff >= 3) {
         // the whole chain in one launch: G CTAs per filter (one critical CTA + queue workers).  Grid sized from the handle's
         // capacity, not from this frame's k: surplus CTAs find the queue empty and exit.
         const int nbR = c->kmax / kNB, nbC = nbR + 1;
@@ -833,6 +838,7 @@ static int run_update(ekfb_ctx* c, int which)
     for (int f = 0; f < c->F; ++f) ku = std::max(ku, c->h_dims[(size_t)f * D_STRIDE + D_ULIST]);
     if (ku == 0) return EKFB_OK;
     const int k = 2 * ku, n = max_of(c->hn);
+    bool usedGeneric = false;
     {
         GroupScope gs(c, G_GAIN);
         CK(launch_k(c, k_gain_rows, dim3(cdiv(c->ld, 256), ku, c->F), dim3(256), 0, v, which));
@@ -848,7 +854,11 @@ static int run_update(ekfb_ctx* c, int which)
         // beside the chain's CTAs; otherwise the chain (one launch) followed by the slab TRSM
         const int fusedSlabs = cdiv(n, 24);
         const int fusedNS = trsm_smem_bytes(k, 24, 3) <= (size_t)kFusedSmemMax ? 3 : (trsm_smem_bytes(k, 24, 2) <= (size_t)kFusedSmemMax ? 2 : 0);
-        if (c->schain_variant == 4 && c->F == 1 && !c->force_generic && fusedNS > 0 && fusedSlabs + 1 + 8 <= c->smCount) {
+        const bool fusedOk = c->F == 1 && !c->force_generic && fusedNS > 0 && fusedSlabs + 1 + 8 <= c->smCount;
+        // automatic choice (measured on B200, profiles/r02_chain_downdate_variants.txt): the fused launch wins once the chain has
+        // three or more block steps; below that (and for batches) one launch per block step is faster
+        c->schain_eff = c->schain_variant >= 0 ? c->schain_variant : ((fusedOk && k > 128) ? 4 : 0);
+        if (c->schain_eff == 4 && fusedOk) {
             const size_t sm = std::max<size_t>(kChainSmem, trsm_smem_bytes(k, 24, fusedNS));
             if (fusedNS == 3)
                 CK(launch_pdl(k_update_fused<24, 3>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
@@ -878,12 +888,13 @@ static int run_update(ekfb_ctx* c, int which)
             else
                 CK(launch_pdl(k_trsm_slab<16, 2>, dim3(cdiv(n, 16), c->F), dim3(256), smem16, c->stream, v));
             count_launch(c);
-            if (c->schain_variant >= 3) {   // next generation of the chain's flags (after everything that follows the chain)
+            if (c->schain_eff >= 3) {   // next generation of the chain's flags (after everything that follows the chain)
                 k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
                 count_launch(c);
             }
         } else {
             // generic path (very large k): right-looking over the whole augmented matrix
+            usedGeneric = true;
             for (int J = 0; J < steps; ++J) {
                 const int J1 = (J + 1) * kNB;
                 const int nS = k > J1 ? cdiv(k - J1, kPanelCols) : 0;
@@ -902,7 +913,7 @@ static int run_update(ekfb_ctx* c, int which)
     }
     {
         GroupScope gs(c, G_DOWNDATE);
-        int rcD = launch_downdate(c, n);
+        int rcD = launch_downdate(c, n, !usedGeneric);
         if (rcD != EKFB_OK) return rcD;
         CK(launch_k(c, k_quat_cov, dim3(cdiv(n, 256), c->F), dim3(256), 0, v));
         count_launch(c, 2);
@@ -1478,7 +1489,7 @@ extern "C" int ekfb_test_downdate(ekfb_handle c, int n, int k, const double* P_i
     DevView& v = c->v;
     CK(cudaMemcpy2DAsync(v.P, sizeof(double) * c->ld, P_in, sizeof(double) * n, sizeof(double) * n, n,
                          cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(v.Bu, 0, sizeof(double) * (size_t)k * c->ld, c->stream));
+    CK(cudaMemsetAsync(v.Bu, 0, sizeof(double) * (size_t)std::min(rup(k, 16), c->kmax) * c->ld, c->stream));
     CK(cudaMemcpy2DAsync(v.Bu, sizeof(double) * c->ld, Wt, sizeof(double) * n, sizeof(double) * n, k,
                          cudaMemcpyHostToDevice, c->stream));
     int* hd = c->h_dims;
@@ -1529,9 +1540,10 @@ extern "C" int ekfb_test_factor(ekfb_handle c, int k, const double* S_in, double
     hd[D_ULIST] = k / 2;
     hd[D_STATUS] = 0;
     CK(cudaMemcpyAsync(v.dims, hd, sizeof(int) * D_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    c->schain_eff = c->schain_variant >= 0 ? c->schain_variant : 0;
     int rc = launch_schain(c, k);
     if (rc != EKFB_OK) return rc;
-    if (c->schain_variant >= 3) k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
+    if (c->schain_eff >= 3) k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
     CK(cudaGetLastError());
     CK(cudaMemcpy2DAsync(U_out, sizeof(double) * (k + 1), v.Sf, sizeof(double) * c->ldS, sizeof(double) * (k + 1), k,
                          cudaMemcpyDeviceToHost, c->stream));

@@ -548,7 +548,8 @@ __device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, C
     for (int I = 0; I < cx.nbR; ++I)
         if (Cnu > I) chain_wait(cx.ctl.xready(I, Cnu), cx.gen, cx.dm + D_STATUS);
     if (__ldcg(dm + D_STATUS) != 0) return;   // not positive definite: no W, the update is skipped
-    for (int e = tid; e < k * SW; e += blockDim.x) {
+    const int kz = min(kpad, (k + 15) & ~15);   // rows k .. end of the last 16-row chunk go back as zeros (TMA-fed downdate)
+    for (int e = tid; e < kz * SW; e += blockDim.x) {
         const int r = e / SW, c = e % SW;
         if (c0 + c < n) Bg[(size_t)r * v.ld + c0 + c] = Xs[(size_t)r * SWP + c];
     }

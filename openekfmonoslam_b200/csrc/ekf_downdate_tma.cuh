@@ -1,19 +1,21 @@
-// ekf_downdate_tma.cuh -- U3 (+ the symmetrise of U4): the covariance downdate  P -= W W^T  (E/Update.cpp:214-218, 307) for a
-// single filter, fed by the TMA engine.  Same contraction and tiling as k_downdate64 (ekf_linalg.cuh: lower 64x64 tiles, 4 warps
-// of 32x32, FP64 DMMA m8n8k4), different plumbing:
-//   * persistent CTAs (two per SM) walk the tile list, so prologues / epilogues of one tile overlap the arithmetic of the
-//     CTA that shares the SM, and the operand ring never drains inside a CTA;
-//   * a PRODUCER WARP feeds everything with tensor-map TMA (cp.async.bulk.tensor.2d + mbarrier complete_tx): the P tile
-//     (64 x 64) into a staging buffer and the K-major operand chunks of W^T (16 rows x 64 columns for the tile's rows and
-//     for its columns) into a 3-stage ring -- full / empty mbarriers, no __syncthreads and no cp.async address arithmetic
-//     in the four CONSUMER warps;
+// ekf_downdate_tma.cuh -- U3 (+ the symmetrise of U4): the covariance downdate  P -= W W^T  (E/Update.cpp:214-218, 307), fed by
+// the TMA engine, for one filter or a batch.  Same contraction and tiling as k_downdate64 (ekf_linalg.cuh: lower 64x64 tiles,
+// 4 warps of 32x32, FP64 DMMA m8n8k4), different plumbing:
+//   * persistent CTAs (two per SM) walk the list of (filter, tile) items, so prologues / epilogues of one tile overlap the
+//     arithmetic of the CTA that shares the SM, and the operand ring never drains inside a CTA;
+//   * a PRODUCER WARP feeds everything with tensor-map TMA (cp.async.bulk.tensor.3d + mbarrier complete_tx; the third
+//     coordinate is the filter): the P tile (64 x 64) into a staging buffer and the K-major operand chunks of W^T (16 rows x
+//     64 columns for the tile's rows and for its columns) into a 3-stage ring -- full / empty mbarriers, no __syncthreads
+//     and no cp.async address arithmetic in the four CONSUMER warps;
 //   * 128-byte swizzled boxes (16 doubles wide) + a row permutation inside the 16-row chunk make every DMMA fragment
 //     load bank-conflict free without padding (TMA writes dense boxes);
-//   * the updated tile leaves through shared memory as ONE TMA tensor store, and its mirror image as a second one
+//   * the updated tile leaves through shared memory as TMA tensor stores, and its mirror image as a second set
 //     (transposed in shared memory), so both triangles are written as full 128-byte rows: P stays exactly symmetric
-//     (the two stores carry bit-identical values) and no thread issues a strided global store;
-//   * rows / columns beyond the matrix edge are clipped by the tensor map (dims = n x n, K rows), not by predicates.
-// Algorithmic work per launch n (n + 1) K flop, minimum traffic 16 n^2 bytes.
+//     (the two stores carry bit-identical values) and no thread issues a strided global store.  Tiles that cross the edge
+//     of their filter's matrix (n is not a multiple of 64) are stored with predicated global stores instead, so nothing
+//     beyond row / column n is ever written.
+// Rows of W^T beyond a filter's K inside its last 16-row chunk must be zero: the slab TRSM writes them (k_trsm_slab).
+// Algorithmic work per launch sum_f n_f (n_f + 1) K_f flop, minimum traffic 16 n^2 bytes per filter.
 #pragma once
 
 #include <cuda.h>
@@ -29,26 +31,26 @@ constexpr int kTdChunkBytes = 16 * 64 * 8;                // one operand chunk: 
 constexpr int kTdSmemBytes = 2 * kTdTileBytes + kTdStages * 2 * kTdChunkBytes + 64;
 
 struct TdMaps {
-    CUtensorMap P;   // dims (n cols, n rows), box (16 | 64, 64)
-    CUtensorMap W;   // dims (ld cols, K rows), box (16 | 64, 16)
+    CUtensorMap P;   // dims (nmax cols, nmax rows, F filters), box (16 | 64, 64, 1)
+    CUtensorMap W;   // dims (ld cols, kmax rows, F filters),  box (16 | 64, 16, 1)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
                      smem_u32(smem)),
-                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2)
 {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                      reinterpret_cast<unsigned long long>(map)),
-                 "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+                 "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -67,9 +69,32 @@ __device__ __forceinline__ int td_off(int r, int c, int rows)
     return (r * 64 + c) * 8;
 }
 
-// grid (min(tiles, 2 * SMs)), 160 threads: warps 0-3 consume, warp 4 produces.  Dynamic shared memory kTdSmemBytes, 1024-byte aligned.
+// work item -> filter, tile coordinates; false if the item has nothing to do (its filter has no update, or the tile lies
+// outside that filter's matrix)
+struct TdItem { int f, tm0, tn0, n, nk; bool diag, edge; };
+__device__ __forceinline__ bool td_item(const DevView& v, int item, int tilesMax, TdItem& o)
+{
+    o.f = item / tilesMax;
+    const int t = item - o.f * tilesMax;
+    const int* dm = fdims(v, o.f);
+    const int K = 2 * dm[D_ULIST];
+    o.n = dm[D_N_STATE];
+    if (K == 0 || dm[D_STATUS] != 0) return false;
+    int I = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while (I * (I + 1) / 2 > t) --I;
+    while ((I + 1) * (I + 2) / 2 <= t) ++I;
+    const int J = t - I * (I + 1) / 2;
+    o.tm0 = I * 64; o.tn0 = J * 64;
+    if (o.tm0 >= o.n) return false;
+    o.nk = (K + 15) >> 4;
+    o.diag = (I == J);
+    o.edge = (o.tm0 + 64 > o.n);      // (tn0 <= tm0: a tile that crosses the edge in its columns also crosses it in its rows)
+    return true;
+}
+
+// grid (min(items, 2 * SMs)), 160 threads: warps 0-3 consume, warp 4 produces.  Dynamic shared memory kTdSmemBytes, 1024-byte aligned.
 template <bool SWZ>
-__global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid_constant__ TdMaps maps)
+__global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid_constant__ TdMaps maps, int tilesMax)
 {
     extern __shared__ __align__(1024) unsigned char tds[];
     unsigned char* Pbuf = tds;
@@ -81,9 +106,6 @@ __global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid
     uint64_t* pfull = bars + 2 * kTdStages;
     uint64_t* pempty = pfull + 1;
     grid_dependency_wait();
-    const int* dm = fdims(v, 0);
-    const int K = 2 * dm[D_ULIST], n = dm[D_N_STATE];
-    if (K == 0 || dm[D_STATUS] != 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < kTdStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 4); }
@@ -91,38 +113,34 @@ __global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid
         mbar_init(pempty, 4);
     }
     __syncthreads();
-    const int nT = (n + 63) >> 6, tiles = nT * (nT + 1) / 2;
-    const int nk = (K + 15) >> 4;
+    const int items = v.F * tilesMax;
     constexpr int BOXES = SWZ ? 4 : 1, BOXC = SWZ ? 16 : 64;
 
     if (warp == 4) {
         // ---------------- producer: one elected lane issues every TMA load ----------------
         if (lane != 0) return;
         int c = 0, it = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-            int I = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-            while (I * (I + 1) / 2 > t) --I;
-            while ((I + 1) * (I + 2) / 2 <= t) ++I;
-            const int J = t - I * (I + 1) / 2;
-            const int tm0 = I * 64, tn0 = J * 64;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            TdItem w;
+            if (!td_item(v, item, tilesMax, w)) continue;
             mbar_wait(pempty, (it & 1) ^ 1);
             mbar_expect_tx(pfull, kTdTileBytes);
 #pragma unroll
-            for (int j = 0; j < BOXES; ++j) tma_load_2d(Pbuf + j * (kTdTileBytes / BOXES), &maps.P, tn0 + j * BOXC, tm0, pfull);
-            const bool diag = (I == J);
-            for (int kt = 0; kt < nk; ++kt, ++c) {
+            for (int j = 0; j < BOXES; ++j) tma_load_3d(Pbuf + j * (kTdTileBytes / BOXES), &maps.P, w.tn0 + j * BOXC, w.tm0, w.f, pfull);
+            for (int kt = 0; kt < w.nk; ++kt, ++c) {
                 const int s = c % kTdStages;
                 mbar_wait(empty + s, ((c / kTdStages) & 1) ^ 1);
-                mbar_expect_tx(full + s, diag ? kTdChunkBytes : 2 * kTdChunkBytes);
+                mbar_expect_tx(full + s, w.diag ? kTdChunkBytes : 2 * kTdChunkBytes);
                 unsigned char* A = ring + s * 2 * kTdChunkBytes;
 #pragma unroll
-                for (int j = 0; j < BOXES; ++j) tma_load_2d(A + j * (kTdChunkBytes / BOXES), &maps.W, tm0 + j * BOXC, kt * 16, full + s);
-                if (!diag) {
+                for (int j = 0; j < BOXES; ++j) tma_load_3d(A + j * (kTdChunkBytes / BOXES), &maps.W, w.tm0 + j * BOXC, kt * 16, w.f, full + s);
+                if (!w.diag) {
 #pragma unroll
                     for (int j = 0; j < BOXES; ++j)
-                        tma_load_2d(A + kTdChunkBytes + j * (kTdChunkBytes / BOXES), &maps.W, tn0 + j * BOXC, kt * 16, full + s);
+                        tma_load_3d(A + kTdChunkBytes + j * (kTdChunkBytes / BOXES), &maps.W, w.tn0 + j * BOXC, kt * 16, w.f, full + s);
                 }
             }
+            ++it;
         }
         return;
     }
@@ -132,13 +150,11 @@ __global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid
     double acc[4][4][2];
     int c = 0, it = 0;
     bool storePending = false;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-        int I = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-        while (I * (I + 1) / 2 > t) --I;
-        while ((I + 1) * (I + 2) / 2 <= t) ++I;
-        const int J = t - I * (I + 1) / 2;
-        const int tm0 = I * 64, tn0 = J * 64;
-        const bool diag = (I == J);
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        TdItem w;
+        if (!td_item(v, item, tilesMax, w)) continue;
+        const int tm0 = w.tm0, tn0 = w.tn0, n = w.n;
+        const bool diag = w.diag;
         // warp tiles with no element of the lower triangle inside the matrix do no arithmetic
         const bool idle = (diag && wn > wm) || (tm0 + wm * 32 >= n) || (tn0 + wn * 32 >= n);
         // accumulators start at -P (the tile arrived by TMA)
@@ -153,7 +169,7 @@ __global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid
             }
         __syncwarp();
         if (lane == 0) mbar_arrive(pempty);     // the producer may fetch the next tile's P
-        for (int kt = 0; kt < nk; ++kt, ++c) {
+        for (int kt = 0; kt < w.nk; ++kt, ++c) {
             const int s = c % kTdStages;
             mbar_wait(full + s, (c / kTdStages) & 1);
             const unsigned char* A = ring + s * 2 * kTdChunkBytes;
@@ -178,7 +194,30 @@ __global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
         }
-        // ---- epilogue: the tile (and its mirror image) through shared memory, TMA tensor stores ----
+        ++it;
+        if (w.edge) {
+            // the tile crosses the edge of this filter's matrix: predicated stores from the registers (lower part + mirror)
+            if (!idle) {
+                double* P = v.P + (size_t)w.f * v.nmax * v.ld;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int gm = tm0 + wm * 32 + a * 8 + g;
+                    if (gm >= n) continue;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int gn = tn0 + wn * 32 + b * 8 + 2 * q + e;
+                            if (gn > gm || gn >= n) continue;
+                            const double val = -acc[a][b][e];
+                            P[(size_t)gm * v.ld + gn] = val;
+                            if (gn != gm) P[(size_t)gn * v.ld + gm] = val;
+                        }
+                }
+            }
+            continue;
+        }
+        // ---- the tile (and its mirror image) through shared memory, TMA tensor stores ----
         if (storePending) {
             if (tid == 0) tma_store_wait_read();     // the previous tile's last store has read Obuf
             bar_consumers();
@@ -200,11 +239,8 @@ __global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid
         fence_async_smem();
         bar_consumers();
         if (tid == 0) {
-            tma_store_2d(&maps.P, Obuf, tn0, tm0);
-            if (SWZ) {
 #pragma unroll
-                for (int j = 1; j < 4; ++j) tma_store_2d(&maps.P, Obuf + j * (kTdTileBytes / 4), tn0 + j * 16, tm0);
-            }
+            for (int j = 0; j < BOXES; ++j) tma_store_3d(&maps.P, Obuf + j * (kTdTileBytes / BOXES), tn0 + j * BOXC, tm0, w.f);
             tma_store_commit();
         }
         storePending = true;
@@ -224,11 +260,8 @@ __global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid
             fence_async_smem();
             bar_consumers();
             if (tid == 0) {
-                tma_store_2d(&maps.P, Obuf, tm0, tn0);
-                if (SWZ) {
 #pragma unroll
-                    for (int j = 1; j < 4; ++j) tma_store_2d(&maps.P, Obuf + j * (kTdTileBytes / 4), tm0 + j * 16, tn0);
-                }
+                for (int j = 0; j < BOXES; ++j) tma_store_3d(&maps.P, Obuf + j * (kTdTileBytes / BOXES), tm0 + j * BOXC, tn0, w.f);
                 tma_store_commit();
             }
         }

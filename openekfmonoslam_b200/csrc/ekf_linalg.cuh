@@ -1028,8 +1028,9 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
         ch = chn;
     }
     cp_async_wait<0>();
-    // W^T back to global, dx = W y
-    for (int e = tid; e < k * SW; e += blockDim.x) {
+    // W^T back to global (rows k .. end of the last 16-row chunk as zeros: the TMA-fed downdate reads whole chunks), dx = W y
+    const int kz = min(kpad, (k + 15) & ~15);
+    for (int e = tid; e < kz * SW; e += blockDim.x) {
         const int r = e / SW, c = e % SW;
         if (c0 + c < n) Bg[(size_t)r * v.ld + c0 + c] = Xs[(size_t)r * SWP + c];
     }

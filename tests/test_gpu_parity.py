@@ -117,6 +117,7 @@ def test_ransac_in_small_rounds_and_legacy_tile_options():
     round size), the 128x128 downdate tiles and the shallow TRSM ring, all against the oracle."""
     sc, orc, gpu = make_pair(640, 480, 100)
     gpu.set_option(7, 2)      # EKFB_OPT_RANSAC_CHUNK
+    gpu.set_option(2, 0)      # EKFB_OPT_DOWNDATE_VARIANT: the cp.async kernels instead of the TMA-fed default
     gpu.set_option(4, 64)     # EKFB_OPT_DOWNDATE_SMALL_K: updates with more than 64 rows use the 128x128 kernel
     gpu.set_option(5, 2)      # EKFB_OPT_TRSM_STAGES
     hyps = []
