@@ -84,6 +84,7 @@ struct ChainCtx {
     ChainCtl ctl;
     int* dm;
     int k, nbR, nbC, ldS, gen, faultInject;
+    long long* dbg;
     int wsBlock;                         // which Uinv block Ws holds (-1: none)
     int pre;                             // D(pre)'s tiles were prefetched into As / Bs (-1: none)
 };
@@ -280,6 +281,8 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3, p = w & 3, nh = w >> 2;
     const int I0 = I * kNB, k = cx.k;
+    long long* dbg = (cx.dbg != nullptr && I == 5 && tid == 0) ? cx.dbg + 48 : nullptr;   // phase clocks of one mid-chain step
+    if (dbg) { dbg[0] = clock64(); dbg[9] = cx.pre == I; }
     if (cx.pre == I) {
         double* t = cx.Ts; cx.Ts = cx.Bs; cx.Bs = t;     // T'(I, I) arrived in Bs
     } else {
@@ -295,6 +298,7 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
     cx.pre = -1;
     cp_async_wait<0>();
     __syncthreads();
+    if (dbg) dbg[1] = clock64();
     if (I > 0) {
         double x[2][4][2], xd[2][4][2];
 #pragma unroll
@@ -303,8 +307,10 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
             for (int b = 0; b < 4; ++b) x[a][b][0] = x[a][b][1] = 0.0;
         x_gemm<false>(cx.Ws, cx.As, cx.As, p, nh, g, q, x, xd);
         __syncthreads();
+        if (dbg) dbg[2] = clock64();
         store_x(cx, x, I0 - kNB, I0, cx.As, p, nh, g, q);     // X(I-1, I): to the factor buffer and, K-major, into As
         chain_signal(cx.ctl.xready(I - 1, I), cx.gen);        // (its __syncthreads also orders the writes to As)
+        if (dbg) dbg[3] = clock64();
         double acc[5][2];
 #pragma unroll
         for (int t = 0; t < 5; ++t) acc[t][0] = acc[t][1] = 0.0;
@@ -312,6 +318,7 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
         tile_sub_upper(cx.Ts, w, g, q, acc);
         __syncthreads();
     }
+    if (dbg) dbg[4] = clock64();
     // factor the diagonal tile: U_II, Uinv_I and (if nu lies in this tile) y_I
     const int kb = min(kNB, k - I0);
     const bool hasNu = (k - I0) < kNB;
@@ -335,8 +342,10 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
         cp_async_commit();
         cx.pre = I + 1;
     };
+    if (dbg) dbg[5] = clock64();
     factor_tile64(cx.Ts, cx.Ws, tid, bad, nullptr, hook);
     __syncthreads();
+    if (dbg) dbg[6] = clock64();
     cx.wsBlock = I;
     if (tid == 0 && (*bad || cx.faultInject)) cx.dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
     for (int e = tid; e < kNB * 32; e += 256) {
@@ -353,7 +362,9 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
         for (int pp = 0; pp <= tid; ++pp) s += cx.Ws[pp * kSS + tid] * cx.nu[pp];
         cx.Sf[(size_t)(I0 + tid) * cx.ldS + k] = s;
     }
+    if (dbg) dbg[7] = clock64();
     chain_signal(cx.ctl.fdone(I), cx.gen);
+    if (dbg) dbg[8] = clock64();
 }
 
 // Position p of the per-filter task queue (row-major; the D tasks are not in it): row I holds A(I, I+1) .. A(I, nbC-1), then
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(256, 1) k_schain_fused(DevView v, int* ctlBase
     cx.UinvG = v.Uinv + (size_t)f * (v.kmax / kNB) * kNB * kNB;
     cx.ctl.base = ctlBase + (size_t)f * chain_ctl_ints(nbMax);
     cx.ctl.nbMax = nbMax;
-    cx.dm = dm; cx.k = k; cx.ldS = v.ldS; cx.faultInject = v.faultInject;
+    cx.dm = dm; cx.k = k; cx.ldS = v.ldS; cx.faultInject = v.faultInject; cx.dbg = (f == 0) ? v.dbg : nullptr;
     cx.nbR = (k + kNB - 1) / kNB; cx.nbC = (k + kNB) / kNB;
     cx.wsBlock = -1; cx.pre = -1;
     if (tid == 0) {
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase
     cx.Sg = v.S; cx.Sf = v.Sf; cx.UinvG = v.Uinv;
     cx.ctl.base = ctlBase;
     cx.ctl.nbMax = nbMax;
-    cx.dm = dm; cx.k = k; cx.ldS = v.ldS; cx.faultInject = v.faultInject;
+    cx.dm = dm; cx.k = k; cx.ldS = v.ldS; cx.faultInject = v.faultInject; cx.dbg = (f == 0) ? v.dbg : nullptr;
     cx.nbR = (k + kNB - 1) / kNB; cx.nbC = (k + kNB) / kNB;
     cx.wsBlock = -1; cx.pre = -1;
     if (tid == 0) {
