@@ -222,7 +222,7 @@ def measure_fp64_peak(device):
     return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
-def run_reference(args, wl, rank, world):
+def run_reference(args, wl, rank, world, json_fd):
     """--impl reference: the reference's CPU path on this workload, rank 0 only: oracle/_ref/libref.so (the reference's own
     sources compiled against oracle/cvshim) when it was built, else the oracle port.  The timed frames are steady-state frames:
     the filter state they start from is produced by running the warm-up frames first -- on the GPU library when a device is
@@ -274,7 +274,7 @@ def run_reference(args, wl, rank, world):
                                "`steps` is the number of frames actually timed"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_wall}
-    print(json.dumps(line), flush=True)
+    emit(json_fd, line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -383,8 +383,17 @@ class Leg:
             blocks.append(ms)
         self.barrier()
         launches = gpu.kernel_launches() - l0
+        lms, lfl = gpu.downdate_launches()
         dd = gpu.downdate_stats()
         gpu.downdate_timing(False)
+        # low-innovation launches (the bulk of the flop) and high-innovation launches (few rows: bandwidth / latency bound) apart
+        if len(lms):
+            big = lfl >= 0.5 * lfl.max()
+            for name, sel in (("low_innovation", big), ("high_innovation", ~big)):
+                if sel.any():
+                    dd[name] = {"launches": int(sel.sum()), "avg_launch_ms": float(lms[sel].mean()),
+                                "algorithmic_flops_per_launch": float(lfl[sel].mean()),
+                                "tflops": float(lfl[sel].sum() / (lms[sel].sum() * 1e-3) / 1e12)}
         return blocks, gathers, launches, dd
 
     def e2e_blocks(self, R):
@@ -466,12 +475,27 @@ def run_leg(args, wl, features, rank, world, local, dev, K, W_, T0, flush):
 
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner, ...) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        run(args, json_fd)
+    finally:
+        sys.stdout.flush()
+
+
+def emit(json_fd, line):
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+
+def run(args, json_fd):
     wl = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, wl, rank, world)
+        run_reference(args, wl, rank, world, json_fd)
         return
 
     import torch
@@ -557,14 +581,16 @@ def main():
                     "what": "pinned host keypoints -> one packed H2D pair -> ekfb_step -> D2H of the records, wall clock, median block"},
             "gpu_launches": res["launches_total"], "gpu_launches_per_step": res["launches_per_step"],
             "per_rank_ms_per_step": res["per_rank_ms_per_step"], "collective_us": res["collective_us"],
-            "roofline": {"bound": "tensor", "kernel": "k_downdate64 (covariance downdate P -= W W^T: lower 64x64 tiles, 4 CTAs/SM, FP64 DMMA m8n8k4)",
+            "roofline": {"bound": "tensor", "kernel": "k_downdate_tma (covariance downdate P -= W W^T: persistent CTAs over the lower 64x64 tiles, "
+                                                     "TMA tensor loads / stores + mbarrier ring, FP64 DMMA m8n8k4)",
                          "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak if peak else None,
                          "traffic": traffic, "traffic_source": traffic_src, "launches": dd["launches"],
                          "avg_launch_ms": dd["ms"] / max(dd["launches"], 1),
                          "algorithmic_flops_per_launch": dd["flops"] / max(dd["launches"], 1),
                          "peak_source": "measured in this run: torch.matmul float64 8192^3 (cuBLAS DGEMM), best of 10; "
                                         "MEASURED_PEAKS.json has no FP64 entry",
-                         "share_of_step": dd["ms"] / res["dev_ms_total"] if res["dev_ms_total"] > 0 else None},
+                         "share_of_step": dd["ms"] / res["dev_ms_total"] if res["dev_ms_total"] > 0 else None,
+                         "by_update": {k2: dict(v2, frac=v2["tflops"] / peak) for k2, v2 in dd.items() if isinstance(v2, dict)}},
             "clocks": sampler.summary(),
             "wall_s_main_leg": wall_main,
         }
@@ -573,7 +599,7 @@ def main():
             line["parity"] = parity
         if c4 is not None:
             line["c4_sharded"] = c4
-        print(json.dumps(line), flush=True)
+        emit(json_fd, line)
     if world > 1:
         dist.destroy_process_group()
 

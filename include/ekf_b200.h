@@ -265,6 +265,9 @@ int ekfb_flush_l2(ekfb_handle h);
 int ekfb_downdate_timing(ekfb_handle h, int enable);
 int ekfb_downdate_stats(ekfb_handle h, double* ms_total, int64_t* launches, double* flops_total,
                         double* bytes_min_total);
+/* the same measurement launch by launch (call before ekfb_downdate_stats, which resets it): ms[i] / flops[i] = duration and
+ * algorithmic flop (n (n + 1) K summed over the handle's filters) of the i-th timed launch; *count = number of launches */
+int ekfb_downdate_launches(ekfb_handle h, int cap, float* ms, double* flops, int32_t* count);
 
 #ifdef __cplusplus
 }

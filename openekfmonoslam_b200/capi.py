@@ -325,6 +325,13 @@ class EkfBatch:
 
     def downdate_timing(self, on=True): self._ck(self.L.ekfb_downdate_timing(self.h, ctypes.c_int(1 if on else 0)))
 
+    def downdate_launches(self, cap=16384):
+        """(ms, flops) numpy arrays, one entry per timed downdate launch; call before downdate_stats()"""
+        ms = np.zeros(cap, np.float32); fl = np.zeros(cap, np.float64); n = ctypes.c_int32()
+        self._ck(self.L.ekfb_downdate_launches(self.h, ctypes.c_int(cap), _ptr(ms), _ptr(fl), ctypes.byref(n)))
+        k = min(n.value, cap)
+        return ms[:k], fl[:k]
+
     def downdate_stats(self):
         ms, fl, by = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         ln = ctypes.c_int64()

@@ -109,6 +109,7 @@ struct ekfb_ctx {
     std::vector<cudaEvent_t> dd_ev;   // pairs
     size_t dd_used = 0;               // events used
     double dd_flops = 0., dd_bytes = 0.;
+    std::vector<double> dd_launch_flops;   // algorithmic flop of every timed launch
     bool map_ready = false;           // map-management buffers are allocated on first use
     uint8_t* mask2 = nullptr;         // new-feature mask (E/DetectNewImageFeatures.cpp:101-122), built by ekfb_map_management
     bool mask2_valid = false;
@@ -779,6 +780,12 @@ static int launch_downdate(ekfb_ctx* c, int n, bool allowTma = true)
     if (timeIt) {
         cudaEventRecord(c->dd_ev[c->dd_used + 1], c->stream);
         c->dd_used += 2;
+        double lf = 0.;
+        for (int f = 0; f < c->F; ++f) {
+            const double nf = c->hn[f], kf = 2.0 * c->h_dims[(size_t)f * D_STRIDE + D_ULIST];
+            lf += nf * (nf + 1.0) * kf;
+        }
+        c->dd_launch_flops.push_back(lf);
         for (int f = 0; f < c->F; ++f) {
             const double nf = c->hn[f], kf = 2.0 * c->h_dims[(size_t)f * D_STRIDE + D_ULIST];
             if (kf > 0) {
@@ -1674,6 +1681,25 @@ extern "C" int ekfb_downdate_timing(ekfb_handle c, int enable)
     c->dd_timing = enable != 0;
     c->dd_used = 0;
     c->dd_flops = c->dd_bytes = 0.;
+    c->dd_launch_flops.clear();
+    return EKFB_OK;
+}
+
+// per-launch view of the same measurement (call before ekfb_downdate_stats, which resets it): duration [ms] and algorithmic
+// flop n (n + 1) K summed over the filters of every timed downdate launch, oldest first
+extern "C" int ekfb_downdate_launches(ekfb_handle c, int cap, float* ms, double* flops, int32_t* count)
+{
+    REQUIRE(c && count, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int nl = (int)std::min<size_t>(c->dd_used / 2, c->dd_launch_flops.size());
+    *count = nl;
+    for (int i = 0; i < nl && i < cap; ++i) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, c->dd_ev[2 * i], c->dd_ev[2 * i + 1]));
+        if (ms) ms[i] = t;
+        if (flops) flops[i] = c->dd_launch_flops[i];
+    }
     return EKFB_OK;
 }
 
@@ -1695,5 +1721,6 @@ extern "C" int ekfb_downdate_stats(ekfb_handle c, double* ms_total, int64_t* lau
     if (bytes_min_total) *bytes_min_total = c->dd_bytes;
     c->dd_used = 0;
     c->dd_flops = c->dd_bytes = 0.;
+    c->dd_launch_flops.clear();
     return EKFB_OK;
 }

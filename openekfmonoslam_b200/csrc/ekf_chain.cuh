@@ -62,9 +62,9 @@ __device__ __forceinline__ void chain_wait(const int* flag, int gen, int* status
 // all threads: the CTA's global stores so far become visible, then the flag is raised
 __device__ __forceinline__ void chain_signal(int* flag, int gen)
 {
-    __syncthreads();                      // every thread's stores are ordered before thread 0's fence (the pattern of a grid barrier)
-    if (threadIdx.x == 0) {
-        __threadfence();
+    __syncthreads();                      // every thread's stores are ordered before the signalling thread's fence (the pattern
+    if (threadIdx.x == blockDim.x - 1) {  // of a grid barrier).  The last thread signals: its warp idles through the in-register
+        __threadfence();                  // phases of the factorisation, so the fence latency stays off the critical warps
         st_release(flag, gen);
     }
 }
@@ -182,6 +182,18 @@ __device__ __forceinline__ void store_x(const ChainCtx& cx, const double (&x)[2]
         }
 }
 
+// X (registers, x_gemm layout) into a shared-memory tile only
+__device__ __forceinline__ void store_x_smem(const double (&x)[2][4][2], double* smemTile, int p, int nh, int g, int q)
+{
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int m = (a == 0 ? 8 * p : 8 * (7 - p)) + g, nn = 32 * nh + 8 * b + 2 * q;
+            *reinterpret_cast<double2*>(smemTile + m * kSS + nn) = make_double2(x[a][b][0], x[a][b][1]);
+        }
+}
+
 // ---- A(I, C): off-diagonal tile -------------------------------------------------------------------------------------
 __device__ void chain_task_offdiag(ChainCtx& cx, int I, int C)
 {
@@ -281,6 +293,7 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3, p = w & 3, nh = w >> 2;
     const int I0 = I * kNB, k = cx.k;
+    const bool deferX = prefetch && I > 0;
     long long* dbg = (cx.dbg != nullptr && I == 5 && tid == 0) ? cx.dbg + 48 : nullptr;   // phase clocks of one mid-chain step
     if (dbg) { dbg[0] = clock64(); dbg[9] = cx.pre == I; }
     if (cx.pre == I) {
@@ -308,8 +321,14 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
         x_gemm<false>(cx.Ws, cx.As, cx.As, p, nh, g, q, x, xd);
         __syncthreads();
         if (dbg) dbg[2] = clock64();
-        store_x(cx, x, I0 - kNB, I0, cx.As, p, nh, g, q);     // X(I-1, I): to the factor buffer and, K-major, into As
-        chain_signal(cx.ctl.xready(I - 1, I), cx.gen);        // (its __syncthreads also orders the writes to As)
+        if (deferX) {
+            // X(I-1, I) K-major into As only; it goes to the factor buffer (and its flag up) from inside the factorisation
+            store_x_smem(x, cx.As, p, nh, g, q);
+            __syncthreads();
+        } else {
+            store_x(cx, x, I0 - kNB, I0, cx.As, p, nh, g, q);     // X(I-1, I): to the factor buffer and, K-major, into As
+            chain_signal(cx.ctl.xready(I - 1, I), cx.gen);        // (its __syncthreads also orders the writes to As)
+        }
         if (dbg) dbg[3] = clock64();
         double acc[5][2];
 #pragma unroll
@@ -334,8 +353,12 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
     }
     __syncthreads();
     const bool wantNext = prefetch && (I + 1 < cx.nbR);
-    auto hook = [&]() {
-        if (!wantNext) return;
+    auto hook = [&](int b) {
+        if (b == 1 && deferX) {   // publish X(I-1, I) while the in-register Cholesky of block 1 runs (As is not touched by the factor)
+            store_tile64(cx.As, cx.Sf, cx.ldS, I0 - kNB, k, I0, k, tid);
+            chain_signal(cx.ctl.xready(I - 1, I), cx.gen);
+        }
+        if (b != 7 || !wantNext) return;
         if (!chain_peek(cx.ctl.tready(I), (I + 1 >= 2) ? cx.ctl.pdready(I + 1) : nullptr, cx.gen, sFlag)) return;
         load_tile64(cx.As, cx.Sg, cx.ldS, I0, k, I0 + kNB, k + 1, tid);
         load_tile64(cx.Bs, cx.Sg, cx.ldS, I0 + kNB, k, I0 + kNB, k + 1, tid);

@@ -128,12 +128,24 @@ __device__ __forceinline__ LLTile ll_tile(double* T, double* W, int s, int i, in
 
 __device__ __forceinline__ void ll_accumulate(const LLTile& t, int kBegin, int kEnd, double (&c)[4])
 {
-    for (int k = kBegin; k < kEnd; k += 8) {
+    // four independent accumulator pairs: the dependent DMMA chain (25 cycles per link) is a quarter of the k-range long
+    double d[4] = {0.0, 0.0, 0.0, 0.0};
+    int k = kBegin;
+    for (; k + 8 < kEnd; k += 16) {
+        const double aa0 = t.ap[k * t.astep], aa1 = t.ap[(k + 4) * t.astep], aa2 = t.ap[(k + 8) * t.astep], aa3 = t.ap[(k + 12) * t.astep];
+        const double bb0 = t.bp[k * kSS], bb1 = t.bp[(k + 4) * kSS], bb2 = t.bp[(k + 8) * kSS], bb3 = t.bp[(k + 12) * kSS];
+        dmma8x8x4(c[0], c[1], aa0, bb0);
+        dmma8x8x4(c[2], c[3], aa1, bb1);
+        dmma8x8x4(d[0], d[1], aa2, bb2);
+        dmma8x8x4(d[2], d[3], aa3, bb3);
+    }
+    if (k < kEnd) {
         const double aa0 = t.ap[k * t.astep], aa1 = t.ap[(k + 4) * t.astep];
         const double bb0 = t.bp[k * kSS], bb1 = t.bp[(k + 4) * kSS];
         dmma8x8x4(c[0], c[1], aa0, bb0);
         dmma8x8x4(c[2], c[3], aa1, bb1);
     }
+    c[0] += d[0]; c[1] += d[1]; c[2] += d[2]; c[3] += d[3];
 }
 
 __device__ __forceinline__ void ll_store(const LLTile& t, const double (&c)[4])
@@ -148,9 +160,10 @@ __device__ __forceinline__ void ll_store(const LLTile& t, const double (&c)[4])
 // valid part by identity and zeroed W): on return T holds U (upper, T = U^T U) and W holds U^-1 (upper, zeros below).
 // Called by all 256 threads: warps 0-3 do the in-register work, warps 4-7 only join the rank-8 tile updates.  *bad is set if a
 // pivot is not positive.
-struct NoHook { __device__ __forceinline__ void operator()() const {} };
+struct NoHook { __device__ __forceinline__ void operator()(int) const {} };
 
-// hook(): called by all threads once, half way through (before block step 5): lets the caller start loads for its next tile
+// hook(b): called by all threads at the start of every 8-row block step b: lets the caller overlap its own memory traffic
+// (publishing finished tiles, prefetching its next tiles) with the latency-bound factorisation
 template <typename Hook = NoHook>
 __device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int* bad, long long* dbg, Hook hook = Hook())
 {
@@ -160,7 +173,7 @@ __device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int
         const int o = 8 * b;
         if (dbg) t0 = clock64();
         double R[8][8], r[8];
-        if (b == 5) hook();
+        hook(b);
         if (b > 0) {  // bring block row b of T and column block b of U^-1 up to date: one tile per warp
             const LLTile t = ll_tile(T, W, b, w, g, q);
             double ca[4] = {0.0, 0.0, 0.0, 0.0};

@@ -48,7 +48,8 @@ def read_report(path):
     for r in rows[2:]:
         if len(r) != len(header):
             continue
-        rec = {"kernel": r[header.index("Kernel Name")], "id": int(r[header.index("ID")])}
+        name = r[header.index("Kernel Name")]
+        rec = {"kernel": name[5:] if name.startswith("void ") else name, "id": int(r[header.index("ID")])}
         for i, h in enumerate(header):
             if h in WANT and r[i] != "":
                 try:
@@ -97,6 +98,7 @@ def main():
         except Exception:
             cur = {}
         cur[workload] = per_launch
+        cur.pop("note", None)
         cur["_source"] = (f"tools/ncu_summary.py over {args}: mean of dram__bytes_read.sum + dram__bytes_write.sum of the "
                           f"{len(dd)} k_downdate launches of one frame ({[round(r['dram_bytes'] / 1e6, 1) for r in dd]} MB)")
         json.dump(cur, open(traffic_out, "w"), indent=1)
