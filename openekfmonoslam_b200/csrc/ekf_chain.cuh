@@ -293,7 +293,8 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3, p = w & 3, nh = w >> 2;
     const int I0 = I * kNB, k = cx.k;
-    const bool deferX = prefetch && I > 0;
+    const bool deferX = false;   // (publishing X(I-1, I) from inside the factorisation was measured: the helpers then deliver
+                                 // T(I, I+1) too late for the prefetch and the step gets longer, profiles/r02_chain_phase_clocks.txt)
     long long* dbg = (cx.dbg != nullptr && I == 5 && tid == 0) ? cx.dbg + 48 : nullptr;   // phase clocks of one mid-chain step
     if (dbg) { dbg[0] = clock64(); dbg[9] = cx.pre == I; }
     if (cx.pre == I) {
@@ -358,7 +359,7 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
             store_tile64(cx.As, cx.Sf, cx.ldS, I0 - kNB, k, I0, k, tid);
             chain_signal(cx.ctl.xready(I - 1, I), cx.gen);
         }
-        if (b != 7 || !wantNext) return;
+        if (b != 5 || !wantNext) return;
         if (!chain_peek(cx.ctl.tready(I), (I + 1 >= 2) ? cx.ctl.pdready(I + 1) : nullptr, cx.gen, sFlag)) return;
         load_tile64(cx.As, cx.Sg, cx.ldS, I0, k, I0 + kNB, k + 1, tid);
         load_tile64(cx.Bs, cx.Sg, cx.ldS, I0 + kNB, k, I0 + kNB, k + 1, tid);
