@@ -252,7 +252,9 @@ enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* covar
        EKFB_OPT_TRSM_PAIR = 6 /* batched filters: 1 (default) = slab footprint that lets two CTAs share an SM when possible */,
        EKFB_OPT_RANSAC_CHUNK = 7 /* RANSAC hypotheses evaluated per round (0 = default: 16 single filter, 4 batched) */,
        EKFB_OPT_PDL = 8 /* 1 (default): the frame's kernels are launched with programmatic stream serialisation */,
-       EKFB_OPT_FAULT_INJECT = 9 /* test hook: 1 = the next factorisations report a non-positive pivot (EKFB_ERR_NUMERIC path) */ };
+       EKFB_OPT_FAULT_INJECT = 9 /* test hook: 1 = the next factorisations report a non-positive pivot (EKFB_ERR_NUMERIC path) */,
+       EKFB_OPT_SMALL_UPDATE = 10 /* 1 (default): updates of at most 128 rows run factorisation + slab TRSM in one launch, the
+                                     factorisation redone by every slab CTA (ekf_update_small.cuh); 0 = per-block-step launches */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

@@ -5,8 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "ekf_b200.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("ekf_b200.cu", "ekf_linalg.cuh", "ekf_schain.cuh", "ekf_kernels.cuh", "ekf_raster.cuh",
-                                                 "ekf_math.cuh", "ekf_map.cuh", "ekf_ncc.cuh", "ekf_frontend.cuh", "ekf_brief_pattern.h")] + \
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))) + \
        [os.path.join(HERE, "..", "include", "ekf_b200.h")]
 OUT_DIR = os.path.join(HERE, "lib")
 OUT = os.path.join(OUT_DIR, "libekf_b200.so")

@@ -18,6 +18,7 @@
 #include "ekf_ncc.cuh"
 #include "ekf_frontend.cuh"
 #include "ekf_downdate_tma.cuh"
+#include "ekf_update_small.cuh"
 
 using namespace ekf;
 
@@ -102,6 +103,9 @@ struct ekfb_ctx {
                               // (ekf_schain.cuh), 1 = panel + trail launches, 3 = the whole chain in one launch (ekf_chain.cuh),
                               // 4 = chain + slab TRSM in one launch (single filter)
     int schain_eff = 0;       // the variant the current update uses
+    int small_update = 1;     // updates of at most 128 rows: factorisation + slab TRSM in one launch, the factorisation redone by
+                              // every slab CTA (ekf_update_small.cuh; option 10).  Batches use it while the slab CTAs of all
+                              // filters fit in two waves (beyond that the redundant factorisations cost more than the launches)
     void* tmaEncode = nullptr;   // cuTensorMapEncodeTiled (driver entry point, fetched once; no link against libcuda)
     int* chainCtl = nullptr;  // per-filter control blocks of the one-launch chain (generation, queue, flags)
     int nbMax = 0;
@@ -337,6 +341,7 @@ static int create_impl(const ekfb_params* p, int device, int n_filters, int max_
     }
     CK(cudaFuncSetAttribute(k_update_fused<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_fused<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CK(cudaFuncSetAttribute(k_update_small<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_small_smem_bytes(24)));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(k_trsm_slab<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -865,7 +870,13 @@ static int run_update(ekfb_ctx* c, int which)
         // automatic choice (measured on B200, profiles/r02_chain_downdate_variants.txt): the fused launch wins once the chain has
         // three or more block steps; below that (and for batches) one launch per block step is faster
         c->schain_eff = c->schain_variant >= 0 ? c->schain_variant : ((fusedOk && k > 128) ? 4 : 0);
-        if (c->schain_eff == 4 && fusedOk) {
+        const bool smallOk = c->small_update && c->schain_variant < 0 && !c->force_generic && k <= 2 * kNB &&
+                             (long long)c->F * cdiv(n, 24) <= 2ll * c->smCount;
+        if (smallOk) {
+            // small update: every slab CTA factors S itself, then solves its slab (ekf_update_small.cuh)
+            CK(launch_pdl(k_update_small<24>, dim3(cdiv(n, 24), c->F), dim3(256), update_small_smem_bytes(24), c->stream, v));
+            count_launch(c);
+        } else if (c->schain_eff == 4 && fusedOk) {
             const size_t sm = std::max<size_t>(kChainSmem, trsm_smem_bytes(k, 24, fusedNS));
             if (fusedNS == 3)
                 CK(launch_pdl(k_update_fused<24, 3>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
@@ -1636,7 +1647,8 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_FAULT_INJECT, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_SMALL_UPDATE, "unknown option");
+    if (option == EKFB_OPT_SMALL_UPDATE) { c->small_update = value; return EKFB_OK; }
     if (option == EKFB_OPT_FAULT_INJECT) { c->v.faultInject = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
     if (option == EKFB_OPT_TRSM_STAGES) { c->trsm_stages = value; return EKFB_OK; }

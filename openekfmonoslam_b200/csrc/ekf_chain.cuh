@@ -22,6 +22,10 @@
 
 namespace ekf {
 
+#ifndef CHAIN_ABSORB_UPDATE
+#define CHAIN_ABSORB_UPDATE 0   /* measured (profiles/r02_chain_phase_clocks.txt): the extra DMMAs land on the critical path of every block step of the factorisation: 28.9 k -> 33.0 k cycles per 64-row step */
+#endif
+
 // per-filter control block in global memory (ints): generation, ticket and queue counters, then the flags.  A flag is "set" when
 // it holds the current generation, so nothing is cleared between launches; k_chain_finish advances the generation.
 constexpr int CH_GEN = 0, CH_TICKET = 1, CH_QUEUE = 2, CH_FLAGS = 4;
@@ -76,10 +80,11 @@ __device__ __forceinline__ bool chain_peek(const int* flagA, const int* flagB, i
     return *sFlag != 0;
 }
 
-constexpr int kChainSmem = (4 * kNB * kSS + 2 * kNB) * (int)sizeof(double);
+constexpr int kChainSmem = (5 * kNB * kSS + 2 * kNB) * (int)sizeof(double);
 
 struct ChainCtx {
     double *Ws, *As, *Bs, *Ts, *nu;     // shared-memory tiles (pitch kSS)
+    double *A2;                         // fifth tile: the critical CTA prefetches T(I, I+1) into it while As still feeds the factorisation
     double *Sg, *Sf, *UinvG;            // this filter's S, factor buffer, diagonal-block inverses
     ChainCtl ctl;
     int* dm;
@@ -293,12 +298,18 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, q = lane & 3, p = w & 3, nh = w >> 2;
     const int I0 = I * kNB, k = cx.k;
+    const int kb = min(kNB, k - I0);
+    const bool hasNu = (k - I0) < kNB;
+    // T(I, I) -= X(I-1, I)^T X(I-1, I) is folded into the factorisation's left-looking tile updates (factor_tile64, Xp) unless the
+    // innovation column lies in this tile (the last block: its nu entries are needed, fully updated, before the factorisation)
+    const bool absorb = (I > 0) && !hasNu && CHAIN_ABSORB_UPDATE;
     const bool deferX = false;   // (publishing X(I-1, I) from inside the factorisation was measured: the helpers then deliver
                                  // T(I, I+1) too late for the prefetch and the step gets longer, profiles/r02_chain_phase_clocks.txt)
     long long* dbg = (cx.dbg != nullptr && I == 5 && tid == 0) ? cx.dbg + 48 : nullptr;   // phase clocks of one mid-chain step
     if (dbg) { dbg[0] = clock64(); dbg[9] = cx.pre == I; }
     if (cx.pre == I) {
-        double* t = cx.Ts; cx.Ts = cx.Bs; cx.Bs = t;     // T'(I, I) arrived in Bs
+        double* t = cx.Ts; cx.Ts = cx.Bs; cx.Bs = t;     // T'(I, I) arrived in Bs,
+        t = cx.As; cx.As = cx.A2; cx.A2 = t;             // T(I-1, I) in A2
     } else {
         if (I > 0) {
             chain_wait(cx.ctl.tready(I - 1), cx.gen, cx.dm + D_STATUS);
@@ -331,17 +342,17 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
             chain_signal(cx.ctl.xready(I - 1, I), cx.gen);        // (its __syncthreads also orders the writes to As)
         }
         if (dbg) dbg[3] = clock64();
-        double acc[5][2];
+        if (!absorb) {
+            double acc[5][2];
 #pragma unroll
-        for (int t = 0; t < 5; ++t) acc[t][0] = acc[t][1] = 0.0;
-        tile_mma_upper(cx.As, w, g, q, acc);
-        tile_sub_upper(cx.Ts, w, g, q, acc);
-        __syncthreads();
+            for (int t = 0; t < 5; ++t) acc[t][0] = acc[t][1] = 0.0;
+            tile_mma_upper(cx.As, w, g, q, acc);
+            tile_sub_upper(cx.Ts, w, g, q, acc);
+            __syncthreads();
+        }
     }
     if (dbg) dbg[4] = clock64();
     // factor the diagonal tile: U_II, Uinv_I and (if nu lies in this tile) y_I
-    const int kb = min(kNB, k - I0);
-    const bool hasNu = (k - I0) < kNB;
     if (hasNu && tid < kNB) cx.nu[tid] = (tid < kb) ? cx.Ts[tid * kSS + kb] : 0.0;
     __syncthreads();
     for (int e = tid; e < kNB * 32; e += 256) {   // identity outside the valid part; W starts at zero
@@ -361,13 +372,13 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
         }
         if (b != 5 || !wantNext) return;
         if (!chain_peek(cx.ctl.tready(I), (I + 1 >= 2) ? cx.ctl.pdready(I + 1) : nullptr, cx.gen, sFlag)) return;
-        load_tile64(cx.As, cx.Sg, cx.ldS, I0, k, I0 + kNB, k + 1, tid);
+        load_tile64(cx.A2, cx.Sg, cx.ldS, I0, k, I0 + kNB, k + 1, tid);
         load_tile64(cx.Bs, cx.Sg, cx.ldS, I0 + kNB, k, I0 + kNB, k + 1, tid);
         cp_async_commit();
         cx.pre = I + 1;
     };
     if (dbg) dbg[5] = clock64();
-    factor_tile64(cx.Ts, cx.Ws, tid, bad, nullptr, hook);
+    factor_tile64(cx.Ts, cx.Ws, tid, bad, nullptr, hook, absorb ? cx.As : nullptr, (kb + 7) >> 3);
     __syncthreads();
     if (dbg) dbg[6] = clock64();
     cx.wsBlock = I;
@@ -419,6 +430,7 @@ __global__ void __launch_bounds__(256, 1) k_schain_fused(DevView v, int* ctlBase
     if (k == 0) return;
     ChainCtx cx;
     cx.Ws = csm; cx.As = cx.Ws + kNB * kSS; cx.Bs = cx.As + kNB * kSS; cx.Ts = cx.Bs + kNB * kSS; cx.nu = cx.Ts + kNB * kSS;
+    cx.A2 = cx.nu + 2 * kNB;
     cx.Sg = v.S + (size_t)f * v.kmax * v.ldS;
     cx.Sf = v.Sf + (size_t)f * v.kmax * v.ldS;
     cx.UinvG = v.Uinv + (size_t)f * (v.kmax / kNB) * kNB * kNB;
@@ -615,6 +627,7 @@ __global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase
     if (k == 0) return;
     ChainCtx cx;
     cx.Ws = csm; cx.As = cx.Ws + kNB * kSS; cx.Bs = cx.As + kNB * kSS; cx.Ts = cx.Bs + kNB * kSS; cx.nu = cx.Ts + kNB * kSS;
+    cx.A2 = cx.nu + 2 * kNB;
     cx.Sg = v.S; cx.Sf = v.Sf; cx.UinvG = v.Uinv;
     cx.ctl.base = ctlBase;
     cx.ctl.nbMax = nbMax;

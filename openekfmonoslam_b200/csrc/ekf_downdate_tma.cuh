@@ -7,8 +7,8 @@
 //     coordinate is the filter): the P tile (64 x 64) into a staging buffer and the K-major operand chunks of W^T (16 rows x
 //     64 columns for the tile's rows and for its columns) into a 3-stage ring -- full / empty mbarriers, no __syncthreads
 //     and no cp.async address arithmetic in the four CONSUMER warps;
-//   * 128-byte swizzled boxes (16 doubles wide) + a row permutation inside the 16-row chunk make every DMMA fragment
-//     load bank-conflict free without padding (TMA writes dense boxes);
+//   * 128-byte swizzled boxes (16 doubles wide) + a row permutation inside the 16-row chunk ({0,2,4,6}, {1,3,5,7}, ... per
+//     k-step) make every DMMA fragment load bank-conflict free without padding (TMA writes dense boxes);
 //   * the updated tile leaves through shared memory as TMA tensor stores, and its mirror image as a second set
 //     (transposed in shared memory), so both triangles are written as full 128-byte rows: P stays exactly symmetric
 //     (the two stores carry bit-identical values) and no thread issues a strided global store.  Tiles that cross the edge
@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(160, 2) k_downdate_tma(DevView v, const __grid
             if (!idle) {
 #pragma unroll
                 for (int st = 0; st < 4; ++st) {
-                    // rows of this k-step: {0,1,4,5}, {2,3,6,7}, {8,9,12,13}, {10,11,14,15}: two rows in each half of the
-                    // 128-byte swizzle period, so the four rows of a fragment load hit disjoint bank halves pairwise
-                    const int r = ((st >> 1) << 3) + ((st & 1) << 1) + (q & 1) + ((q >> 1) << 2);
+                    // rows of this k-step: {0,2,4,6}, {1,3,5,7}, {8,10,12,14}, {9,11,13,15}.  An 8-byte fragment load is served per
+                    // half-warp (g = 0..3 | 4..7: two 16-byte chunks of each of the four rows); with the swizzle XORing the
+                    // chunk index with (row & 7), rows of equal parity put those chunk pairs on eight different chunks, i.e.
+                    // all 32 banks exactly once ({0,1,4,5} collided pairwise: ncu counted one conflict per wavefront)
+                    const int r = ((st >> 1) << 3) + (st & 1) + (q << 1);
                     double af[4], bf[4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) af[a] = *reinterpret_cast<const double*>(A + td_off<SWZ>(r, wm * 32 + a * 8 + g, 16));

@@ -164,20 +164,34 @@ struct NoHook { __device__ __forceinline__ void operator()(int) const {} };
 
 // hook(b): called by all threads at the start of every 8-row block step b: lets the caller overlap its own memory traffic
 // (publishing finished tiles, prefetching its next tiles) with the latency-bound factorisation
+// Xp != nullptr: a K-major 64x64 tile X whose product X^T X is still to be subtracted from T (the previous block row of the
+// blocked factorisation): it is folded into the left-looking tile updates -- block row b of T gets its share right before it
+// is needed -- instead of costing a separate 64^3 product in front of the factorisation.
+// nblk < 8: only the leading 8 * nblk rows are factored -- the caller guarantees that the rest of T is the identity padding
+// (then U and U^-1 are the identity there: W gets ones on that part of its diagonal and the remaining block steps are skipped).
 template <typename Hook = NoHook>
-__device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int* bad, long long* dbg, Hook hook = Hook())
+__device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int* bad, long long* dbg, Hook hook = Hook(),
+                                              const double* Xp = nullptr, int nblk = 8)
 {
+    if (tid >= 8 * nblk && tid < kNB) W[tid * kSS + tid] = 1.0;   // (disjoint from everything the block steps below touch)
     long long tA = 0, tB = 0, tC = 0, t0 = 0;
     const int lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < nblk; ++b) {
         const int o = 8 * b;
         if (dbg) t0 = clock64();
         double R[8][8], r[8];
         hook(b);
-        if (b > 0) {  // bring block row b of T and column block b of U^-1 up to date: one tile per warp
+        if (b > 0 || Xp != nullptr) {  // bring block row b of T and column block b of U^-1 up to date: one tile per warp
             const LLTile t = ll_tile(T, W, b, w, g, q);
             double ca[4] = {0.0, 0.0, 0.0, 0.0};
-            ll_accumulate(t, t.k0, o, ca);
+            if (b > 0) ll_accumulate(t, t.k0, o, ca);
+            if (Xp != nullptr && !t.inv) {
+                LLTile tx = t;
+                tx.ap = Xp + q * kSS + o + g;
+                tx.astep = kSS;
+                tx.bp = Xp + q * kSS + 8 * (b + w) + g;
+                ll_accumulate(tx, 0, kNB, ca);
+            }
             ll_store(t, ca);
             __syncthreads();
         }
@@ -412,7 +426,7 @@ __global__ void __launch_bounds__(256, 1) k_schain_step(DevView v, int J)
     }
     __syncthreads();
     if (dbg) dbg[6] = clock64();
-    factor_tile64(Ts, Ws, tid, &bad, dbg ? dbg + 8 : nullptr);
+    factor_tile64(Ts, Ws, tid, &bad, dbg ? dbg + 8 : nullptr, NoHook(), nullptr, (kb + 7) >> 3);
     __syncthreads();
     if (dbg) dbg[4] = clock64();
     if (tid == 0 && (bad || v.faultInject)) dm[D_STATUS] = 4;  // EKFB_ERR_NUMERIC
