@@ -254,7 +254,11 @@ enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* covar
        EKFB_OPT_PDL = 8 /* 1 (default): the frame's kernels are launched with programmatic stream serialisation */,
        EKFB_OPT_FAULT_INJECT = 9 /* test hook: 1 = the next factorisations report a non-positive pivot (EKFB_ERR_NUMERIC path) */,
        EKFB_OPT_SMALL_UPDATE = 10 /* 1 (default): updates of at most 128 rows run factorisation + slab TRSM in one launch, the
-                                     factorisation redone by every slab CTA (ekf_update_small.cuh); 0 = per-block-step launches */ };
+                                     factorisation redone by every slab CTA (ekf_update_small.cuh); 0 = per-block-step launches */,
+       EKFB_OPT_LANES = 11 /* batched handles: the filters run as this many lanes on their own streams, interleaved by ekfb_step
+                              (0 / -1 = automatic: 2 for 8 or more filters; 1 = off) */,
+       EKFB_OPT_DOWNDATE_CTAS = 12 /* persistent CTAs per SM of the TMA-fed downdate: 2 (default) or 1 (leaves half of every SM
+                                      to the kernels of another lane / stream) */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

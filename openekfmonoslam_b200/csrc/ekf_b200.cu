@@ -53,6 +53,19 @@ struct SeqDev {
     std::vector<int> off;
 };
 
+// A lane = a contiguous range of the handle's filters that runs its frame on its own stream (batched handles only): the
+// latency-bound phases of one lane (factorisation steps, RANSAC, the host's two reads of the counters) overlap the
+// throughput-bound phases (covariance downdate) of the other.  See step_lanes.
+struct Lane {
+    int f0 = 0, F = 0;
+    cudaStream_t stream = nullptr;   // lane 0 runs on the handle's stream
+    cudaEvent_t done = nullptr;
+    std::vector<int> hn, hN, hKp;
+    DevView v;
+    int seq = 0, chunk0 = 0;
+    bool pending = false;
+};
+
 struct ekfb_ctx {
     ekfb_params prm;
     int device = 0, F = 0, Nmax = 0, nmax = 0, ld = 0, Kpmax = 0, kmax = 0, ldS = 0, supWords = 0;
@@ -103,6 +116,10 @@ struct ekfb_ctx {
                               // (ekf_schain.cuh), 1 = panel + trail launches, 3 = the whole chain in one launch (ekf_chain.cuh),
                               // 4 = chain + slab TRSM in one launch (single filter)
     int schain_eff = 0;       // the variant the current update uses
+    int dd_ctas_per_sm = 2;   // persistent CTAs per SM of the TMA-fed downdate (option 12)
+    int lanes_opt = -1;       // lanes per handle (option 11): -1 = automatic (2 for 8 or more filters), 1 = off
+    std::vector<Lane> lanes;
+    cudaEvent_t evLaneFork = nullptr;
     int small_update = 1;     // updates of at most 128 rows: factorisation + slab TRSM in one launch, the factorisation redone by
                               // every slab CTA (ekf_update_small.cuh; option 10).  Batches use it while the slab CTAs of all
                               // filters fit in two waves (beyond that the redundant factorisations cost more than the launches)
@@ -361,6 +378,11 @@ extern "C" int ekfb_destroy(ekfb_handle c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocs) cudaFree(p);
+    for (Lane& L : c->lanes) {
+        if (L.stream && L.stream != c->stream) cudaStreamDestroy(L.stream);
+        if (L.done) cudaEventDestroy(L.done);
+    }
+    if (c->evLaneFork) cudaEventDestroy(c->evLaneFork);
     for (SeqDev& s : c->seq) {
         if (s.xy) cudaFree(s.xy);
         if (s.desc) cudaFree(s.desc);
@@ -695,27 +717,47 @@ extern "C" int ekfb_match(ekfb_handle c)
     return EKFB_OK;
 }
 
+// hypotheses per round: the adaptive cap of the reference's rule collapses to 2-5 once a majority hypothesis is seen, so
+// batches (where surplus hypotheses cost real throughput) go four at a time, a single filter (latency) sixteen
+static int ransac_chunk_len(const ekfb_ctx* c) { return c->ransac_chunk > 0 ? std::min(c->ransac_chunk, 64) : (c->F >= 8 ? 4 : 16); }
+
+// one round: hypotheses chunk0 .. chunk0 + CH - 1 of every filter, then the sequential acceptance rule; *seq = the sequence
+// number the counters will be published under
+static int ransac_launch(ekfb_ctx* c, int chunk0, int* seq)
+{
+    const int CH = ransac_chunk_len(c);
+    CK(launch_k(c, k_ransac_hyp, dim3(CH, c->F, cdiv(c->Nmax, kHypFeat)), dim3(416), 0, c->v, chunk0));
+    *seq = ++c->dims_seq;
+    CK(launch_k(c, k_ransac_select, dim3(c->F), dim3(256), 0, c->v, chunk0, CH, *seq));
+    count_launch(c, 2);
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
+// waits for the counters of the round; *done = every filter has finished (or no hypotheses are left)
+static int ransac_collect(ekfb_ctx* c, int seq, int chunk0, bool* done)
+{
+    int rc = wait_published_dims(c, seq);
+    if (rc != EKFB_OK) return rc;
+    bool all = true;
+    for (int f = 0; f < c->F; ++f) all = all && c->h_dims[(size_t)f * D_STRIDE + D_RANSAC_DONE];
+    *done = all || chunk0 + ransac_chunk_len(c) >= std::max(max_of(c->hN), 1);
+    return EKFB_OK;
+}
+
 extern "C" int ekfb_ransac(ekfb_handle c)
 {
     REQUIRE(c, "null handle");
     CK(cudaSetDevice(c->device));
     GroupScope gs(c, G_RANSAC);
-    // hypotheses per round: the adaptive cap of the reference's rule collapses to 2-5 once a majority hypothesis is seen, so
-    // batches (where surplus hypotheses cost real throughput) go four at a time, a single filter (latency) sixteen
-    const int CH = c->ransac_chunk > 0 ? std::min(c->ransac_chunk, 64) : (c->F >= 8 ? 4 : 16);
-    const int n = max_of(c->hn), N = max_of(c->hN);
-    (void)n;
-    for (int chunk0 = 0; chunk0 < std::max(N, 1); chunk0 += CH) {
-        CK(launch_k(c, k_ransac_hyp, dim3(CH, c->F, cdiv(c->Nmax, kHypFeat)), dim3(416), 0, c->v, chunk0));
-        const int seq = ++c->dims_seq;
-        CK(launch_k(c, k_ransac_select, dim3(c->F), dim3(256), 0, c->v, chunk0, CH, seq));
-        count_launch(c, 2);
-        CK(cudaGetLastError());
-        int rc = wait_published_dims(c, seq);
+    const int CH = ransac_chunk_len(c);
+    for (int chunk0 = 0;; chunk0 += CH) {
+        int seq = 0;
+        bool done = false;
+        int rc = ransac_launch(c, chunk0, &seq);
+        if (rc == EKFB_OK) rc = ransac_collect(c, seq, chunk0, &done);
         if (rc != EKFB_OK) return rc;
-        bool all = true;
-        for (int f = 0; f < c->F; ++f) all = all && c->h_dims[(size_t)f * D_STRIDE + D_RANSAC_DONE];
-        if (all) break;
+        if (done) break;
     }
     return EKFB_OK;
 }
@@ -753,7 +795,7 @@ static int launch_downdate(ekfb_ctx* c, int n, bool allowTma = true)
             return EKFB_ERR_CUDA;
         }
         const int nT = cdiv(n, 64), tilesMax = nT * (nT + 1) / 2;
-        const dim3 grid((unsigned)std::min<long long>((long long)tilesMax * c->F, 2ll * c->smCount));
+        const dim3 grid((unsigned)std::min<long long>((long long)tilesMax * c->F, (long long)c->dd_ctas_per_sm * c->smCount));
         if (swz) CK(launch_k(c, k_downdate_tma<true>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps, tilesMax));
         else CK(launch_k(c, k_downdate_tma<false>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps, tilesMax));
     } else if (c->downdate_variant == 1)
@@ -948,17 +990,25 @@ extern "C" int ekfb_update(ekfb_handle c, int which)
     return run_update(c, which);
 }
 
+static int rescue_launch(ekfb_ctx* c, int* seq)
+{
+    int rc = launch_measure(c, 1);
+    if (rc != EKFB_OK) return rc;
+    *seq = ++c->dims_seq;
+    CK(launch_k(c, k_rescue_gate, dim3(c->F), dim3(256), 0, c->v, *seq));
+    count_launch(c);
+    CK(cudaGetLastError());
+    return EKFB_OK;
+}
+
 extern "C" int ekfb_rescue(ekfb_handle c)
 {
     REQUIRE(c, "null handle");
     CK(cudaSetDevice(c->device));
     GroupScope gs(c, G_RESCUE);
-    int rc = launch_measure(c, 1);
+    int seq = 0;
+    int rc = rescue_launch(c, &seq);
     if (rc != EKFB_OK) return rc;
-    const int seq = ++c->dims_seq;
-    CK(launch_k(c, k_rescue_gate, dim3(c->F), dim3(256), 0, c->v, seq));
-    count_launch(c);
-    CK(cudaGetLastError());
     return wait_published_dims(c, seq);
 }
 
@@ -1398,9 +1448,139 @@ extern "C" int ekfb_ncc_get_scores(ekfb_handle c, int f, double* score, int32_t*
     return EKFB_OK;
 }
 
+// the view of filters f0 .. f0 + cnt - 1: every filter-major array starts at its f0-th slice
+static DevView lane_view(const ekfb_ctx* c, int f0, int cnt)
+{
+    DevView s = c->v;
+    s.F = cnt;
+    const size_t f = (size_t)f0, N = (size_t)c->Nmax;
+#define LANE_OFF(p, stride) do { if (s.p) s.p += f * (size_t)(stride); } while (0)
+    LANE_OFF(x, c->ld); LANE_OFF(P, (size_t)c->nmax * c->ld);
+    LANE_OFF(ftype, N); LANE_OFF(foff, N); LANE_OFF(desc, N * 32); LANE_OFF(tpred, N); LANE_OFF(tmatch, N); LANE_OFF(dims, D_STRIDE);
+    LANE_OFF(vis, N); LANE_OFF(h, N * 2); LANE_OFF(Si, N * 4); LANE_OFF(Hx, N * 14); LANE_OFF(Hf, N * 12); LANE_OFF(ellax, N * 2); LANE_OFF(ellang, N);
+    LANE_OFF(vis2, N); LANE_OFF(h2, N * 2); LANE_OFF(Si2, N * 4); LANE_OFF(Hx2, N * 14); LANE_OFF(Hf2, N * 12);
+    LANE_OFF(mflag, N); LANE_OFF(z, N * 2); LANE_OFF(mkp, N); LANE_OFF(mdist, N); LANE_OFF(mlist, N);
+    LANE_OFF(inl, N); LANE_OFF(outl, N); LANE_OFF(resc, N); LANE_OFF(ulist, N);
+    LANE_OFF(kpxy, 1); LANE_OFF(kpdesc, 1); LANE_OFF(kpok, c->Kpmax); LANE_OFF(mask, (size_t)s.W * s.H);
+    LANE_OFF(hypcount, N); LANE_OFF(hypsup, N * c->supWords);
+    LANE_OFF(Bu, (size_t)c->kmax * c->ld); LANE_OFF(S, (size_t)c->kmax * c->ldS); LANE_OFF(Sf, (size_t)c->kmax * c->ldS); LANE_OFF(dx, c->ld);
+    LANE_OFF(Jq, 16); LANE_OFF(Uinv, (size_t)(c->kmax / kNB) * kNB * kNB);
+    LANE_OFF(hostDims, D_STRIDE); LANE_OFF(hostFlag, 1);
+#undef LANE_OFF
+    return s;
+}
+
+// while alive, the handle IS the lane: view, filter count, stream and the host mirrors are the lane's, so the phase functions
+// run unchanged on the lane's filters
+struct LaneScope {
+    ekfb_ctx* c;
+    Lane* L;
+    DevView v0;
+    int F0;
+    cudaStream_t s0;
+    LaneScope(ekfb_ctx* c_, Lane* L_) : c(c_), L(L_), v0(c_->v), F0(c_->F), s0(c_->stream)
+    {
+        c->v = L->v; c->F = L->F; c->stream = L->stream;
+        std::swap(c->hn, L->hn); std::swap(c->hN, L->hN); std::swap(c->hKp, L->hKp);
+        shift(+1);
+    }
+    ~LaneScope()
+    {
+        shift(-1);
+        std::swap(c->hn, L->hn); std::swap(c->hN, L->hN); std::swap(c->hKp, L->hKp);
+        c->v = v0; c->F = F0; c->stream = s0;
+    }
+    void shift(int sign)
+    {
+        const ptrdiff_t f = (ptrdiff_t)sign * L->f0;
+        c->h_dims += f * D_STRIDE; c->h_dims_zc += f * D_STRIDE; c->h_flag_zc += f;
+        c->chainCtl += f * (ptrdiff_t)chain_ctl_ints(c->nbMax);
+    }
+};
+
+static int lanes_wanted(const ekfb_ctx* c)
+{
+    if (c->prof) return 1;   // the per-group timers bracket one stream
+    const int want = c->lanes_opt > 0 ? c->lanes_opt : (c->F >= 8 ? 2 : 1);
+    return std::max(1, std::min(want, c->F));
+}
+
+// The frame of a batched handle as `nl` lanes on `nl` streams, interleaved phase by phase by this one host thread: while the host
+// waits for lane A's counters (RANSAC, rescue) lane B's kernels are already queued, and on the device the short latency-bound
+// kernels of one lane run beside the covariance downdate of the other.  Same kernels, same per-filter results.
+static int step_lanes(ekfb_ctx* c, int nl)
+{
+    CK(cudaSetDevice(c->device));
+    if ((int)c->lanes.size() != nl) {
+        for (Lane& L : c->lanes) {
+            if (L.stream && L.stream != c->stream) cudaStreamDestroy(L.stream);
+            if (L.done) cudaEventDestroy(L.done);
+        }
+        c->lanes.assign(nl, Lane());
+        for (int i = 0; i < nl; ++i) {
+            Lane& L = c->lanes[i];
+            L.f0 = (int)((long long)c->F * i / nl);
+            L.F = (int)((long long)c->F * (i + 1) / nl) - L.f0;
+            if (i == 0) L.stream = c->stream;
+            else CK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        }
+        if (!c->evLaneFork) CK(cudaEventCreateWithFlags(&c->evLaneFork, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->evLaneFork, c->stream));
+    for (Lane& L : c->lanes) {
+        if (L.stream != c->stream) CK(cudaStreamWaitEvent(L.stream, c->evLaneFork, 0));
+        L.v = lane_view(c, L.f0, L.F);
+        L.hn.assign(c->hn.begin() + L.f0, c->hn.begin() + L.f0 + L.F);
+        L.hN.assign(c->hN.begin() + L.f0, c->hN.begin() + L.f0 + L.F);
+        L.hKp.assign(c->hKp.begin() + L.f0, c->hKp.begin() + L.f0 + L.F);
+    }
+    int rc;
+    for (Lane& L : c->lanes) {
+        LaneScope ls(c, &L);
+        if ((rc = ekfb_predict(c)) != EKFB_OK) return rc;
+        if ((rc = ekfb_measure(c)) != EKFB_OK) return rc;
+        if ((rc = ekfb_match(c)) != EKFB_OK) return rc;
+        L.chunk0 = 0;
+        if ((rc = ransac_launch(c, 0, &L.seq)) != EKFB_OK) return rc;
+        L.pending = true;
+    }
+    for (bool any = true; any;) {
+        any = false;
+        for (Lane& L : c->lanes) {
+            if (!L.pending) continue;
+            LaneScope ls(c, &L);
+            bool done = false;
+            if ((rc = ransac_collect(c, L.seq, L.chunk0, &done)) != EKFB_OK) return rc;
+            if (!done) {
+                L.chunk0 += ransac_chunk_len(c);
+                if ((rc = ransac_launch(c, L.chunk0, &L.seq)) != EKFB_OK) return rc;
+                any = true;
+                continue;
+            }
+            L.pending = false;
+            if ((rc = ekfb_update(c, 0)) != EKFB_OK) return rc;
+            if ((rc = rescue_launch(c, &L.seq)) != EKFB_OK) return rc;
+        }
+    }
+    for (Lane& L : c->lanes) {
+        LaneScope ls(c, &L);
+        if ((rc = wait_published_dims(c, L.seq)) != EKFB_OK) return rc;
+        if ((rc = ekfb_update(c, 1)) != EKFB_OK) return rc;
+        if ((rc = ekfb_update_map_features(c)) != EKFB_OK) return rc;
+        if (L.stream != ls.s0) CK(cudaEventRecord(L.done, L.stream));
+    }
+    for (Lane& L : c->lanes)
+        if (L.stream != c->stream) CK(cudaStreamWaitEvent(c->stream, L.done, 0));
+    return EKFB_OK;
+}
+
 extern "C" int ekfb_step(ekfb_handle c)
 {
     int rc;
+    REQUIRE(c, "null handle");
+    const int nl = lanes_wanted(c);
+    if (nl > 1) return step_lanes(c, nl);
     if ((rc = ekfb_predict(c)) != EKFB_OK) return rc;
     if ((rc = ekfb_measure(c)) != EKFB_OK) return rc;
     if ((rc = ekfb_match(c)) != EKFB_OK) return rc;
@@ -1647,8 +1827,10 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_SMALL_UPDATE, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_DOWNDATE_CTAS, "unknown option");
     if (option == EKFB_OPT_SMALL_UPDATE) { c->small_update = value; return EKFB_OK; }
+    if (option == EKFB_OPT_LANES) { c->lanes_opt = value; return EKFB_OK; }
+    if (option == EKFB_OPT_DOWNDATE_CTAS) { c->dd_ctas_per_sm = value == 1 ? 1 : 2; return EKFB_OK; }
     if (option == EKFB_OPT_FAULT_INJECT) { c->v.faultInject = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
     if (option == EKFB_OPT_TRSM_STAGES) { c->trsm_stages = value; return EKFB_OK; }

@@ -323,12 +323,13 @@ def test_one_launch_chain_batched_filters():
             assert gpu.frame_info(f)["status"] == 0
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4])
+@pytest.mark.parametrize("variant", [-1, 0, 3, 4])
 def test_numeric_failure_leaves_the_filter_untouched(variant):
     """EKFB_ERR_NUMERIC: when the factorisation of an innovation covariance reports a non-positive pivot (injected here with
     EKFB_OPT_FAULT_INJECT; the reference inverts S by LU, E/Update.cpp:108, and cannot fail this way) the frame's status is set
     and that update -- and the rest of the frame's updates -- are skipped: state and covariance stay exactly as the
-    prediction left them.  The next frame starts clean; `reserved` keeps the sticky flag."""
+    prediction left them.  The next frame starts clean; `reserved` keeps the sticky flag.  variant -1 = the automatic choice (these
+    updates have at most 128 rows: k_update_small)."""
     sc, orc, gpu = make_pair(320, 240, 30)
     gpu.set_option(3, variant)
     gpu.set_keypoints(0, *sc.frame(1))
@@ -411,3 +412,68 @@ def test_decision_margins_of_a_sequence():
         assert c > 0 and z == 0 and m > 1e4 * max(worst, 1e-13), (k, mg[k], worst)
     # the ratio test compares integer Hamming distances (exact on both sides); dead-bands: a value exactly 0 stays 0
     assert mg["ratio_test_hamming"][1] > 0 and mg["dead_band"][1] > 0
+
+
+def _run_batch(F, N, T, options):
+    scs = [Scenario(640, 480, N, seed_offset=i) for i in range(F)]
+    gpu = EkfBatch(scs[0].params, F, N, 4 * N + 64)
+    for o, val in options:
+        gpu.set_option(o, val)
+    for i, sc in enumerate(scs):
+        x, P, ft, fo, desc, _ = sc.init_map()
+        gpu.set_state(i, x, P, ft, fo, desc)
+    for t in range(1, T + 1):
+        for i, sc in enumerate(scs):
+            gpu.set_keypoints(i, *sc.frame(t))
+        gpu.step()
+    out = []
+    for i in range(F):
+        x, P = gpu.get_state(i)
+        r = gpu.feature_results(i)
+        out.append((x, P, r["matched"], r["inlier"], r["rescued"], gpu.frame_info(i)))
+    gpu.close()
+    return out
+
+
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_lanes_give_bit_identical_filters(lanes):
+    """EKFB_OPT_LANES: the filters of a handle run as lanes on their own streams, interleaved by ekfb_step -- the same kernels
+    on the same per-filter data, so every filter must come out bit for bit as without lanes (9 filters: uneven split)."""
+    ref = _run_batch(9, 40, 6, [(11, 1)])
+    got = _run_batch(9, 40, 6, [(11, lanes)])
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), f"filter {i}: state / covariance differ"
+        for j in (2, 3, 4):
+            assert np.array_equal(a[j], b[j]), f"filter {i}: sets differ"
+        assert a[5] == b[5]
+
+
+@pytest.mark.parametrize("N", [12, 40, 64])
+def test_small_update_kernel_against_the_block_step_path(N):
+    """k_update_small (factorisation + slab TRSM + dx in one launch, every slab CTA factoring S itself; updates of at most 128
+    rows) against the per-block-step launches it replaces, and against the oracle: N = 12 -> one block, N = 40 -> two blocks
+    (k ~ 60..80), N = 64 -> the low-innovation update leaves the small path (k > 128) while the rescue update stays on it."""
+    sc = Scenario(640, 480, N)
+    x, P, ft, fo, desc, _ = sc.init_map()
+    orc = OracleFilter(sc.params)
+    orc.set_state(x, P, ft, fo, desc)
+    a = EkfBatch(sc.params, 1, N, 4 * N + 64)
+    b = EkfBatch(sc.params, 1, N, 4 * N + 64)
+    b.set_option(10, 0)
+    for g in (a, b):
+        g.set_state(0, x, P, ft, fo, desc)
+    for t in range(1, 9):
+        kp, ds = sc.frame(t)
+        orc.step(kp, ds)
+        for g in (a, b):
+            g.set_keypoints(0, kp, ds); g.step()
+        (xa, Pa), (xb, Pb) = a.get_state(0), b.get_state(0)
+        xo, Po = orc.get_state()
+        assert rel_err(xa, xb) < 1e-12 and rel_err(Pa, Pb) < 1e-12, t
+        assert rel_err(xa, xo) < TOL and rel_err(Pa, Po) < TOL, t
+        assert np.array_equal(Pa, Pa.T)
+        ra, rb = a.feature_results(0), b.feature_results(0)
+        for key in ("matched", "inlier", "rescued"):
+            assert np.array_equal(ra[key], rb[key])
+        assert np.array_equal(ra["inlier"], orc.get_ransac()["inlier"])
+        assert a.frame_info(0)["status"] == 0
