@@ -57,7 +57,7 @@ struct SeqDev {
 // latency-bound phases of one lane (factorisation steps, RANSAC, the host's two reads of the counters) overlap the
 // throughput-bound phases (covariance downdate) of the other.  See step_lanes.
 struct Lane {
-    int f0 = 0, F = 0;
+    int idx = 0, f0 = 0, F = 0;
     cudaStream_t stream = nullptr;   // lane 0 runs on the handle's stream
     cudaEvent_t done = nullptr;
     std::vector<int> hn, hN, hKp;
@@ -116,6 +116,9 @@ struct ekfb_ctx {
                               // (ekf_schain.cuh), 1 = panel + trail launches, 3 = the whole chain in one launch (ekf_chain.cuh),
                               // 4 = chain + slab TRSM in one launch (single filter)
     int schain_eff = 0;       // the variant the current update uses
+    int* ddQueue = nullptr;   // work queues of the TMA-fed downdate: [8][2] ints (position, CTAs done), zero between launches
+    int ddQueueNext = 0;      // queue the next launch uses (a lane's index; 0 without lanes)
+    int dd_probe = 0;         // timing probe of the TMA-fed downdate (option 13; results are wrong when set): 1 = no DMMA, 2 = no stores, 4 = no mirror store
     int dd_ctas_per_sm = 2;   // persistent CTAs per SM of the TMA-fed downdate (option 12)
     int lanes_opt = -1;       // lanes per handle (option 11): -1 = automatic (2 for 8 or more filters), 1 = off
     std::vector<Lane> lanes;
@@ -306,6 +309,7 @@ static int create_impl(const ekfb_params* p, int device, int n_filters, int max_
     ALLOC(c->d_kpxy, F * c->Kpmax * 2); ALLOC(c->d_kpdesc, F * c->Kpmax * 32);
     ALLOC(c->d_kpxy_ptr, F); ALLOC(c->d_kpdesc_ptr, F); ALLOC(c->d_kpcount, F);
     ALLOC(c->d_rec, F);
+    ALLOC(c->ddQueue, 16);
     c->nbMax = c->kmax / kNB + 1;
     ALLOC(c->chainCtl, F * (size_t)chain_ctl_ints(c->nbMax));
     v.kpxy = c->d_kpxy_ptr;
@@ -796,8 +800,9 @@ static int launch_downdate(ekfb_ctx* c, int n, bool allowTma = true)
         }
         const int nT = cdiv(n, 64), tilesMax = nT * (nT + 1) / 2;
         const dim3 grid((unsigned)std::min<long long>((long long)tilesMax * c->F, (long long)c->dd_ctas_per_sm * c->smCount));
-        if (swz) CK(launch_k(c, k_downdate_tma<true>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps, tilesMax));
-        else CK(launch_k(c, k_downdate_tma<false>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps, tilesMax));
+        int* queue = c->ddQueue + 2 * c->ddQueueNext;   // the handle's lanes (streams) launch concurrently: a queue each
+        if (swz) CK(launch_k(c, k_downdate_tma<true>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps, tilesMax, nT, queue, c->dd_probe));
+        else CK(launch_k(c, k_downdate_tma<false>, grid, dim3(160), (size_t)kTdSmemBytes, v, maps, tilesMax, nT, queue, c->dd_probe));
     } else if (c->downdate_variant == 1)
         k_downdate<<<dim3(nI * (nI + 1), c->F), 128, kDownSmemBytes, c->stream>>>(v);
     else if (kMax <= c->downdate_small_k) {
@@ -1481,6 +1486,7 @@ struct LaneScope {
     LaneScope(ekfb_ctx* c_, Lane* L_) : c(c_), L(L_), v0(c_->v), F0(c_->F), s0(c_->stream)
     {
         c->v = L->v; c->F = L->F; c->stream = L->stream;
+        c->ddQueueNext = L->idx;
         std::swap(c->hn, L->hn); std::swap(c->hN, L->hN); std::swap(c->hKp, L->hKp);
         shift(+1);
     }
@@ -1489,6 +1495,7 @@ struct LaneScope {
         shift(-1);
         std::swap(c->hn, L->hn); std::swap(c->hN, L->hN); std::swap(c->hKp, L->hKp);
         c->v = v0; c->F = F0; c->stream = s0;
+        c->ddQueueNext = 0;
     }
     void shift(int sign)
     {
@@ -1502,7 +1509,7 @@ static int lanes_wanted(const ekfb_ctx* c)
 {
     if (c->prof) return 1;   // the per-group timers bracket one stream
     const int want = c->lanes_opt > 0 ? c->lanes_opt : (c->F >= 8 ? 2 : 1);
-    return std::max(1, std::min(want, c->F));
+    return std::max(1, std::min(std::min(want, 8), c->F));
 }
 
 // The frame of a batched handle as `nl` lanes on `nl` streams, interleaved phase by phase by this one host thread: while the host
@@ -1519,6 +1526,7 @@ static int step_lanes(ekfb_ctx* c, int nl)
         c->lanes.assign(nl, Lane());
         for (int i = 0; i < nl; ++i) {
             Lane& L = c->lanes[i];
+            L.idx = i;
             L.f0 = (int)((long long)c->F * i / nl);
             L.F = (int)((long long)c->F * (i + 1) / nl) - L.f0;
             if (i == 0) L.stream = c->stream;
@@ -1827,9 +1835,10 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_DOWNDATE_CTAS, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= 13, "unknown option");
     if (option == EKFB_OPT_SMALL_UPDATE) { c->small_update = value; return EKFB_OK; }
     if (option == EKFB_OPT_LANES) { c->lanes_opt = value; return EKFB_OK; }
+    if (option == 13) { c->dd_probe = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_CTAS) { c->dd_ctas_per_sm = value == 1 ? 1 : 2; return EKFB_OK; }
     if (option == EKFB_OPT_FAULT_INJECT) { c->v.faultInject = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
