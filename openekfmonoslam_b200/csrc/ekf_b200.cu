@@ -123,6 +123,8 @@ struct ekfb_ctx {
     int lanes_opt = -1;       // lanes per handle (option 11): -1 = automatic (2 for 8 or more filters), 1 = off
     std::vector<Lane> lanes;
     cudaEvent_t evLaneFork = nullptr;
+    bool in_step = false;      // set by ekfb_step: phases may fold their neighbours' small launches into their own kernels
+    bool mask_cleared = false; // ekfb_measure has cleared the matching mask for the ekfb_match that follows
     int small_update = 1;     // updates of at most 128 rows: factorisation + slab TRSM in one launch, the factorisation redone by
                               // every slab CTA (ekf_update_small.cuh; option 10).  Batches use it while the slab CTAs of all
                               // filters fit in two waves (beyond that the redundant factorisations cost more than the launches)
@@ -363,11 +365,11 @@ static int create_impl(const ekfb_params* p, int device, int n_filters, int max_
     CK(cudaFuncSetAttribute(k_update_fused<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_fused<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_small<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_small_smem_bytes(24)));
-    CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(k_trsm_slab<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(k_trsm_slab<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(k_trsm_slab<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CK(cudaFuncSetAttribute(k_trsm_slab<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CK(cudaFuncSetAttribute(k_trsm_slab<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CK(cudaFuncSetAttribute(k_trsm_slab<24, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_ransac_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             std::min<int>(227 * 1024 - 2048, c->ld * (int)sizeof(double))));
     const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
@@ -677,12 +679,12 @@ extern "C" int ekfb_predict(ekfb_handle c)
     return EKFB_OK;
 }
 
-static int launch_measure(ekfb_ctx* c, int mode)
+static int launch_measure(ekfb_ctx* c, int mode, int seq = 0, int extra = 0)
 {
-    const int N = max_of(c->hN);
+    const int N = std::max(max_of(c->hN), mode ? 1 : 0);   // (the rescue pass must run its tail even for an empty map)
     if (N == 0) return EKFB_OK;
     dim3 grid(cdiv(N, 8), c->F);
-    CK(launch_k(c, k_measure, grid, dim3(256), 0, c->v, mode));
+    CK(launch_k(c, k_measure, grid, dim3(256), 0, c->v, mode, seq, extra));
     count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
@@ -693,7 +695,10 @@ extern "C" int ekfb_measure(ekfb_handle c)
     REQUIRE(c, "null handle");
     CK(cudaSetDevice(c->device));
     GroupScope gs(c, G_MEASURE);
-    return launch_measure(c, 0);
+    // inside ekfb_step the measurement kernel also clears the matching mask (one launch less in front of the rasteriser)
+    const bool clear = c->in_step && ((size_t)c->v.W * c->v.H) % 16 == 0 && max_of(c->hN) > 0;
+    c->mask_cleared = clear;
+    return launch_measure(c, 0, 0, clear ? 1 : 0);
 }
 
 extern "C" int ekfb_match(ekfb_handle c)
@@ -703,20 +708,20 @@ extern "C" int ekfb_match(ekfb_handle c)
     GroupScope gs(c, G_MATCH);
     const int N = max_of(c->hN), Kp = max_of(c->hKp);
     DevView& v = c->v;
-    CK(cudaMemsetAsync(v.mask, 0, (size_t)c->F * v.W * v.H, c->stream));
+    if (!c->mask_cleared) CK(cudaMemsetAsync(v.mask, 0, (size_t)c->F * v.W * v.H, c->stream));
+    c->mask_cleared = false;
     if (N > 0) {
         const int rasterSmem = 4 * (int)(sizeof(RasterScratch) + sizeof(int) * 2 * (size_t)v.H);
         CK(launch_k(c, k_mask_raster, dim3(cdiv(N, 4), c->F), dim3(128), rasterSmem, v, v.mask, v.maxAxes, 255));
         count_launch(c);
-        if (Kp > 0) {
-            CK(launch_k(c, k_kp_mask, dim3(cdiv(Kp, 256), c->F), dim3(256), 0, v));
-            count_launch(c);
-        }
-        CK(launch_k(c, k_match, dim3(cdiv(N, 8), c->F), dim3(256), 0, v));
+        // the detector-mask test of the keypoints and the bookkeeping after matching (counts, match list, RANSAC reset) are
+        // part of the matching kernel: staged with the keypoints / run by the block that finishes last
+        CK(launch_k(c, k_match, dim3(cdiv(N, 8), c->F), dim3(256), 0, v, 1, 1));
+        count_launch(c);
+    } else {
+        CK(launch_k(c, k_after_match, dim3(c->F), dim3(256), 0, v));
         count_launch(c);
     }
-    CK(launch_k(c, k_after_match, dim3(c->F), dim3(256), 0, v));
-    count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
 }
@@ -730,10 +735,10 @@ static int ransac_chunk_len(const ekfb_ctx* c) { return c->ransac_chunk > 0 ? st
 static int ransac_launch(ekfb_ctx* c, int chunk0, int* seq)
 {
     const int CH = ransac_chunk_len(c);
-    CK(launch_k(c, k_ransac_hyp, dim3(CH, c->F, cdiv(c->Nmax, kHypFeat)), dim3(416), 0, c->v, chunk0));
     *seq = ++c->dims_seq;
-    CK(launch_k(c, k_ransac_select, dim3(c->F), dim3(256), 0, c->v, chunk0, CH, *seq));
-    count_launch(c, 2);
+    // (the acceptance rule + the inlier split are run by the hypothesis block that finishes last: one launch per round)
+    CK(launch_k(c, k_ransac_hyp, dim3(CH, c->F, cdiv(c->Nmax, kHypFeat)), dim3(416), 0, c->v, chunk0, *seq));
+    count_launch(c);
     CK(cudaGetLastError());
     return EKFB_OK;
 }
@@ -908,7 +913,7 @@ static int run_update(ekfb_ctx* c, int which)
         GroupScope gs(c, G_CHOL);
         const int steps = cdiv(k, kNB);
         const size_t smem16 = trsm_smem_bytes(k, 16);
-        const size_t smemMax = 227 * 1024;
+        const size_t smemMax = kFusedSmemMax;   // (the kernels also hold a few bytes of static shared memory)
         // single filter, variant 4: chain and slab TRSM overlapped in one launch (ekf_chain.cuh), when one slab per SM fits
         // beside the chain's CTAs; otherwise the chain (one launch) followed by the slab TRSM
         const int fusedSlabs = cdiv(n, 24);
@@ -929,8 +934,7 @@ static int run_update(ekfb_ctx* c, int which)
                 CK(launch_pdl(k_update_fused<24, 3>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
             else
                 CK(launch_pdl(k_update_fused<24, 2>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
-            k_chain_finish<<<1, 32, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
-            count_launch(c, 2);
+            count_launch(c);   // (its last block also advances the chain's generation and applies the state correction)
         } else if (smem16 <= smemMax && !c->force_generic) {
             // fast path: S-only chain, diagonal-block inverses, slab TRSM
             { int rcC = launch_schain(c, k); if (rcC != EKFB_OK) return rcC; }
@@ -973,8 +977,10 @@ static int run_update(ekfb_ctx* c, int which)
                 }
             }
         }
-        CK(launch_k(c, k_state_apply, dim3(cdiv(n, 256), c->F), dim3(256), 0, v));   // + quaternion normalisation (block 0)
-        count_launch(c);
+        if (usedGeneric) {   // (every other path applies the state correction in the last block of its TRSM kernel)
+            CK(launch_k(c, k_state_apply, dim3(cdiv(n, 256), c->F), dim3(256), 0, v));   // + quaternion normalisation (block 0)
+            count_launch(c);
+        }
     }
     {
         GroupScope gs(c, G_DOWNDATE);
@@ -997,13 +1003,9 @@ extern "C" int ekfb_update(ekfb_handle c, int which)
 
 static int rescue_launch(ekfb_ctx* c, int* seq)
 {
-    int rc = launch_measure(c, 1);
-    if (rc != EKFB_OK) return rc;
+    // the re-prediction of the outliers; the block that finishes last applies the chi-square gate and publishes the counters
     *seq = ++c->dims_seq;
-    CK(launch_k(c, k_rescue_gate, dim3(c->F), dim3(256), 0, c->v, *seq));
-    count_launch(c);
-    CK(cudaGetLastError());
-    return EKFB_OK;
+    return launch_measure(c, 1, *seq, c->in_step ? 2 : 0);   // inside ekfb_step: + the map-feature bookkeeping of the frame
 }
 
 extern "C" int ekfb_rescue(ekfb_handle c)
@@ -1575,7 +1577,6 @@ static int step_lanes(ekfb_ctx* c, int nl)
         LaneScope ls(c, &L);
         if ((rc = wait_published_dims(c, L.seq)) != EKFB_OK) return rc;
         if ((rc = ekfb_update(c, 1)) != EKFB_OK) return rc;
-        if ((rc = ekfb_update_map_features(c)) != EKFB_OK) return rc;
         if (L.stream != ls.s0) CK(cudaEventRecord(L.done, L.stream));
     }
     for (Lane& L : c->lanes)
@@ -1587,6 +1588,7 @@ extern "C" int ekfb_step(ekfb_handle c)
 {
     int rc;
     REQUIRE(c, "null handle");
+    struct InStep { ekfb_ctx* c; InStep(ekfb_ctx* c_) : c(c_) { c->in_step = true; } ~InStep() { c->in_step = false; } } inStep(c);
     const int nl = lanes_wanted(c);
     if (nl > 1) return step_lanes(c, nl);
     if ((rc = ekfb_predict(c)) != EKFB_OK) return rc;
@@ -1596,8 +1598,7 @@ extern "C" int ekfb_step(ekfb_handle c)
     if ((rc = ekfb_update(c, 0)) != EKFB_OK) return rc;
     if ((rc = ekfb_rescue(c)) != EKFB_OK) return rc;
     if ((rc = ekfb_update(c, 1)) != EKFB_OK) return rc;
-    if ((rc = ekfb_update_map_features(c)) != EKFB_OK) return rc;
-    return EKFB_OK;
+    return EKFB_OK;   // (the map-feature bookkeeping ran in the tail of the rescue pass)
 }
 
 // ---- results -----------------------------------------------------------------------------------

@@ -615,9 +615,8 @@ __device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, C
 }
 
 template <int SW, int NS>
-__global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase, int nbMax, int nSlabs)
+__device__ __forceinline__ void update_fused_body(const DevView& v, int* ctlBase, int nbMax, int nSlabs, double* csm)
 {
-    extern __shared__ __align__(16) double csm[];
     __shared__ int sTicket, sPos, bad, sFlag;
     const int f = 0, tid = threadIdx.x;
     grid_launch_dependents();
@@ -659,6 +658,23 @@ __global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase
         if (kind == 0) chain_task_offdiag(cx, tI, tC);
         else chain_task_partial_diag(cx, tC);
     }
+}
+
+// The block that finishes last (every flag of the dataflow has been consumed by then) advances the chain's generation and
+// clears its counters -- what k_chain_finish does as a launch of its own -- and applies the state correction
+// (state_apply_tail): the update is ONE launch from S to x.
+template <int SW, int NS>
+__global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase, int nbMax, int nSlabs)
+{
+    extern __shared__ __align__(16) double csm[];
+    update_fused_body<SW, NS>(v, ctlBase, nbMax, nSlabs, csm);
+    if (!last_block_done(fdims(v, 0) + D_TICKET_UPD, (int)gridDim.x)) return;
+    if (threadIdx.x == 0 && ctlBase[CH_TICKET] != 0) {
+        ctlBase[CH_GEN] += 1;
+        ctlBase[CH_TICKET] = 0;
+        ctlBase[CH_QUEUE] = 0;
+    }
+    state_apply_tail(v, 0);
 }
 
 }  // namespace ekf

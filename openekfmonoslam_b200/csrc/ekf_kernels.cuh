@@ -28,7 +28,9 @@ enum DimSlot {
     D_MAP_CHANGED = 17, D_MAP_NEW_N = 18, D_MAP_NEW_NF = 19, D_MAP_CONVERT = 20, D_MAP_NEEDED = 21, D_MAP_NBAD = 22,
     D_MAP_NUNSEEN = 23, D_MAP_CONV_OLDOFF = 24, D_MAP_CONV_NEWOFF = 25,
     D_PRED_TICKET = 26 /* blocks of k_predict_cov that have finished (reset by the last one) */,
-    D_STATUS_EVER = 27 /* OR of the per-frame status values since ekfb_set_state */, D_STRIDE = 32
+    D_STATUS_EVER = 27 /* OR of the per-frame status values since ekfb_set_state */,
+    /* "last block done" tickets of kernels whose tail is run by the block that finishes last (each resets its own) */
+    D_TICKET_MATCH = 28, D_TICKET_HYP = 29, D_TICKET_MEAS = 30, D_TICKET_UPD = 31, D_STRIDE = 32
 };
 
 struct DevView {
@@ -65,7 +67,7 @@ __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddep
 #define PDL_EARLY_TRIGGER 0   /* measured: triggering the successor at kernel start is slightly slower than letting it launch as blocks exit */
 #endif
 
-// The two kernels whose counters size the next launches (k_ransac_select, k_rescue_gate) end by writing the filter's counter
+// The two kernel tails whose counters size the next launches (ransac_select_tail, rescue_gate_tail) end by writing the filter's counter
 // block straight into mapped host memory and then a sequence number the host spins on: the host learns the counts a few
 // microseconds after the kernel's last store instead of after a copy + stream synchronisation.  Call from all threads.
 __device__ __forceinline__ void publish_dims(const DevView& v, int f, int seq)
@@ -78,6 +80,24 @@ __device__ __forceinline__ void publish_dims(const DevView& v, int f, int seq)
     for (int i = 0; i < D_STRIDE; ++i) hd[i] = dm[i];
     __threadfence_system();
     v.hostFlag[f] = seq;
+}
+
+// "Last block done": called by ALL threads of a block once its global writes are issued; true in exactly one block per filter
+// and launch -- the one that arrives last of `total` -- whose threads may then read what the other blocks wrote (through L2:
+// use __ldcg / volatile for such reads) and run the launch's serial tail in place of a one-block follow-up kernel.
+__device__ __forceinline__ bool last_block_done(int* ticket, int total)
+{
+    __shared__ int sLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        sLast = (t == total - 1);
+        if (sLast) *ticket = 0;
+        __threadfence();
+    }
+    __syncthreads();
+    return sLast != 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,10 +189,10 @@ __global__ void k_symmetrize(DevView v, int f)
 // 595-658).  mode 0: all features -> vis,h,Si,Hx,Hf,ell.  mode 1: the outlier subset after the
 // low-innovation update -> vis2,h2,Si2,Hx2,Hf2 (E/EKF.cpp:464-468).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_measure(DevView v, int mode)
+__device__ void rescue_gate_tail(const DevView& v, int f, int seq);
+
+__device__ __forceinline__ void measure_body(const DevView& v, int mode)
 {
-    grid_dependency_wait();
-    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     const int N = dm[D_N_FEAT];
@@ -245,6 +265,29 @@ __global__ void __launch_bounds__(256) k_measure(DevView v, int mode)
     }
 }
 
+// seq > 0 (mode 1 only): the block of a filter that finishes last applies the chi-square gate to the re-predicted outliers
+// (k_rescue_gate's body) and publishes the counters under that sequence number
+// extra & 1 (mode 0): every block also clears its slice of the matching mask (the memset in front of the rasteriser);
+// extra & 2 (mode 1): the tail also does the map-feature bookkeeping of the frame (k_update_map_features' body: it needs the
+// inlier and rescued flags only, not the high-innovation update) -- ekfb_step uses both, the phase-by-phase API neither.
+__device__ void map_features_tail(const DevView& v, int f);
+
+__global__ void __launch_bounds__(256) k_measure(DevView v, int mode, int seq, int extra)
+{
+    grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
+    if (extra & 1) {
+        uint4* m4 = reinterpret_cast<uint4*>(v.mask + (size_t)blockIdx.y * v.W * v.H);
+        const int n16 = (v.W * v.H) >> 4;   // (ekfb_measure only asks for this when W * H is a multiple of 16)
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n16; e += gridDim.x * blockDim.x) m4[e] = make_uint4(0, 0, 0, 0);
+    }
+    measure_body(v, mode);
+    if (seq > 0 && last_block_done(fdims(v, blockIdx.y) + D_TICKET_MEAS, (int)gridDim.x)) {
+        rescue_gate_tail(v, blockIdx.y, seq);
+        if (extra & 2) map_features_tail(v, blockIdx.y);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // M1(1): mask = union of filled gate ellipses (E/Matching.cpp:193-202 -> Gui/Draw.cpp:42-64).
 // One warp per predicted feature; dynamic smem: per warp a RasterScratch and 2*H span ints.
@@ -273,29 +316,17 @@ __global__ void __launch_bounds__(128) k_mask_raster(DevView v, uint8_t* maskBas
     raster_ellipse_warp(maskBase + (size_t)f * v.W * v.H, v.W, v.H, icx, icy, iw, ih, angDeg, sc, spans, lane, (uint8_t)val);
 }
 
-// keypoint survives the detector mask iff mask[(int)(y+0.5f)][(int)(x+0.5f)] != 0
-// (cv::KeyPointsFilter::runByPixelsMask, applied inside detector->detect, E/Matching.cpp:206)
-__global__ void k_kp_mask(DevView v)
-{
-    grid_dependency_wait();
-    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
-    const int f = blockIdx.y;
-    const int Kp = fdims(v, f)[D_N_KP];
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= Kp) return;
-    const float* xy = v.kpxy[f];
-    const int yy = (int)(xy[2 * j + 1] + 0.5f), xx = (int)(xy[2 * j] + 0.5f);
-    const bool ok = xx >= 0 && xx < v.W && yy >= 0 && yy < v.H && v.mask[((size_t)f * v.H + yy) * v.W + xx] != 0;
-    v.kpok[(size_t)f * v.Kpmax + j] = ok;
-}
-
 // ---------------------------------------------------------------------------------------------
 // M1(4) + M2 + M3: one warp per predicted feature.  Lanes stride over the keypoints, gate them
 // with the foci test (C/EKFMath.cpp:302-351), ballot-compact the candidates IN KEYPOINT ORDER and
 // replay the reference's order-dependent push-front 2-best rule (E/Matching.cpp:116-144) and its
 // ratio test (:169-175).  Hamming distance of 32-byte descriptors with __popc.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_match(DevView v)
+__device__ void after_match_tail(const DevView& v, int f);   // (below: counts, match list, RANSAC state reset)
+
+// kpMask != 0: the detector-mask test of the keypoints is applied here as the keypoints are staged (block 0 also writes kpok);
+// tail != 0: the block that finishes last runs k_after_match's body.  ekfb_match uses both: mask raster -> this kernel.
+__global__ void __launch_bounds__(256) k_match(DevView v, int kpMask, int tail)
 {
     grid_dependency_wait();
     if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
@@ -334,8 +365,17 @@ __global__ void __launch_bounds__(256) k_match(DevView v)
         const int cn = min(CHUNK, Kp - c0);
         __syncthreads();
         for (int e = threadIdx.x; e < cn; e += blockDim.x) {
-            sxy[e] = xy2[c0 + e];
-            sok[e] = ok[c0 + e];
+            const float2 pt = xy2[c0 + e];
+            sxy[e] = pt;
+            if (kpMask) {
+                // keypoint survives the detector mask iff mask[(int)(y+0.5f)][(int)(x+0.5f)] != 0
+                // (cv::KeyPointsFilter::runByPixelsMask, applied inside detector->detect, E/Matching.cpp:206)
+                const int yy = (int)(pt.y + 0.5f), xx = (int)(pt.x + 0.5f);
+                const bool o = xx >= 0 && xx < v.W && yy >= 0 && yy < v.H && v.mask[((size_t)f * v.H + yy) * v.W + xx] != 0;
+                sok[e] = o;
+                if (blockIdx.x == 0) v.kpok[(size_t)f * v.Kpmax + c0 + e] = o;
+            } else
+                sok[e] = ok[c0 + e];
         }
         __syncthreads();
         if (!active) continue;
@@ -384,11 +424,13 @@ __global__ void __launch_bounds__(256) k_match(DevView v)
             if (active) v.mkp[fj] = -1;
         }
     }
+    if (tail && last_block_done(fdims(v, f) + D_TICKET_MATCH, (int)gridDim.x)) after_match_tail(v, f);
 }
 
 // ---------------------------------------------------------------------------------------------
 // ordered compaction of a per-feature flag array into a rank -> feature list (one CTA per filter)
 // ---------------------------------------------------------------------------------------------
+// (flags are read through L2: the callers include "last block done" tails that read what other blocks of the launch wrote)
 __device__ inline int block_compact(const uint8_t* flags, int N, int* list)
 {
     __shared__ int warpTot[32];
@@ -398,7 +440,7 @@ __device__ inline int block_compact(const uint8_t* flags, int N, int* list)
     __syncthreads();
     for (int base = 0; base < N; base += blockDim.x) {
         const int j = base + threadIdx.x;
-        const bool fl = (j < N) && flags[j];
+        const bool fl = (j < N) && __ldcg(flags + j);
         const unsigned bal = __ballot_sync(0xffffffffu, fl);
         if (lane == 0) warpTot[wid] = __popc(bal);
         __syncthreads();
@@ -417,11 +459,8 @@ __device__ inline int block_compact(const uint8_t* flags, int N, int* list)
 }
 
 // after matching: counts, match list, RANSAC state reset (E/1PointRansac.cpp:101-125)
-__global__ void __launch_bounds__(256) k_after_match(DevView v)
+__device__ void after_match_tail(const DevView& v, int f)
 {
-    grid_dependency_wait();
-    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
-    const int f = blockIdx.x;
     int* dm = fdims(v, f);
     const int N = dm[D_N_FEAT];
     const size_t fo = (size_t)f * v.Nmax;
@@ -456,6 +495,14 @@ __global__ void __launch_bounds__(256) k_after_match(DevView v)
     }
 }
 
+// the same as its own launch (no features: nothing else of the matching phase runs)
+__global__ void __launch_bounds__(256) k_after_match(DevView v)
+{
+    grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
+    after_match_tail(v, blockIdx.x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // R1: the hypotheses of 1-point RANSAC (E/1PointRansac.cpp:125-161).  Hypothesis i = i-th match.  The state-only
 // EKF update uses K_i = P H_i^T (H_i P H_i^T + sigma I)^-1 with the symmetric-row gather P[:, c] = P[c, :]
@@ -467,10 +514,10 @@ __global__ void __launch_bounds__(256) k_after_match(DevView v)
 // ---------------------------------------------------------------------------------------------
 constexpr int kHypFeat = 64;  // features per CTA
 
-__global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0)
+__device__ void ransac_select_tail(const DevView& v, int f, int chunk0, int chunkLen, int seq);
+
+__device__ __forceinline__ void ransac_hyp_body(const DevView& v, int chunk0)
 {
-    grid_dependency_wait();
-    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
     __shared__ double xc[13], xs[kHypFeat * 6];
     __shared__ double sK[4], sNu[2], sHx[14], sHf[12], sR[27];
     const int f = blockIdx.y, part = blockIdx.z;
@@ -560,14 +607,22 @@ __global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0)
     if ((tid & 31) == 0 && (j >> 5) < v.supWords) sup[j >> 5] = bal;
 }
 
-// Sequential replay of the acceptance / adaptive-cap rule over one evaluated chunk
-// (E/1PointRansac.cpp:125-186), then -- once the loop has ended -- the inlier/outlier split in
-// match order (:201-227) and the inlier list for the low-innovation update.
-__global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, int chunkLen, int seq)
+// seq > 0: the block of a filter that finishes last replays the acceptance rule (k_ransac_select's body) and publishes the
+// counters under that sequence number: one launch per RANSAC round
+__global__ void __launch_bounds__(448) k_ransac_hyp(DevView v, int chunk0, int seq)
 {
     grid_dependency_wait();
     if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
-    const int f = blockIdx.x;
+    ransac_hyp_body(v, chunk0);
+    if (seq > 0 && last_block_done(fdims(v, blockIdx.y) + D_TICKET_HYP, (int)(gridDim.x * gridDim.z)))
+        ransac_select_tail(v, blockIdx.y, chunk0, (int)gridDim.x, seq);
+}
+
+// Sequential replay of the acceptance / adaptive-cap rule over one evaluated chunk
+// (E/1PointRansac.cpp:125-186), then -- once the loop has ended -- the inlier/outlier split in
+// match order (:201-227) and the inlier list for the low-innovation update.
+__device__ void ransac_select_tail(const DevView& v, int f, int chunk0, int chunkLen, int seq)
+{
     int* dm = fdims(v, f);
     const size_t fo = (size_t)f * v.Nmax;
     const int N = dm[D_N_FEAT], m = dm[D_N_MATCH];
@@ -577,8 +632,8 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
         const int i = chunk0 + threadIdx.x;
         int cnt = 0;
         if (i < m && !dm[D_RANSAC_DONE]) {
-            const uint32_t* sw = v.hypsup + ((size_t)f * v.Nmax + i) * v.supWords;
-            for (int w = 0; w < v.supWords; ++w) cnt += __popc(sw[w]);
+            const uint32_t* sw = v.hypsup + ((size_t)f * v.Nmax + i) * v.supWords;   // (written by other blocks: read through L2)
+            for (int w = 0; w < v.supWords; ++w) cnt += __popc(__ldcg(sw + w));
         }
         cnts[threadIdx.x] = cnt;
     }
@@ -625,7 +680,7 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
     const uint32_t* sup = v.hypsup + ((size_t)f * v.Nmax + (bestHyp < 0 ? 0 : bestHyp)) * v.supWords;
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
         const bool mt = v.mflag[fo + j];
-        const bool in = mt && bestHyp >= 0 && ((sup[j >> 5] >> (j & 31)) & 1u);
+        const bool in = mt && bestHyp >= 0 && ((__ldcg(sup + (j >> 5)) >> (j & 31)) & 1u);
         v.inl[fo + j] = in;
         v.outl[fo + j] = mt && !in;
     }
@@ -639,15 +694,13 @@ __global__ void __launch_bounds__(256) k_ransac_select(DevView v, int chunk0, in
     publish_dims(v, f, seq);
 }
 
+
 // ---------------------------------------------------------------------------------------------
 // X1: chi-square gate on the re-predicted outliers (E/EKF.cpp:477-506 + :68-119), then the
 // rescued list for the high-innovation update.  One CTA per filter.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rescue_gate(DevView v, int seq)
+__device__ void rescue_gate_tail(const DevView& v, int f, int seq)
 {
-    grid_dependency_wait();
-    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
-    const int f = blockIdx.x;
     int* dm = fdims(v, f);
     const size_t fo = (size_t)f * v.Nmax;
     const int N = dm[D_N_FEAT];
@@ -655,16 +708,19 @@ __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, int seq)
     if (threadIdx.x == 0) npred2 = 0;
     __syncthreads();
     int c = 0;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) c += (v.outl[fo + j] && v.vis2[fo + j]) ? 1 : 0;
+    // (vis2, h2, Si2 were written by the other blocks of this launch: read through L2)
+    for (int j = threadIdx.x; j < N; j += blockDim.x) c += (v.outl[fo + j] && __ldcg(v.vis2 + fo + j)) ? 1 : 0;
     atomicAdd(&npred2, c);
     __syncthreads();
     // npred2 == 0 with outliers present: the reference indexes an empty vector (undefined); rescue nothing.
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
         bool r = false;
-        if (npred2 > 0 && v.outl[fo + j] && v.vis2[fo + j]) {
-            const double d0 = v.z[(fo + j) * 2] - v.h2[(fo + j) * 2], d1 = v.z[(fo + j) * 2 + 1] - v.h2[(fo + j) * 2 + 1];
-            double Sinv[4];
-            inv2(v.Si2 + (fo + j) * 4, Sinv);
+        if (npred2 > 0 && v.outl[fo + j] && __ldcg(v.vis2 + fo + j)) {
+            const double d0 = v.z[(fo + j) * 2] - __ldcg(v.h2 + (fo + j) * 2), d1 = v.z[(fo + j) * 2 + 1] - __ldcg(v.h2 + (fo + j) * 2 + 1);
+            double S2[4], Sinv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) S2[a] = __ldcg(v.Si2 + (fo + j) * 4 + a);
+            inv2(S2, Sinv);
             const double t0 = d0 * Sinv[0] + d1 * Sinv[2];
             const double t1 = d0 * Sinv[1] + d1 * Sinv[3];
             r = (t0 * d0 + t1 * d1) < v.chi2;
@@ -682,14 +738,8 @@ __global__ void __launch_bounds__(256) k_rescue_gate(DevView v, int seq)
 }
 
 // updateMapFeatures (E/MapManagement.cpp:77-113): hit counters and descriptor refresh of inliers + rescued
-__global__ void k_update_map_features(DevView v)
+__device__ __forceinline__ void map_feature_one(const DevView& v, int f, int j)
 {
-    grid_dependency_wait();
-    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
-    const int f = blockIdx.y;
-    const int N = fdims(v, f)[D_N_FEAT];
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
     const size_t fj = (size_t)f * v.Nmax + j;
     if (v.vis[fj]) v.tpred[fj] += 1;
     if (v.inl[fj] || v.resc[fj]) {
@@ -700,6 +750,24 @@ __global__ void k_update_map_features(DevView v)
 #pragma unroll
         for (int a = 0; a < 8; ++a) dst[a] = src[a];
     }
+}
+
+__global__ void k_update_map_features(DevView v)
+{
+    grid_dependency_wait();
+    if (PDL_EARLY_TRIGGER) grid_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid has started
+    const int f = blockIdx.y;
+    const int N = fdims(v, f)[D_N_FEAT];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N) map_feature_one(v, f, j);
+}
+
+// the same by one block (tail of the rescue pass; resc was written by this block just before: a barrier lies in between)
+__device__ void map_features_tail(const DevView& v, int f)
+{
+    __syncthreads();
+    const int N = fdims(v, f)[D_N_FEAT];
+    for (int j = threadIdx.x; j < N; j += blockDim.x) map_feature_one(v, f, j);
 }
 
 // keypoint counts of all filters in one launch (ekfb_select_frame / ekfb_set_keypoints_batch)

@@ -903,6 +903,31 @@ __global__ void __launch_bounds__(128) k_schain_trail(DevView v, int J)
     }
 }
 
+// U2 + U4 (a) as the tail of the kernel that produced dx (run by its last block, see last_block_done): x += deadband(dx)
+// (E/Update.cpp:143-204), then J = d(q/|q|)/dq at the un-normalised q and q <- q/|q| (E/Update.cpp:45-60,309-317).  The same
+// arithmetic as k_state_apply, one block for the whole state.
+__device__ inline void state_apply_tail(const DevView& v, int f)
+{
+    const int* dm = fdims(v, f);
+    if (dm[D_ULIST] == 0 || __ldcg(dm + D_STATUS) != 0) return;
+    const int n = dm[D_N_STATE];
+    double* x = v.x + (size_t)f * v.ld;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = __ldcg(v.dx + (size_t)f * v.ld + i);   // (written by the other blocks of this launch: read through L2)
+        if (fabs(d) > kDelta) x[i] += d;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double r = x[3], a = x[4], b = x[5], c = x[6];
+    const double nrm = sqrt(r * r + a * a + b * b + c * c);
+    const double s = 1.0 / (nrm * nrm * nrm);
+    const double M[16] = {a * a + b * b + c * c, -r * a, -r * b, -r * c, -a * r, r * r + b * b + c * c, -a * b, -a * c,
+                          -b * r, -b * a, r * r + a * a + c * c, -b * c, -c * r, -c * a, -c * b, r * r + a * a + b * b};
+    double* Jq = v.Jq + (size_t)f * 16;
+    for (int e = 0; e < 16; ++e) Jq[e] = M[e] * s;
+    x[3] = r / nrm; x[4] = a / nrm; x[5] = b / nrm; x[6] = c / nrm;
+}
+
 // W^T = U^-T B on the tensor pipe.  CTA = slab of SW columns of B kept in shared memory (K-major,
 // pitch SW + 4).  For row block J (left-looking):
 //     T   = B_J - sum_{r < J0} U[r][J0 + m] * X[r][c]        (A chunks: 32 rows x 64 cols of U)
@@ -924,10 +949,9 @@ inline size_t trsm_smem_bytes(int k, int SW, int stages = 2)
 // the L2 round trip of its load, so the kernel's time is (number of chunks) x (load latency / chunks in flight): NS - 1
 // chunks are kept in flight, as many as the shared memory left beside the slab allows (run_update picks NS).
 template <int SW, int NS>
-__global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
+__device__ __forceinline__ void trsm_slab_body(const DevView& v, double* tsm)
 {
     constexpr int SWP = SW + 4, NT = SW / 8;
-    extern __shared__ __align__(16) double tsm[];
     const int f = blockIdx.y;
     const int* dm = fdims(v, f);
     const int k = 2 * dm[D_ULIST], n = dm[D_N_STATE];
@@ -1046,6 +1070,15 @@ __global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
         for (int ww = 0; ww < 8; ++ww) s += red[ww * SW + tid];
         v.dx[(size_t)f * v.ld + c0 + tid] = s;
     }
+}
+
+// the filter's block that finishes last applies the state correction (state_apply_tail): no k_state_apply launch behind it
+template <int SW, int NS>
+__global__ void __launch_bounds__(256, 1) k_trsm_slab(DevView v)
+{
+    extern __shared__ __align__(16) double tsm[];
+    trsm_slab_body<SW, NS>(v, tsm);
+    if (last_block_done(fdims(v, blockIdx.y) + D_TICKET_UPD, (int)gridDim.x)) state_apply_tail(v, blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------

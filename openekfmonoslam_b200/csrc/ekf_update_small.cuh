@@ -9,7 +9,8 @@
 //     T(0,0) = U00^T U00, Uinv0;   X01 = Uinv0^T S(0,1);   T(1,1) = S(1,1) - X01^T X01 = U11^T U11, Uinv1;   y = U^-T nu
 //     X0 = Uinv0^T B0;   X1 = Uinv1^T (B1 - X01^T X0);   dx = X^T y;   W^T = X -> Bu
 // All CTAs compute bit-identical factors (same code, same inputs), so W^T is consistent across slabs; a non-positive pivot is
-// seen by every CTA, CTA 0 records EKFB_ERR_NUMERIC and nobody writes (x and P stay untouched).
+// seen by every CTA, CTA 0 records EKFB_ERR_NUMERIC and nobody writes (x and P stay untouched).  The CTA that finishes last
+// applies the state correction x += deadband(dx) and normalises the quaternion (U2, U4a).
 // grid (ceil(n / SW), F), 256 threads, dynamic shared memory update_small_smem_bytes(SW).
 #pragma once
 
@@ -36,10 +37,9 @@ __device__ __forceinline__ void pad_diag_tile(double* T, double* W, int kb, int 
 }
 
 template <int SW>
-__global__ void __launch_bounds__(256, 1) k_update_small(DevView v)
+__device__ __forceinline__ void update_small_body(const DevView& v, double* usm)
 {
     constexpr int SWP = SW + 4, NT = SW / 8;
-    extern __shared__ __align__(16) double usm[];
     double* W0 = usm;                     // Uinv_0
     double* W1 = W0 + kNB * kSS;          // Uinv_1
     double* Xa = W1 + kNB * kSS;          // S(0,1) -> X01 (K-major: row of block 0, column of block 1)
@@ -191,6 +191,15 @@ __global__ void __launch_bounds__(256, 1) k_update_small(DevView v)
         for (int ww = 0; ww < 8; ++ww) s += red[ww * SW + tid];
         v.dx[(size_t)f * v.ld + c0 + tid] = s;
     }
+}
+
+// the filter's block that finishes last applies the state correction (state_apply_tail): no k_state_apply launch behind it
+template <int SW>
+__global__ void __launch_bounds__(256, 1) k_update_small(DevView v)
+{
+    extern __shared__ __align__(16) double usm[];
+    update_small_body<SW>(v, usm);
+    if (last_block_done(fdims(v, blockIdx.y) + D_TICKET_UPD, (int)gridDim.x)) state_apply_tail(v, blockIdx.y);
 }
 
 }  // namespace ekf
