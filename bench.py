@@ -581,8 +581,8 @@ def run(args, json_fd):
                     "what": "pinned host keypoints -> one packed H2D pair -> ekfb_step -> D2H of the records, wall clock, median block"},
             "gpu_launches": res["launches_total"], "gpu_launches_per_step": res["launches_per_step"],
             "per_rank_ms_per_step": res["per_rank_ms_per_step"], "collective_us": res["collective_us"],
-            "roofline": {"bound": "tensor", "kernel": "k_downdate_tma (covariance downdate P -= W W^T: persistent CTAs over the lower 64x64 tiles, "
-                                                     "TMA tensor loads / stores + mbarrier ring, FP64 DMMA m8n8k4)",
+            "roofline": {"bound": "tensor", "kernel": "k_downdate_tma (covariance downdate P -= W W^T: persistent CTAs take the lower 64x64 tiles from a dynamic "
+                                                     "queue, TMA tensor loads / stores + mbarrier ring, FP64 DMMA m8n8k4)",
                          "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak if peak else None,
                          "traffic": traffic, "traffic_source": traffic_src, "launches": dd["launches"],
                          "avg_launch_ms": dd["ms"] / max(dd["launches"], 1),

@@ -166,6 +166,8 @@ private:
     std::vector<unsigned char> _mask, _stamp;
     int _stampR;
     EkfbTraceWriter _trace;
+    void* _logFile;   // FILE*: log.txt (E/EKF.cpp:135-136)
+    void writeLogState();
     int _lastStatus;
     void* _setDump;   // FILE*
 };

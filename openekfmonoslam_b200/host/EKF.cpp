@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <iostream>
 
 namespace {
@@ -137,7 +139,7 @@ void State::removeAllFeatures()
 EKF::EKF(const char* configurationFileName, const char* outputPath)
     : _ekfSteps(0), _strOutputPath(outputPath ? outputPath : ""), _maxFeatures(0), _device(0), _configOk(false),
       _frontEnd(nullptr), _deviceFrontEnd(false), _fastThreshold(20), _h(nullptr), _lastAdded(0), _featuresBefore(0), _stampR(0),
-      _lastStatus(0), _setDump(nullptr)
+      _logFile(nullptr), _lastStatus(0), _setDump(nullptr)
 {
     std::memset(&_info, 0, sizeof(_info));
     std::memset(&_mapResult, 0, sizeof(_mapResult));
@@ -152,10 +154,11 @@ EKF::EKF(const char* configurationFileName, const char* outputPath)
     else if (_cfg.policy.max_map_size > 13) _maxFeatures = (_cfg.policy.max_map_size - 13) / 3 + minM;
     else _maxFeatures = 4 * minM;
     if (!_strOutputPath.empty()) {
-        // E/EKF.cpp:129-143: output.yml in outputPath.  log.txt, the per-frame PNG overlays and videoOutput.mpg are GUI
+        // E/EKF.cpp:129-143: output.yml and log.txt in outputPath.  The per-frame PNG overlays and videoOutput.mpg are GUI
         // artefacts (modules/Gui) and are not written by this build.
         if (!_trace.open(_strOutputPath + "output.yml"))
             std::cerr << "EKF: cannot write " << _strOutputPath << "output.yml" << std::endl;
+        _logFile = std::fopen((_strOutputPath + "log.txt").c_str(), "w");
     }
 }
 
@@ -163,6 +166,37 @@ EKF::~EKF()
 {
     if (_h) ekfb_destroy(_h);
     if (_setDump) std::fclose((FILE*)_setDump);
+    if (_logFile) std::fclose((FILE*)_logFile);
+}
+
+// log.txt: the state after init and after every step, in the layout of State::showDetailed (E/State.cpp:229-240,371-399,
+// E/MapFeature.cpp:130-145): camera position, quaternion, Euler angles (C/EKFMath.cpp:355-365), velocities, the map size,
+// then one line per map feature with its position and its (timesMatched/timesPredicted) counters.  %g = the six significant
+// digits of an ostream's default formatting.
+void EKF::writeLogState()
+{
+    FILE* f = (FILE*)_logFile;
+    if (!f) return;
+    const double* q = state.orientation;
+    const double roll = std::atan2(2 * (q[0] * q[1] + q[2] * q[3]), 1 - 2 * (q[1] * q[1] + q[2] * q[2]));
+    const double pitch = std::asin(2 * (q[0] * q[2] - q[3] * q[1]));
+    const double yaw = std::atan2(2 * (q[0] * q[3] + q[1] * q[2]), 1 - 2 * (q[2] * q[2] + q[3] * q[3]));
+    std::fprintf(f, "Posicion de la camara: %g, %g, %g\n", state.position[0], state.position[1], state.position[2]);
+    std::fprintf(f, "Orientacion(cuaternions): %g, %g, %g, %g\n", q[0], q[1], q[2], q[3]);
+    std::fprintf(f, "Orientacion en angulos eulerianos: %g, %g, %g\n", roll, pitch, yaw);
+    std::fprintf(f, "Velocidad lineal (con respecto al mundo): %g, %g, %g\n", state.linearVelocity[0], state.linearVelocity[1],
+                 state.linearVelocity[2]);
+    std::fprintf(f, "Velocidad angular (con respecto a la camara): %g, %g, %g\n", state.angularVelocity[0], state.angularVelocity[1],
+                 state.angularVelocity[2]);
+    std::fprintf(f, "Cantidad de features en el mapa: %zu\n\n", state.mapFeatures.size());
+    std::fprintf(f, "Map Features (%zu):\n", state.mapFeatures.size());
+    for (size_t i = 0; i < state.mapFeatures.size(); ++i) {
+        const MapFeature* m = state.mapFeatures[i];
+        std::fprintf(f, "%zu: ", i);
+        for (int a = 0; a < m->positionDimension; ++a) std::fprintf(f, a ? ", %g" : "%g", m->position[a]);
+        std::fprintf(f, " (%u/%u)\n", m->timesMatched, m->timesPredicted);
+    }
+    std::fflush(f);
 }
 
 void EKF::fail(int status, const char* where)
@@ -384,6 +418,19 @@ bool EKF::acquireKeypoints(const cv::Mat& image)
 void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
 {
     _lastStatus = EKFB_OK;
+    if (_logFile) {
+        // E/EKF.cpp:172-180: the reference re-seeds rand() from time() whenever it logs, which makes a logged run choose other
+        // new features than an unlogged one.  Here that is opt-in (EKFB_LOG_RANDOM_SEED=1): by default a run is
+        // reproducible whether or not it writes log.txt, and the line says which seed stream is in use.
+        const char* reseed = std::getenv("EKFB_LOG_RANDOM_SEED");
+        if (reseed && reseed[0] == '1') {
+            const time_t seed = time(nullptr);
+            srand(static_cast<unsigned int>(seed));
+            std::fprintf((FILE*)_logFile, "Random Seed: %lld\n\n", (long long)seed);
+        } else
+            std::fprintf((FILE*)_logFile, "Random Seed: (the caller's rand() stream, not re-seeded)\n\n");
+        std::fprintf((FILE*)_logFile, "~~~~~~~~~~~~ STEP %d ~~~~~~~~~~~~\n", _ekfSteps);
+    }
     if (!_configOk || (!_frontEnd && !_deviceFrontEnd)) {
         std::cerr << "EKF::init: no configuration or no front end" << std::endl;
         _lastStatus = EKFB_ERR_ARG;
@@ -415,6 +462,7 @@ void EKF::init(const cv::Mat& image)  // E/EKF.cpp:170-237
     }
     _lastAdded = addNewFeatures(_cfg.policy.min_matches_per_image, false);
     refreshMirror(true);
+    writeLogState();
 }
 
 void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
@@ -455,6 +503,7 @@ void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
         return;
     }
     _ekfSteps++;   // a failed frame does not count (the reference has no failure path: E/EKF.cpp:242)
+    if (_logFile) std::fprintf((FILE*)_logFile, "\n\n~~~~~~~~~~~~ STEP %d ~~~~~~~~~~~~\n", _ekfSteps);   // E/EKF.cpp:246-250
     ekfb_peek_frame_info(_h, 0, &_info);   // the counters ekfb_step synchronised; status is refreshed from the record below
     if (_setDump) dumpFrameSets();
     // map management (E/EKF.cpp:572-612): bad / unseen features out, one conversion, new features in
@@ -495,6 +544,7 @@ void EKF::step(const cv::Mat& image)  // E/EKF.cpp:242-666
             for (int j = 0; j < 13; ++j) t.cov[i * 13 + j] = stateCovarianceMatrix[i][j];
         _trace.frame(_ekfSteps, t);
     }
+    writeLogState();   // E/EKF.cpp:662-665
 }
 
 void EKF::syncCovariance()

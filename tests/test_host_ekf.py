@@ -276,6 +276,14 @@ def test_sample_driver_with_map_management_follows_the_reference(tmp_path):
     assert int(last.getNode("totalMatches").real()) == int(rows[-1][3])
     assert last.getNode("UpdateLI").real() > 0
     fs.release()
+    # log.txt (E/EKF.cpp:172-180,246-250,662-665 -> State::showDetailed): one banner per step, the camera line and one line
+    # per map feature of the final state, positions to six significant digits
+    log = open(out_dir + "log.txt").read()
+    assert log.count("~~~~~~~~~~~~ STEP ") == T + 1 and f"STEP {T} ~" in log
+    tail = log[log.rindex("~~~~~~~~~~~~ STEP "):]
+    cam = [ln for ln in tail.splitlines() if ln.startswith("Posicion de la camara: ")][0]
+    assert np.allclose([float(v) for v in cam.split(": ")[1].split(", ")], xr[:3], rtol=1e-5, atol=1e-12)
+    assert f"Map Features ({Nf}):" in tail and len([ln for ln in tail.splitlines() if ln[:1].isdigit() and ": " in ln]) == Nf
     r.close()
 
 
