@@ -398,7 +398,8 @@ class Leg:
 
     def e2e_blocks(self, R):
         """R blocks of K steps fed from pinned host memory: ONE packed H2D pair per step for all filters of the handle
-        (ekfb_set_keypoints_packed), the step, D2H of the result records (+ the gather when due).  Wall clock."""
+        (ekfb_set_keypoints_packed), the step, D2H of the result records (+ the gather when due).  Host wall clock per step, from
+        before the H2D is issued until the D2H has completed; the L2 flush between steps (timing hygiene) is outside the clock."""
         torch, gpu, K, F = self.torch, self.gpu, self.K, self.F
         fr = [[sc.frame(t) for t in range(self.t_next, self.t_next + R * K)] for sc in self.scene_list]
         self.t_next += R * K
@@ -414,11 +415,13 @@ class Leg:
         blocks, h2d = [], 0
         recs = None
         for b in range(R):
-            t0 = time.perf_counter()
+            blk = 0.0
             for s in range(K):
                 xy, ds, off = pins[b * K + s]
-                if self.flush:
+                if self.flush:          # timing hygiene, not part of the path: the flush and its completion stay off the clock
                     gpu.flush_l2()
+                    gpu.sync()
+                t0 = time.perf_counter()
                 gpu.set_keypoints_packed_raw(xy.data_ptr(), ds.data_ptr(), off)
                 h2d += xy.numel() * 4 + ds.numel()
                 gpu.step()
@@ -426,7 +429,8 @@ class Leg:
                 if self.world > 1 and ((s % GATHER_EVERY == GATHER_EVERY - 1) or s == K - 1):
                     gpu.write_records_device(self.rec_dev.data_ptr())
                     self.gather()
-            blocks.append(time.perf_counter() - t0)
+                blk += time.perf_counter() - t0
+            blocks.append(blk)
         self.barrier()
         assert abs(np.linalg.norm(np.array(recs[0].x_cam)[3:7]) - 1.0) < 1e-9
         return blocks, h2d // (R * K)
@@ -578,7 +582,9 @@ def run(args, json_fd):
                        "c4_sharded": c4},
             "e2e": {"value": res["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": res["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": res["filters_total"] * RECORD_BYTES, "blocks": res["e2e_blocks"],
-                    "what": "pinned host keypoints -> one packed H2D pair -> ekfb_step -> D2H of the records, wall clock, median block"},
+                    "what": "per step: pinned host keypoints -> one packed H2D pair -> ekfb_step -> D2H of the records (+ the NCCL gather when due), "
+                            "host wall clock from before the H2D to after the D2H has completed, summed over the block's steps (the L2 flush "
+                            "between steps and its completion are outside the clock), median block"},
             "gpu_launches": res["launches_total"], "gpu_launches_per_step": res["launches_per_step"],
             "per_rank_ms_per_step": res["per_rank_ms_per_step"], "collective_us": res["collective_us"],
             "roofline": {"bound": "tensor", "kernel": "k_downdate_tma (covariance downdate P -= W W^T: persistent CTAs take the lower 64x64 tiles from a dynamic "

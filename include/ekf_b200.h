@@ -196,6 +196,14 @@ int ekfb_ncc_set_image(ekfb_handle h, int filter, const uint8_t* gray, int strid
 int ekfb_ncc_set_templates(ekfb_handle h, int filter, int first_feature, int count, const uint8_t* templates);
 /* after ekfb_measure, instead of ekfb_match: fills the same match arrays (z = matched pixel, distance = 1 - score) */
 int ekfb_match_ncc(ekfb_handle h, double ncc_min);
+/* templates (count x 3 x 121 bytes) and anchors (count x 10 doubles: camera position, quaternion, pixel at capture, valid flag) of
+ * features first_feature .. first_feature + count - 1, as captured by ekfb_add_features / set by ekfb_ncc_set_templates and
+ * carried through map management; either output may be NULL */
+int ekfb_ncc_get_templates(ekfb_handle h, int filter, int first_feature, int count, uint8_t* templates, double* anchors);
+/* anchors for caller-supplied templates (same layout; call after ekfb_ncc_set_templates, which clears them) */
+int ekfb_ncc_set_anchors(ekfb_handle h, int filter, int first_feature, int count, const double* anchors);
+/* acceptance threshold of the NCC matcher when it runs inside ekfb_match / ekfb_step (EKFB_OPT_MATCHER = 1); default 0.8 */
+int ekfb_ncc_set_threshold(ekfb_handle h, double ncc_min);
 /* level-0 score (-2: no candidate) and start level (-1: not predicted) per feature of the last ekfb_match_ncc */
 int ekfb_ncc_get_scores(ekfb_handle h, int filter, double* score, int32_t* level);
 /* one pyramid level back to the host (w x h bytes, tightly packed); out may be NULL to query the size */
@@ -258,7 +266,13 @@ enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* covar
        EKFB_OPT_LANES = 11 /* batched handles: the filters run as this many lanes on their own streams, interleaved by ekfb_step
                               (0 / -1 = automatic: 2 for 8 or more filters; 1 = off) */,
        EKFB_OPT_DOWNDATE_CTAS = 12 /* persistent CTAs per SM of the TMA-fed downdate: 2 (default) or 1 (leaves half of every SM
-                                      to the kernels of another lane / stream) */ };
+                                      to the kernels of another lane / stream) */,
+       EKFB_OPT_DOWNDATE_PROBE = 13 /* timing probe of the TMA-fed downdate (results are wrong when set): 1 = no DMMA, 2 = no stores,
+                                       4 = no mirror store */,
+       EKFB_OPT_MATCHER = 14 /* matcher used by ekfb_match / ekfb_step: 0 (default) = the reference's descriptor matcher, 1 = the NCC
+                                active search (needs ekfb_ncc_set_image / ekfb_set_image every frame; templates captured on the device
+                                by ekfb_add_features or supplied with ekfb_ncc_set_templates) */,
+       EKFB_OPT_NCC_WARP = 15 /* 1 (default): templates with an anchor are warped to the current camera before the comparison */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

@@ -265,6 +265,18 @@ class EkfBatch:
         t = np.ascontiguousarray(templates, np.uint8).reshape(-1, 3, 121)
         self._ck(self.L.ekfb_ncc_set_templates(self.h, ctypes.c_int(f), ctypes.c_int(first), ctypes.c_int(t.shape[0]), _ptr(t)))
 
+    def ncc_get_templates(self, f, first, count):
+        """(templates [count, 3, 121] uint8, anchors [count, 10] float64) of features first .. first + count - 1"""
+        t = np.zeros((count, 3, 121), np.uint8); a = np.zeros((count, 10))
+        self._ck(self.L.ekfb_ncc_get_templates(self.h, ctypes.c_int(f), ctypes.c_int(first), ctypes.c_int(count), _ptr(t), _ptr(a)))
+        return t, a
+
+    def ncc_set_anchors(self, f, first, anchors):
+        a = np.ascontiguousarray(anchors, np.float64).reshape(-1, 10)
+        self._ck(self.L.ekfb_ncc_set_anchors(self.h, ctypes.c_int(f), ctypes.c_int(first), ctypes.c_int(a.shape[0]), _ptr(a)))
+
+    def ncc_set_threshold(self, ncc_min): self._ck(self.L.ekfb_ncc_set_threshold(self.h, ctypes.c_double(ncc_min)))
+
     def match_ncc(self, ncc_min=0.8):
         self._ck(self.L.ekfb_match_ncc(self.h, ctypes.c_double(ncc_min)))
 

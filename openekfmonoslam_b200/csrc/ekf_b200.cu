@@ -145,6 +145,13 @@ struct ekfb_ctx {
     size_t ncc_level_bytes[kNccLevels] = {0, 0, 0};
     NccView ncc;
     uint8_t* ncc_tmpl = nullptr;
+    uint8_t* ncc_tmpl2 = nullptr;     // compaction targets (swapped with the live arrays by ekfb_map_management)
+    double* ncc_anchor = nullptr;     // [F][Nmax][10]: camera pose + pixel at template capture (ekf_ncc.cuh)
+    double* ncc_anchor2 = nullptr;
+    std::vector<uint8_t> ncc_has_image;   // per filter: a frame has been set (templates of new features are captured from it)
+    int matcher = 0;                  // option 14: 0 = the reference's descriptor matcher, 1 = NCC active search inside ekfb_match
+    int ncc_warp = 1;                 // option 15: predict the template's appearance for the current camera (affine warp)
+    double ncc_min_score = 0.8;       // acceptance threshold of the NCC matcher inside ekfb_match (ekfb_ncc_set_threshold)
     // device front end (ekf_frontend.cuh): corner-score image, per-row counts / offsets, keypoint count per filter
     uint8_t* fe_score = nullptr;
     uint8_t* fe_color = nullptr;   // staging for a colour frame (W x H x 4)
@@ -705,6 +712,10 @@ extern "C" int ekfb_match(ekfb_handle c)
 {
     REQUIRE(c, "null handle");
     CK(cudaSetDevice(c->device));
+    if (c->matcher == 1 && c->ncc_ready) {   // EKFB_OPT_MATCHER: the NCC active search in place of the descriptor matcher
+        c->mask_cleared = false;
+        return ekfb_match_ncc(c, c->ncc_min_score);
+    }
     GroupScope gs(c, G_MATCH);
     const int N = max_of(c->hN), Kp = max_of(c->hKp);
     DevView& v = c->v;
@@ -1091,6 +1102,13 @@ extern "C" int ekfb_map_management(ekfb_handle c, const ekfb_map_policy* pol, ek
         k_map_convert<<<dim3(cdiv(nnMax, 256), c->F), 256, 0, c->stream>>>(v);
         k_map_commit<<<cdiv(c->F, 128), 128, 0, c->stream>>>(v);
         count_launch(c, 3);
+        if (c->ncc_ready) {   // NCC templates and anchors follow their features
+            const int Nold = max_of(c->hN);
+            k_ncc_compact<<<c->F, 256, sizeof(int) * std::max(Nold, 1), c->stream>>>(v, c->ncc_tmpl, c->ncc_tmpl2, c->ncc_anchor, c->ncc_anchor2, Nold);
+            count_launch(c);
+            std::swap(c->ncc_tmpl, c->ncc_tmpl2);
+            std::swap(c->ncc_anchor, c->ncc_anchor2);
+        }
         CK(cudaGetLastError());
         std::swap(v.P, v.P2); std::swap(v.x, v.x2); std::swap(v.ftype, v.ftype2); std::swap(v.foff, v.foff2);
         std::swap(v.desc, v.desc2); std::swap(v.tpred, v.tpred2); std::swap(v.tmatch, v.tmatch2);
@@ -1142,6 +1160,15 @@ extern "C" int ekfb_add_features(ekfb_handle c, int f, int count, const double* 
                                                 c->prm.init_inv_depth_rho, c->prm.inverse_depth_rho_sd);
     k_add_cov<<<dim3(cdiv(n0 + 6 * count, 256), count), 256, 0, c->stream>>>(v, f, n0, count);
     count_launch(c, 2);
+    if (c->ncc_ready && c->ncc_has_image[f]) {
+        // NCC appearance of the new features: templates cut from the frame's pyramid at their pixels, and the camera pose
+        // they were seen from (ekf_ncc.cuh)
+        NccView nv = c->ncc;
+        for (int l = 0; l < kNccLevels; ++l) nv.img[l] = c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l];
+        k_ncc_capture<<<count, 128, 0, c->stream>>>(v, nv, f, N0, count, v.adduv, c->ncc_tmpl + (size_t)f * c->Nmax * kNccLevels * 128,
+                                                    c->ncc_anchor + (size_t)f * c->Nmax * kNccAnchor);
+        count_launch(c);
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));   // uv / desc may be pageable
     c->hn[f] = n0 + 6 * count;
@@ -1280,6 +1307,10 @@ static int ensure_ncc(ekfb_ctx* c)
         W /= 2; H /= 2;
     }
     ALLOC(c->ncc_tmpl, (size_t)c->F * c->Nmax * kNccLevels * 128);
+    ALLOC(c->ncc_tmpl2, (size_t)c->F * c->Nmax * kNccLevels * 128);
+    ALLOC(c->ncc_anchor, (size_t)c->F * c->Nmax * kNccAnchor);
+    ALLOC(c->ncc_anchor2, (size_t)c->F * c->Nmax * kNccAnchor);
+    c->ncc_has_image.assign(c->F, 0);
     ALLOC(nv.score, (size_t)c->F * c->Nmax);
     ALLOC(nv.level, (size_t)c->F * c->Nmax);
     nv.ncc_min = 0.8;
@@ -1310,6 +1341,7 @@ extern "C" int ekfb_ncc_set_image(ekfb_handle c, int f, const uint8_t* gray, int
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));   // the caller's image may be pageable
+    c->ncc_has_image[f] = 1;
     return EKFB_OK;
 }
 
@@ -1417,7 +1449,44 @@ extern "C" int ekfb_ncc_set_templates(ekfb_handle c, int f, int first_feature, i
     if (rc != EKFB_OK) return rc;
     uint8_t* dst = c->ncc_tmpl + ((size_t)f * c->Nmax + first_feature) * kNccLevels * 128;
     CK(cudaMemcpy2DAsync(dst, 128, templates, kNccPP, kNccPP, (size_t)count * kNccLevels, cudaMemcpyHostToDevice, c->stream));
+    // caller-supplied templates carry no anchor: they are compared as they are (no warp)
+    CK(cudaMemsetAsync(c->ncc_anchor + ((size_t)f * c->Nmax + first_feature) * kNccAnchor, 0, sizeof(double) * kNccAnchor * count, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_ncc_get_templates(ekfb_handle c, int f, int first_feature, int count, uint8_t* templates, double* anchors)
+{
+    REQUIRE(c && c->ncc_ready, "no NCC data");
+    REQUIRE(f >= 0 && f < c->F && first_feature >= 0 && count >= 0 && first_feature + count <= c->Nmax, "bad filter index or range");
+    CK(cudaSetDevice(c->device));
+    if (templates)
+        CK(cudaMemcpy2DAsync(templates, kNccPP, c->ncc_tmpl + ((size_t)f * c->Nmax + first_feature) * kNccLevels * 128, 128, kNccPP,
+                             (size_t)count * kNccLevels, cudaMemcpyDeviceToHost, c->stream));
+    if (anchors)
+        CK(cudaMemcpyAsync(anchors, c->ncc_anchor + ((size_t)f * c->Nmax + first_feature) * kNccAnchor, sizeof(double) * kNccAnchor * count,
+                           cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_ncc_set_anchors(ekfb_handle c, int f, int first_feature, int count, const double* anchors)
+{
+    REQUIRE(c && anchors, "null argument");
+    REQUIRE(f >= 0 && f < c->F && first_feature >= 0 && count >= 0 && first_feature + count <= c->Nmax, "bad filter index or range");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_ncc(c);
+    if (rc != EKFB_OK) return rc;
+    CK(cudaMemcpyAsync(c->ncc_anchor + ((size_t)f * c->Nmax + first_feature) * kNccAnchor, anchors, sizeof(double) * kNccAnchor * count,
+                       cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EKFB_OK;
+}
+
+extern "C" int ekfb_ncc_set_threshold(ekfb_handle c, double ncc_min)
+{
+    REQUIRE(c, "null handle");
+    c->ncc_min_score = ncc_min;
     return EKFB_OK;
 }
 
@@ -1433,6 +1502,8 @@ extern "C" int ekfb_match_ncc(ekfb_handle c, double ncc_min)
         nv.score = c->ncc.score + (size_t)f * c->Nmax;
         nv.level = c->ncc.level + (size_t)f * c->Nmax;
         nv.ncc_min = ncc_min;
+        nv.anchor = c->ncc_anchor + (size_t)f * c->Nmax * kNccAnchor;
+        nv.warp = c->ncc_warp;
         for (int l = 0; l < kNccLevels; ++l) nv.img[l] = c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l];
         k_search_ncc<<<c->hN[f], 128, 0, c->stream>>>(c->v, nv, f);
         count_launch(c);
@@ -1510,6 +1581,7 @@ struct LaneScope {
 static int lanes_wanted(const ekfb_ctx* c)
 {
     if (c->prof) return 1;   // the per-group timers bracket one stream
+    if (c->matcher == 1) return 1;   // the NCC search indexes its own per-filter arrays (not part of the lane views)
     const int want = c->lanes_opt > 0 ? c->lanes_opt : (c->F >= 8 ? 2 : 1);
     return std::max(1, std::min(std::min(want, 8), c->F));
 }
@@ -1836,10 +1908,12 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= 13, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_NCC_WARP, "unknown option");
     if (option == EKFB_OPT_SMALL_UPDATE) { c->small_update = value; return EKFB_OK; }
     if (option == EKFB_OPT_LANES) { c->lanes_opt = value; return EKFB_OK; }
     if (option == 13) { c->dd_probe = value; return EKFB_OK; }
+    if (option == EKFB_OPT_MATCHER) { c->matcher = value; return EKFB_OK; }
+    if (option == EKFB_OPT_NCC_WARP) { c->ncc_warp = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_CTAS) { c->dd_ctas_per_sm = value == 1 ? 1 : 2; return EKFB_OK; }
     if (option == EKFB_OPT_FAULT_INJECT) { c->v.faultInject = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }

@@ -3,7 +3,18 @@
 //
 // Specification (restated on the CPU in oracle/ncc_oracle.py, which the GPU tests compare against bit for bit):
 //   pyramid   L0 = the frame (8-bit grey), L(l+1)(y,x) = (a + b + c + d + 2) >> 2 over the 2x2 block, floor(W/2) x floor(H/2)
-//   template  per feature and level an 11 x 11 8-bit patch T_l
+//   template  per feature and level an 11 x 11 8-bit patch T_l, supplied by the caller (ekfb_ncc_set_templates) or CAPTURED ON THE
+//             DEVICE when the feature is created (ekfb_add_features with an image set: k_ncc_capture cuts the patch centred on
+//             ((int)u >> l, (int)v >> l) of every level, zero where it leaves the level) together with the ANCHOR of the
+//             feature: camera position r0, orientation q0 and the pixel (u0, v0) at that moment (10 doubles)
+//   warp      (features with an anchor; EKFB_OPT_NCC_WARP) the patch is predicted for the current camera before it is compared:
+//             the surface around the point X is taken as the plane through X facing the anchor camera, n = (X - r0)/|X - r0|;
+//             pinhole model (fx, fy, cx, cy; lens distortion is ignored by the warp); A = d(u1, v1)/d(u0, v0) by unit
+//             differences: anchor pixels (u0 + 1, v0), (u0, v0 + 1) -> rays R(q0) ((u - cx)/fx, (v - cy)/fy, 1) -> plane ->
+//             current camera R(q1)^T (X' - r1) -> pixel, minus the same for (u0, v0).  Warped template
+//             T'_l(tx, ty) = bilinear sample of T_l at (5, 5) + A^-1 (tx - 5, ty - 5), coordinates clamped to [0, 10], rounded
+//             to the nearest byte.  A is replaced by the identity (raw template) when max|A - I| < 0.05 or when
+//             det A is outside [0.25, 4] or not finite.  The same A serves all three levels.
 //   search    for every predicted feature: centre c0 = (int)(float)h, integer gate axes (aw, ah) and angle as in the
 //             descriptor matcher (E/Matching.cpp:227-239); start level l = smallest level with ceil(max(aw,ah) / 2^l) <= 12
 //             (at most 2), window half-size R = min(12, that value); candidates = displacements in [-R, R]^2 around c0 >> l
@@ -33,6 +44,8 @@ struct NccView {
     int W[kNccLevels], H[kNccLevels], pitch[kNccLevels];
     const uint8_t* img[kNccLevels];   // this filter's pyramid levels, 16-byte aligned rows
     const uint8_t* tmpl;   // [Nmax][3][128] (121 used)
+    const double* anchor;  // [Nmax][10]: r0[3], q0[4], (u0, v0), valid (1.0) -- nullptr or valid == 0: no warp
+    int warp;              // EKFB_OPT_NCC_WARP
     double* score;         // [Nmax] level-0 score of the last search (-2: none)
     int* level;            // [Nmax] start level
     double ncc_min;
@@ -73,6 +86,109 @@ __device__ __forceinline__ void tma_bulk_load(void* smem, const void* gmem, int 
                  : "memory");
 }
 
+constexpr int kNccAnchor = 10;
+
+// Template + anchor capture for `count` new features first .. first + count - 1 of filter f at pixels uv (doubles, 2 each):
+// one CTA (128 threads) per feature.  tmpl / anchor point at the filter's slices.
+__global__ void __launch_bounds__(128) k_ncc_capture(DevView v, NccView nv, int f, int first, int count, const double* uv, uint8_t* tmpl,
+                                                     double* anchor)
+{
+    const int i = blockIdx.x;
+    if (i >= count) return;
+    const int j = first + i;
+    const int x = (int)uv[2 * i], y = (int)uv[2 * i + 1];
+    for (int l = 0; l < kNccLevels; ++l) {
+        const int cx = x >> l, cy = y >> l;
+        uint8_t* T = tmpl + ((size_t)j * kNccLevels + l) * 128;
+        for (int e = threadIdx.x; e < 128; e += blockDim.x) {
+            uint8_t val = 0;
+            if (e < kNccPP) {
+                const int px = cx - 5 + e % kNccP, py = cy - 5 + e / kNccP;
+                if (px >= 0 && px < nv.W[l] && py >= 0 && py < nv.H[l]) val = nv.img[l][(size_t)py * nv.pitch[l] + px];
+            }
+            T[e] = val;
+        }
+    }
+    if (threadIdx.x < kNccAnchor) {
+        const double* xs = v.x + (size_t)f * v.ld;
+        const int a = threadIdx.x;
+        anchor[(size_t)j * kNccAnchor + a] = a < 7 ? xs[a] : (a < 9 ? uv[2 * i + a - 7] : 1.0);
+    }
+}
+
+// Map compaction (ekfb_map_management): templates and anchors follow their features.  keepList[r] = old index of the r-th
+// surviving feature (ordered), built from the removal flags of k_map_plan.  One CTA per filter.
+__global__ void __launch_bounds__(256) k_ncc_compact(DevView v, const uint8_t* tmpl, uint8_t* tmpl2, const double* anchor, double* anchor2,
+                                                     int Nold_max)
+{
+    const int f = blockIdx.x;
+    const size_t fo = (size_t)f * v.Nmax;
+    extern __shared__ int keepList[];
+    __shared__ int nKeep;
+    if (threadIdx.x == 0) {   // (serial: a few hundred features, once per map change)
+        int r = 0;
+        const int Nold = Nold_max;
+        for (int i = 0; i < Nold; ++i)
+            if (v.mapflag[fo + i] == 0) keepList[r++] = i;
+        nKeep = min(r, fdims(v, f)[D_MAP_NEW_NF]);
+    }
+    __syncthreads();
+    const size_t tstride = (size_t)kNccLevels * 128;
+    for (int r = 0; r < nKeep; ++r) {
+        const int i = keepList[r];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tmpl + (fo + i) * tstride);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tmpl2 + (fo + r) * tstride);
+        for (int e = threadIdx.x; e < (int)(tstride / 4); e += blockDim.x) dst[e] = src[e];
+        if (threadIdx.x < kNccAnchor) anchor2[(fo + r) * kNccAnchor + threadIdx.x] = anchor[(fo + i) * kNccAnchor + threadIdx.x];
+    }
+}
+
+// A = d(current pixel)/d(anchor pixel) of the plane-induced warp (see the header); false: use the raw template
+__device__ inline bool ncc_warp_matrix(const CamParams& c, const double* an, const double* X, const double* r1, const double* q1, double* A)
+{
+    double R0[9], R1[9];
+    quat_to_rot(an + 3, R0);
+    quat_to_rot(q1, R1);
+    double nrm[3] = {X[0] - an[0], X[1] - an[1], X[2] - an[2]};
+    const double len = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+    if (!(len > 0.0)) return false;
+    for (int a = 0; a < 3; ++a) nrm[a] /= len;
+    double uvw[3][2];
+    for (int e = 0; e < 3; ++e) {
+        const double u = an[7] + (e == 1 ? 1.0 : 0.0), w = an[8] + (e == 2 ? 1.0 : 0.0);
+        const double dc[3] = {(u - c.cx) / c.fx, (w - c.cy) / c.fy, 1.0};
+        double dw[3];
+        for (int a = 0; a < 3; ++a) dw[a] = R0[a * 3] * dc[0] + R0[a * 3 + 1] * dc[1] + R0[a * 3 + 2] * dc[2];
+        const double den = nrm[0] * dw[0] + nrm[1] * dw[1] + nrm[2] * dw[2];
+        const double t = len / den;   // n . (X - r0) = len
+        double pw[3], pc[3];
+        for (int a = 0; a < 3; ++a) pw[a] = an[a] + t * dw[a] - r1[a];
+        for (int a = 0; a < 3; ++a) pc[a] = R1[a] * pw[0] + R1[3 + a] * pw[1] + R1[6 + a] * pw[2];   // R1^T
+        uvw[e][0] = c.cx + c.fx * pc[0] / pc[2];
+        uvw[e][1] = c.cy + c.fy * pc[1] / pc[2];
+    }
+    A[0] = uvw[1][0] - uvw[0][0]; A[1] = uvw[2][0] - uvw[0][0];
+    A[2] = uvw[1][1] - uvw[0][1]; A[3] = uvw[2][1] - uvw[0][1];
+    const double det = A[0] * A[3] - A[1] * A[2];
+    if (!(det >= 0.25 && det <= 4.0)) return false;   // (also false for NaN)
+    const double dev = fmax(fmax(fabs(A[0] - 1.0), fabs(A[3] - 1.0)), fmax(fabs(A[1]), fabs(A[2])));
+    return dev >= 0.05;
+}
+
+// T'(tx, ty) = bilinear sample of T at (5, 5) + Ainv (tx - 5, ty - 5), clamped to the patch, rounded to the nearest byte
+__device__ __forceinline__ uint8_t ncc_warp_sample(const uint8_t* T, const double* Ainv, int tx, int ty)
+{
+    const double ox = tx - 5.0, oy = ty - 5.0;
+    double sx = 5.0 + (Ainv[0] * ox + Ainv[1] * oy), sy = 5.0 + (Ainv[2] * ox + Ainv[3] * oy);
+    sx = fmin(fmax(sx, 0.0), 10.0);
+    sy = fmin(fmax(sy, 0.0), 10.0);
+    const int x0 = min((int)sx, 9), y0 = min((int)sy, 9);
+    const double fx = sx - x0, fy = sy - y0;
+    const double t00 = T[y0 * kNccP + x0], t01 = T[y0 * kNccP + x0 + 1], t10 = T[(y0 + 1) * kNccP + x0], t11 = T[(y0 + 1) * kNccP + x0 + 1];
+    const double top = t00 + fx * (t01 - t00), bot = t10 + fx * (t11 - t10);
+    return (uint8_t)(int)(top + fy * (bot - top) + 0.5);
+}
+
 struct NccBest { double s; int dy, dx; };
 __device__ __forceinline__ bool ncc_better(double s, int dy, int dx, const NccBest& b)
 {
@@ -88,6 +204,9 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f
     __shared__ NccBest wbest[4];
     __shared__ int sBest[3];   // x, y (level coordinates), valid
     __shared__ int sSum[2];    // S_t, S_tt
+    __shared__ __align__(16) uint8_t traw[128];
+    __shared__ double sAinv[4];
+    __shared__ int sWarp;
     const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = fdims(v, f)[D_N_FEAT];
     if (j >= N) return;
@@ -110,6 +229,24 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f
     if (tid == 0) {
         mbar_init(&bar, 1);
         nv.level[j] = lev;
+        // the warp of the template for the current camera (see the header): one 2x2 matrix per feature, all levels
+        sWarp = 0;
+        if (nv.warp && nv.anchor != nullptr && nv.anchor[(size_t)j * kNccAnchor + 9] != 0.0) {
+            const double* x = v.x + (size_t)f * v.ld;
+            const double* y = x + v.foff[fj];
+            double X[3], A[4];
+            if (v.ftype[fj] == kTypeInvDepth) {
+                double m[3];
+                direction(y[3], y[4], m);
+                for (int a = 0; a < 3; ++a) X[a] = y[a] + m[a] / y[5];
+            } else
+                for (int a = 0; a < 3; ++a) X[a] = y[a];
+            if (ncc_warp_matrix(v.cam, nv.anchor + (size_t)j * kNccAnchor, X, x, x + 3, A)) {
+                const double det = A[0] * A[3] - A[1] * A[2];
+                sAinv[0] = A[3] / det; sAinv[1] = -A[1] / det; sAinv[2] = -A[2] / det; sAinv[3] = A[0] / det;
+                sWarp = 1;
+            }
+        }
     }
     __syncthreads();
     int phase = 0;
@@ -128,8 +265,12 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f
                 for (int yy = ys; yy < ye; ++yy)
                     tma_bulk_load(win + (yy - y0) * kNccBoxW + (xs - x0a), nv.img[l] + (size_t)yy * nv.pitch[l] + xs, bytes, &bar);
         }
-        if (tid < 32) reinterpret_cast<uint32_t*>(tm)[tid] = reinterpret_cast<const uint32_t*>(nv.tmpl + ((size_t)j * kNccLevels + l) * 128)[tid];
+        if (tid < 32) reinterpret_cast<uint32_t*>(sWarp ? traw : tm)[tid] = reinterpret_cast<const uint32_t*>(nv.tmpl + ((size_t)j * kNccLevels + l) * 128)[tid];
         __syncthreads();
+        if (sWarp) {
+            if (tid < kNccPP) tm[tid] = ncc_warp_sample(traw, sAinv, tid % kNccP, tid / kNccP);
+            __syncthreads();
+        }
         if (warp == 0) {   // template sums by warp-shuffle reduction
             int st = 0, stt = 0;
             for (int e = lane; e < kNccPP; e += 32) { const int t = tm[e]; st += t; stt += t * t; }

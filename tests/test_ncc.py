@@ -146,3 +146,140 @@ def test_gpu_ncc_search_two_filters_of_one_handle():
         assert np.array_equal(gs, score) and np.array_equal(gl, level) and np.array_equal(r["matched"], matched)
         assert np.array_equal(r["z"][matched.astype(bool)], z[matched.astype(bool)])
     assert gpu.frame_info(0)["n_matches"] != gpu.frame_info(1)["n_matches"] or not np.array_equal(gpu.ncc_scores(0)[0], gpu.ncc_scores(1)[0])
+
+
+def test_oracle_warp_matrix_basics():
+    """no camera motion -> no warp; a roll about the optical axis -> a rotation matrix; moving closer -> magnification"""
+    cam = (200.0, 200.0, 160.0, 120.0)
+    an = np.array([0, 0, 0, 1, 0, 0, 0, 160.0, 120.0, 1.0])
+    X = np.array([0.0, 0.0, 2.0])
+    assert ncc_oracle.warp_matrix(cam, an, X, [0, 0, 0], [1, 0, 0, 0]) is None
+    a = 0.3
+    A = ncc_oracle.warp_matrix(cam, an, X, [0, 0, 0], [np.cos(a / 2), 0, 0, np.sin(a / 2)])
+    assert np.allclose(A, [[np.cos(a), np.sin(a)], [-np.sin(a), np.cos(a)]], atol=1e-9)
+    A = ncc_oracle.warp_matrix(cam, an, X, [0, 0, 0.5], [1, 0, 0, 0])
+    assert np.allclose(A, np.eye(2) * (2.0 / 1.5), atol=1e-9)
+    T = (np.arange(121) % 11 * 20).astype(np.uint8)       # horizontal ramp
+    Tw = ncc_oracle.warp_template(T, np.eye(2) * 2.0).reshape(11, 11)
+    assert np.array_equal(Tw[5], [50, 60, 70, 80, 90, 100, 110, 120, 130, 140, 150])
+
+
+def _rolled_camera_case(N, W, H, roll):
+    """map + templates captured at the initial pose; then the camera is rolled about its optical axis by `roll` rad, so every
+    patch appears rotated: the un-warped template no longer correlates, the warped one does"""
+    sc = Scenario(W, H, N)
+    x, P, ft, fo, desc, uv0 = sc.init_map()
+    rng = np.random.default_rng(7)
+    tex = smooth_textures(rng, N)
+    return sc, (x, P, ft, fo, desc), uv0, tex
+
+
+@pytest.mark.gpu
+def test_gpu_template_capture_compaction_and_warp():
+    """NCC appearance on the device: (1) ekfb_add_features captures the templates of new features from the frame's pyramid and
+    their anchor (camera pose + pixel) -- equal to the oracle's cut_templates / anchors; (2) ekfb_map_management carries both
+    along with the surviving features; (3) after a camera roll the search warps the templates (plane-induced affine warp) --
+    matched flags, pixels, levels and scores equal the oracle's search with the oracle's warped templates, and the warp is what
+    makes the rolled patches match."""
+    from openekfmonoslam_b200.capi import EkfBatch
+    from openekfmonoslam_b200.params import MapPolicy
+    W, H, N = 320, 240, 30
+    sc, (x, P, ft, fo, desc), uv0, tex = _rolled_camera_case(N, W, H, 0.0)
+    p = sc.params
+    cam = (p.fx, p.fy, p.cx, p.cy)
+    # (1) capture: an empty filter, the first frame, the features added on the device
+    gpu = EkfBatch(p, 1, N + 8, 4 * N + 64)
+    x13 = np.array(x[:13]); P13 = np.array(P[:13, :13])
+    gpu.set_state(0, x13, P13, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 32), np.uint8))
+    img0 = render(W, H, uv0, tex, 1)
+    gpu.ncc_set_image(0, img0)
+    gpu.add_features(0, uv0, desc)
+    tg, ag = gpu.ncc_get_templates(0, 0, N)
+    assert np.array_equal(tg, ncc_oracle.cut_templates(ncc_oracle.pyramid(img0), uv0))
+    assert np.array_equal(ag, ncc_oracle.anchors(x13, uv0))
+    # (2) compaction: mark a few features as never matched -> removed; the rest keep their templates
+    tp = np.full(N, 10, np.int32); tm = np.full(N, 10, np.int32)
+    drop = np.array([0, 3, 4, 11, N - 1])
+    tm[drop] = 0
+    gpu.set_hit_counters(0, tp, tm)
+    gpu.set_keypoints(0, np.zeros((0, 2), np.float32), np.zeros((0, 32), np.uint8))
+    gpu.predict(); gpu.measure(); gpu.match(); gpu.ransac(); gpu.update(0); gpu.rescue(); gpu.update(1)
+    res = gpu.map_management(MapPolicy(1, 0, 0, 0, 0.5, 0.0))[0]
+    keep = np.setdiff1d(np.arange(N), drop)
+    assert res["n_features"] == len(keep)
+    tg2, ag2 = gpu.ncc_get_templates(0, 0, len(keep))
+    assert np.array_equal(tg2, tg[keep]) and np.array_equal(ag2, ag[keep])
+    gpu.close()
+    # (3) warp: full map at the initial pose, then a rolled camera
+    rates = {}
+    for roll in (0.0, 0.8):
+        gpu = EkfBatch(p, 1, N, 4 * N + 64)
+        orc = OracleFilter(p)
+        q = np.array([np.cos(roll / 2), 0.0, 0.0, np.sin(roll / 2)])
+        xr = np.array(x); xr[3:7] = q; xr[7:13] = 0.0      # rolled, at rest: the prediction keeps the pose
+        gpu.set_state(0, xr, P, ft, fo, desc); orc.set_state(xr, P, ft, fo, desc)
+        tmpl = ncc_oracle.cut_templates(ncc_oracle.pyramid(img0), uv0)
+        gpu.ncc_set_templates(0, 0, tmpl)
+        # anchors through the capture path: write them by adding nothing -- use the API that sets templates, then anchors
+        # come from a second handle's capture above (same pixels, initial pose)
+        gpu.set_option(15, 1)
+        orc.predict(); orc.measure(); gpu.predict(); gpu.measure()
+        mo = orc.get_measure()
+        xs, _ = orc.get_state()
+        # the frame as the rolled camera sees it: every texture rotated by -roll about its predicted pixel
+        pos = mo["h"]
+        A = np.array([[np.cos(roll), np.sin(roll)], [-np.sin(roll), np.cos(roll)]])
+        texr = np.stack([ncc_oracle.warp_template(t, A) if roll else t for t in tex])
+        img = render(W, H, pos, texr, 5)
+        gpu.ncc_set_image(0, img)
+        pyr = ncc_oracle.pyramid(img)
+        for use_anchor in ((False, True) if roll else (False,)):
+            anc = ag if use_anchor else None
+            if use_anchor:
+                gpu.ncc_set_anchors(0, 0, ag)
+            tw, flags = ncc_oracle.warped_templates(tmpl, anc, cam, xs, ft, fo)
+            matched, z, score, level = ncc_oracle.search(pyr, tw, mo["vis"], mo["h"], mo["ell"][:, :2], mo["ell"][:, 2])
+            gpu.match_ncc(0.8)
+            r = gpu.feature_results(0)
+            gs, gl = gpu.ncc_scores(0)
+            assert np.array_equal(gl, level) and np.array_equal(r["matched"], matched)
+            assert np.array_equal(gs, score), np.abs(gs - score).max()
+            assert np.array_equal(r["z"][matched.astype(bool)], z[matched.astype(bool)])
+            vis = mo["vis"].astype(bool)
+            rates[(roll > 0, use_anchor)] = matched[vis].mean()
+            if roll and use_anchor:
+                assert flags[vis].all()
+        gpu.close()
+    # at rest the raw templates match; after a 46 degree roll they mostly do not, the warped ones do again
+    assert rates[(False, False)] > 0.7 and rates[(True, True)] > 0.7 and rates[(True, False)] < rates[(True, True)] - 0.25, rates
+
+
+@pytest.mark.gpu
+def test_gpu_step_with_the_ncc_matcher():
+    """EKFB_OPT_MATCHER = 1: ekfb_step runs the NCC active search in place of the descriptor matcher (image set every frame,
+    no keypoints needed) -- bit-identical to calling the phases one by one with ekfb_match_ncc, and the filter keeps tracking."""
+    from openekfmonoslam_b200.capi import EkfBatch
+    W, H, N = 320, 240, 40
+    sc, orc, (x, P, ft, fo, desc), tex, tmpl = ncc_case(N, W, H)
+    a = EkfBatch(sc.params, 1, N, 64); b = EkfBatch(sc.params, 1, N, 64)
+    for g in (a, b):
+        g.set_state(0, x, P, ft, fo, desc)
+        g.ncc_set_templates(0, 0, tmpl)
+        g.set_keypoints(0, np.zeros((0, 2), np.float32), np.zeros((0, 32), np.uint8))
+    a.set_option(14, 1)
+    a.ncc_set_threshold(0.8)
+    inl = []
+    for t in range(1, 7):
+        img = render(W, H, feature_pixels(sc, t), tex, 30 + t)
+        for g in (a, b):
+            g.ncc_set_image(0, img)
+        a.step()
+        b.predict(); b.measure(); b.match_ncc(0.8); b.ransac(); b.update(0); b.rescue(); b.update(1); b.update_map_features()
+        (xa, Pa), (xb, Pb) = a.get_state(0), b.get_state(0)
+        assert np.array_equal(xa, xb) and np.array_equal(Pa, Pb), t
+        ia = a.frame_info(0)
+        assert ia == b.frame_info(0) and ia["status"] == 0
+        inl.append(ia["n_inliers"])
+        assert np.array_equal(Pa, Pa.T)
+    assert min(inl) > N // 3, inl
+    a.close(); b.close()
