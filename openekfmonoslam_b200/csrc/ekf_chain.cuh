@@ -51,12 +51,15 @@ __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.rel
 constexpr int kChainTimeoutStatus = 5;   // EKFB_ERR_INTERNAL: a flag did not arrive within ~1 s (never observed; bounds a hang)
 
 // all threads: wait until *flag == gen (thread 0 polls).  Returns with the data published before the flag visible to the CTA.
-__device__ __forceinline__ void chain_wait(const int* flag, int gen, int* status)
+// backoff: the 140-odd helper / TRSM CTAs that wait for a flag sleep ~100 ns between polls, so their polling does not load
+// the L2 slice the critical CTA's flags and tiles live in; the critical CTA itself (backoff = false) polls back to back
+__device__ __forceinline__ void chain_wait(const int* flag, int gen, int* status, bool backoff = true)
 {
     if (threadIdx.x == 0) {
         if (ld_acquire(flag) != gen) {
             const long long t0 = clock64();
             while (ld_acquire(flag) != gen) {
+                if (backoff) __nanosleep(100);
                 if (clock64() - t0 > (1ll << 31)) { atomicExch(status, kChainTimeoutStatus); break; }
             }
         }
@@ -66,11 +69,10 @@ __device__ __forceinline__ void chain_wait(const int* flag, int gen, int* status
 // all threads: the CTA's global stores so far become visible, then the flag is raised
 __device__ __forceinline__ void chain_signal(int* flag, int gen)
 {
-    __syncthreads();                      // every thread's stores are ordered before the signalling thread's fence (the pattern
-    if (threadIdx.x == blockDim.x - 1) {  // of a grid barrier).  The last thread signals: its warp idles through the in-register
-        __threadfence();                  // phases of the factorisation, so the fence latency stays off the critical warps
-        st_release(flag, gen);
-    }
+    __syncthreads();                      // every thread's stores happen-before the signalling thread's release store, which is
+    if (threadIdx.x == blockDim.x - 1)    // cumulative (the pattern of cutlass::Barrier::arrive_inc: barrier, then ONE fence +
+        st_release(flag, gen);            // store; a __threadfence() in front of the st.release paid for the fence twice).  The
+                                          // last thread signals: its warp idles through the in-register phases of the factorisation
 }
 // non-blocking: is the flag already raised?  (thread 0 looks, everybody gets the answer)
 __device__ __forceinline__ bool chain_peek(const int* flagA, const int* flagB, int gen, int* sFlag)
@@ -312,8 +314,8 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
         t = cx.As; cx.As = cx.A2; cx.A2 = t;             // T(I-1, I) in A2
     } else {
         if (I > 0) {
-            chain_wait(cx.ctl.tready(I - 1), cx.gen, cx.dm + D_STATUS);
-            if (I >= 2) chain_wait(cx.ctl.pdready(I), cx.gen, cx.dm + D_STATUS);
+            chain_wait(cx.ctl.tready(I - 1), cx.gen, cx.dm + D_STATUS, false);
+            if (I >= 2) chain_wait(cx.ctl.pdready(I), cx.gen, cx.dm + D_STATUS, false);
             if (cx.wsBlock != I - 1) load_uinv(cx, I - 1, tid);
             load_tile64(cx.As, cx.Sg, cx.ldS, I0 - kNB, k, I0, k + 1, tid);
         }
@@ -371,14 +373,20 @@ __device__ void chain_task_diag(ChainCtx& cx, int I, int* bad, int* sFlag, bool 
             chain_signal(cx.ctl.xready(I - 1, I), cx.gen);
         }
         if (b != 5 || !wantNext) return;
-        if (!chain_peek(cx.ctl.tready(I), (I + 1 >= 2) ? cx.ctl.pdready(I + 1) : nullptr, cx.gen, sFlag)) return;
+        if (!*sFlag) return;   // (polled by an idle warp during block step 4, see below)
         load_tile64(cx.A2, cx.Sg, cx.ldS, I0, k, I0 + kNB, k + 1, tid);
         load_tile64(cx.Bs, cx.Sg, cx.ldS, I0 + kNB, k, I0 + kNB, k + 1, tid);
         cp_async_commit();
         cx.pre = I + 1;
     };
+    // are the next step's tiles there?  Asked by a thread of the idle warps while block step 4's Cholesky runs: the two L2 round
+    // trips of the acquire loads used to sit in front of block step 5 with all eight warps waiting for them
+    auto idle = [&](int b) {
+        if (b != 4 || tid != 255) return;
+        *sFlag = wantNext && ld_acquire(cx.ctl.tready(I)) == cx.gen && (I + 1 < 2 || ld_acquire(cx.ctl.pdready(I + 1)) == cx.gen);
+    };
     if (dbg) dbg[5] = clock64();
-    factor_tile64(cx.Ts, cx.Ws, tid, bad, nullptr, hook, absorb ? cx.As : nullptr, (kb + 7) >> 3);
+    factor_tile64(cx.Ts, cx.Ws, tid, bad, nullptr, hook, absorb ? cx.As : nullptr, (kb + 7) >> 3, idle);
     __syncthreads();
     if (dbg) dbg[6] = clock64();
     cx.wsBlock = I;
@@ -534,7 +542,15 @@ __device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, C
     int Ji = 0, chi = 0, stagei = 0;   // issue position: NS - 1 chunks ahead of the consume position (J, ch, stage)
     auto issue_next = [&]() {
         if (Ji < steps) {
-            if (chi == 0) chain_wait(cx.ctl.fdone(Ji), cx.gen, cx.dm + D_STATUS);   // block column Ji of U and Uinv_Ji are published
+            // The accumulation over the earlier row blocks only needs the tiles X(r, Ji), which the chain publishes well before it
+            // has factored tile (Ji, Ji): wait for each 64-row block of U as its first chunk comes up, and for the diagonal
+            // factor (Uinv_Ji) only in front of the last two chunks -- so when the chain ends, the TRSM of the last row block
+            // has four chunks left instead of its whole left-looking pass
+            const int nUi = (Ji * kNB) / 32;
+            if (chi < nUi) {
+                if ((chi & 1) == 0) chain_wait(cx.ctl.xready(chi >> 1, Ji), cx.gen, cx.dm + D_STATUS);
+            } else if (chi == nUi)
+                chain_wait(cx.ctl.fdone(Ji), cx.gen, cx.dm + D_STATUS);
             issue(Ji, chi, stagei);
             if (++chi == (Ji * kNB) / 32 + 2) { ++Ji; chi = 0; }
             stagei = (stagei + 1 == NS) ? 0 : stagei + 1;

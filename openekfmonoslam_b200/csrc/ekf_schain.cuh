@@ -169,9 +169,11 @@ struct NoHook { __device__ __forceinline__ void operator()(int) const {} };
 // is needed -- instead of costing a separate 64^3 product in front of the factorisation.
 // nblk < 8: only the leading 8 * nblk rows are factored -- the caller guarantees that the rest of T is the identity padding
 // (then U and U^-1 are the identity there: W gets ones on that part of its diagonal and the remaining block steps are skipped).
-template <typename Hook = NoHook>
+// idle(b): called by warps 4-7 only, while warps 0-3 run the in-register Cholesky and the substitutions of block step b (they
+// have nothing to do then): global-memory latency spent here (a flag poll) stays off the critical path.
+template <typename Hook = NoHook, typename Idle = NoHook>
 __device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int* bad, long long* dbg, Hook hook = Hook(),
-                                              const double* Xp = nullptr, int nblk = 8)
+                                              const double* Xp = nullptr, int nblk = 8, Idle idle = Idle())
 {
     if (tid >= 8 * nblk && tid < kNB) W[tid * kSS + tid] = 1.0;   // (disjoint from everything the block steps below touch)
     long long tA = 0, tB = 0, tC = 0, t0 = 0;
@@ -247,7 +249,8 @@ __device__ __forceinline__ void factor_tile64(double* T, double* W, int tid, int
 #pragma unroll
             for (int j = 0; j < 8; ++j) wr[j] = x[j];
         }
-        }
+        } else
+            idle(b);
         __syncthreads();
         if (dbg) { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
         if (tid == 56 + (b & 1)) {  // the diagonal block of U (after the barrier: the other warps read it during their Cholesky)
