@@ -272,7 +272,9 @@ enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* covar
        EKFB_OPT_MATCHER = 14 /* matcher used by ekfb_match / ekfb_step: 0 (default) = the reference's descriptor matcher, 1 = the NCC
                                 active search (needs ekfb_ncc_set_image / ekfb_set_image every frame; templates captured on the device
                                 by ekfb_add_features or supplied with ekfb_ncc_set_templates) */,
-       EKFB_OPT_NCC_WARP = 15 /* 1 (default): templates with an anchor are warped to the current camera before the comparison */ };
+       EKFB_OPT_NCC_WARP = 15 /* 1 (default): templates with an anchor are warped to the current camera before the comparison */,
+       EKFB_OPT_NCC_TMA_WINDOW = 16 /* 1 (default): the NCC search stages its window by one tensor-map TMA load per level, 0 = by
+                                       bulk row copies (the results are identical) */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

@@ -148,8 +148,11 @@ struct ekfb_ctx {
     uint8_t* ncc_tmpl2 = nullptr;     // compaction targets (swapped with the live arrays by ekfb_map_management)
     double* ncc_anchor = nullptr;     // [F][Nmax][10]: camera pose + pixel at template capture (ekf_ncc.cuh)
     double* ncc_anchor2 = nullptr;
+    std::vector<NccMaps> ncc_maps;    // per filter: tensor maps of its three pyramid levels (window loads of the search)
+    int ncc_tma_level[kNccLevels] = {0, 0, 0};
     std::vector<uint8_t> ncc_has_image;   // per filter: a frame has been set (templates of new features are captured from it)
     int matcher = 0;                  // option 14: 0 = the reference's descriptor matcher, 1 = NCC active search inside ekfb_match
+    int ncc_tma_window = 1;           // option 16: 1 = search windows by tensor-map TMA where the level allows, 0 = bulk row copies
     int ncc_warp = 1;                 // option 15: predict the template's appearance for the current camera (affine warp)
     double ncc_min_score = 0.8;       // acceptance threshold of the NCC matcher inside ekfb_match (ekfb_ncc_set_threshold)
     // device front end (ekf_frontend.cuh): corner-score image, per-row counts / offsets, keypoint count per filter
@@ -1311,6 +1314,24 @@ static int ensure_ncc(ekfb_ctx* c)
     ALLOC(c->ncc_anchor, (size_t)c->F * c->Nmax * kNccAnchor);
     ALLOC(c->ncc_anchor2, (size_t)c->F * c->Nmax * kNccAnchor);
     c->ncc_has_image.assign(c->F, 0);
+    // tensor maps of the pyramid levels (one window load per level and feature instead of 36 bulk row copies); a level smaller
+    // than the box, or a failed encode, keeps the bulk-copy form
+    c->ncc_maps.assign(c->F, NccMaps());
+    for (int l = 0; l < kNccLevels; ++l) {
+        bool ok = c->tmaEncode != nullptr && nv.W[l] >= kNccBoxW && nv.H[l] >= kNccBoxH;
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        for (int f = 0; ok && f < c->F; ++f) {
+            const cuuint64_t dims[2] = {(cuuint64_t)nv.W[l], (cuuint64_t)nv.H[l]};
+            const cuuint64_t strides[1] = {(cuuint64_t)nv.pitch[l]};
+            const cuuint32_t box[2] = {(cuuint32_t)kNccBoxW, (cuuint32_t)kNccBoxH}, es[2] = {1, 1};
+            ok = ((EncodeFn)c->tmaEncode)(&c->ncc_maps[f].m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l],
+                                          dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        c->ncc_tma_level[l] = ok ? 1 : 0;
+    }
     ALLOC(nv.score, (size_t)c->F * c->Nmax);
     ALLOC(nv.level, (size_t)c->F * c->Nmax);
     nv.ncc_min = 0.8;
@@ -1505,7 +1526,8 @@ extern "C" int ekfb_match_ncc(ekfb_handle c, double ncc_min)
         nv.anchor = c->ncc_anchor + (size_t)f * c->Nmax * kNccAnchor;
         nv.warp = c->ncc_warp;
         for (int l = 0; l < kNccLevels; ++l) nv.img[l] = c->ncc_img[l] + (size_t)f * c->ncc_level_bytes[l];
-        k_search_ncc<<<c->hN[f], 128, 0, c->stream>>>(c->v, nv, f);
+        for (int l = 0; l < kNccLevels; ++l) nv.tmaLevel[l] = c->ncc_tma_window ? c->ncc_tma_level[l] : 0;
+        k_search_ncc<<<c->hN[f], 128, 0, c->stream>>>(c->v, nv, c->ncc_maps[f], f);
         count_launch(c);
     }
     CK(launch_k(c, k_after_match, dim3(c->F), dim3(256), 0, c->v));
@@ -1908,12 +1930,13 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_NCC_WARP, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_NCC_TMA_WINDOW, "unknown option");
     if (option == EKFB_OPT_SMALL_UPDATE) { c->small_update = value; return EKFB_OK; }
     if (option == EKFB_OPT_LANES) { c->lanes_opt = value; return EKFB_OK; }
     if (option == 13) { c->dd_probe = value; return EKFB_OK; }
     if (option == EKFB_OPT_MATCHER) { c->matcher = value; return EKFB_OK; }
     if (option == EKFB_OPT_NCC_WARP) { c->ncc_warp = value; return EKFB_OK; }
+    if (option == EKFB_OPT_NCC_TMA_WINDOW) { c->ncc_tma_window = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_CTAS) { c->dd_ctas_per_sm = value == 1 ? 1 : 2; return EKFB_OK; }
     if (option == EKFB_OPT_FAULT_INJECT) { c->v.faultInject = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }

@@ -26,13 +26,16 @@
 // One CTA per feature.  The search window -- (2R + 11)^2 <= 35 x 35 bytes -- is staged in shared memory by the TMA
 // engine: one bulk asynchronous copy (cp.async.bulk.shared::cluster.global, 64 bytes from a 16-byte aligned source) per
 // window row, all completing on one mbarrier (complete_tx); rows and columns outside the image are clamped away (their
-// bytes are never read: a candidate's patch must lie inside the level).  The tensor-map form (cp.async.bulk.tensor.2d)
-// would need one instruction per window instead of 35, but raised "illegal instruction" at the UTMALDG on this pool's
-// driver (580.x) in every variant tried -- tools/tma_probe.cu keeps the reproducer -- so the 1-D form is used.
+// bytes are never read: a candidate's patch must lie inside the level).  Where the level is at least one box large the window
+// comes instead by ONE tensor-map load (cp.async.bulk.tensor.2d, UTMALDG.2D; box 64 x 36 bytes at the 16-byte aligned origin,
+// out-of-bounds zero fill) -- round 1 believed that form faulted on this pool; the fault was the probe's misaligned
+// innermost coordinate (profiles/r02_tma_probe.txt).
 // Warp w takes displacement rows w, w + 4, ..., lane = dx, so the 32 lanes of a warp read consecutive window bytes
 // (conflict-free) and the same template byte (broadcast); template sums and the arg-max are warp-shuffle reductions.
 // Bound: shared-memory bandwidth (2 x 121 byte reads per candidate) / latency; HBM traffic is the window bytes only.
 #pragma once
+
+#include <cuda.h>
 
 #include "ekf_kernels.cuh"
 
@@ -44,12 +47,19 @@ struct NccView {
     int W[kNccLevels], H[kNccLevels], pitch[kNccLevels];
     const uint8_t* img[kNccLevels];   // this filter's pyramid levels, 16-byte aligned rows
     const uint8_t* tmpl;   // [Nmax][3][128] (121 used)
+    int tmaLevel[kNccLevels];   // 1: this level's window comes by ONE tensor-map TMA load (NccMaps), 0: by per-row bulk copies
     const double* anchor;  // [Nmax][10]: r0[3], q0[4], (u0, v0), valid (1.0) -- nullptr or valid == 0: no warp
     int warp;              // EKFB_OPT_NCC_WARP
     double* score;         // [Nmax] level-0 score of the last search (-2: none)
     int* level;            // [Nmax] start level
     double ncc_min;
 };
+
+// tensor maps of this filter's pyramid levels: UINT8, dims (W_l, H_l), row stride pitch_l, box kNccBoxW x kNccBoxH, no swizzle,
+// out-of-bounds elements read as zero.  The innermost coordinate of a load must be a multiple of 16 BYTES (a misaligned one
+// raises "illegal instruction" at the UTMALDG: round 1's probe used x = 100, tools/tma_probe.cu, profiles/r02_tma_probe.txt);
+// the window origin is therefore rounded down to x0a = x0 & ~15, as for the bulk-copy form.
+struct NccMaps { CUtensorMap m[kNccLevels]; };
 
 // L(l+1) from L(l).  grid (ceil(Wo/32), ceil(Ho/8)), block (32, 8)
 __global__ void k_pyr_down(const uint8_t* src, int sp, uint8_t* dst, int dp, int Wo, int Ho)
@@ -196,7 +206,15 @@ __device__ __forceinline__ bool ncc_better(double s, int dy, int dx, const NccBe
 }
 
 // grid N (one CTA per feature of filter f), block 128
-__global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f)
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem)),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, const __grid_constant__ NccMaps maps, int f)
 {
     __shared__ __align__(128) uint8_t win[kNccBoxW * kNccBoxH];
     __shared__ __align__(16) uint8_t tm[128];
@@ -255,7 +273,11 @@ __global__ void __launch_bounds__(128) k_search_ncc(DevView v, NccView nv, int f
         const int Wl = nv.W[l], Hl = nv.H[l];
         // window origin (x0, y0); columns are fetched from the 16-byte aligned x0a <= x0, clamped to the row
         const int x0 = cx - R - 5, y0 = cy - R - 5, x0a = x0 & ~15, xoff = x0 - x0a;
-        if (tid == 0) {
+        if (tid == 0 && nv.tmaLevel[l]) {
+            // the whole window in one tensor-map TMA load; rows / columns outside the level arrive as zeros
+            mbar_expect_tx(&bar, kNccBoxW * kNccBoxH);
+            tma_load_2d(win, &maps.m[l], x0a, y0, &bar);
+        } else if (tid == 0) {
             const int xs = max(x0a, 0), xe = min(x0a + kNccBoxW, nv.pitch[l]);
             const int ys = max(y0, 0), ye = min(y0 + kNccBoxH, Hl);
             const int bytes = xe - xs, rows = ye - ys;

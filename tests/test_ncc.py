@@ -283,3 +283,35 @@ def test_gpu_step_with_the_ncc_matcher():
         assert np.array_equal(Pa, Pa.T)
     assert min(inl) > N // 3, inl
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H", [(320, 240), (251, 187)])
+def test_gpu_ncc_window_by_tensor_map_equals_bulk_copies(W, H):
+    """EKFB_OPT_NCC_TMA_WINDOW: the search window staged by one tensor-map TMA load per level (box 64 x 36 at a 16-byte aligned
+    origin, zero fill outside the level) or by per-row bulk copies -- same flags, pixels, levels and scores, and both equal the
+    oracle's.  251 x 187: level 2 (62 x 46) is smaller than the box and keeps the bulk copies while levels 0-1 use the tensor map;
+    features near the border exercise the out-of-bounds fill (negative origin, origin + box beyond the image)."""
+    from openekfmonoslam_b200.capi import EkfBatch
+    N = 40
+    sc, orc, (x, P, ft, fo, desc), tex, tmpl = ncc_case(N, W, H, 4.0)
+    img = render(W, H, feature_pixels(sc, 1), tex, 3)
+    orc.predict(); orc.measure()
+    mo = orc.get_measure()
+    matched, z, score, level = ncc_oracle.search(ncc_oracle.pyramid(img), tmpl, mo["vis"], mo["h"], mo["ell"][:, :2], mo["ell"][:, 2])
+    out = []
+    for tma in (1, 0):
+        gpu = EkfBatch(sc.params, 1, N, 64)
+        gpu.set_option(16, tma)
+        gpu.set_state(0, x, P, ft, fo, desc)
+        gpu.ncc_set_templates(0, 0, tmpl)
+        gpu.ncc_set_image(0, img)
+        gpu.predict(); gpu.measure(); gpu.match_ncc(0.8)
+        r = gpu.feature_results(0)
+        gs, gl = gpu.ncc_scores(0)
+        out.append((r["matched"].copy(), r["z"].copy(), gs, gl))
+        gpu.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out[0][0], matched) and np.array_equal(out[0][2], score) and np.array_equal(out[0][3], level)
+    assert matched.sum() > N // 3
