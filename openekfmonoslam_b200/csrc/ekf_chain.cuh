@@ -513,6 +513,7 @@ __device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, C
     const int c0 = slab * SW;
     if (c0 >= n) return;
     const int kpad = (k + kNB - 1) / kNB * kNB, steps = kpad / kNB;
+    const int kz = min(kpad, (k + 15) & ~15);
     double* Xs = tsm;
     double* Us = Xs + (size_t)kpad * SWP;   // NS stages x [32][68]
     double* Ts = Us + NS * 32 * 68;         // [64][SWP]
@@ -601,6 +602,16 @@ __device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, C
                 }
         }
         __syncthreads();
+        if (ch == nCh - 1) {
+            // W^T rows of this block back to global right away (under the chain, not behind it); rows k .. end of the last 16-row
+            // chunk go back as zeros (the TMA-fed downdate reads whole chunks).  Bu is scratch: if a later pivot fails, the rows
+            // already written are never read (every consumer checks the status first).
+            const int rEnd = min(J0 + kNB, kz);
+            for (int e = tid; e < (rEnd - J0) * SW; e += blockDim.x) {
+                const int r = J0 + e / SW, c = e % SW;
+                if (c0 + c < n) Bg[(size_t)r * v.ld + c0 + c] = Xs[(size_t)r * SWP + c];
+            }
+        }
         stage = (stage + 1 == NS) ? 0 : stage + 1;
         J = Jn;
         ch = chn;
@@ -610,12 +621,7 @@ __device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, C
     const int Cnu = cx.nbC - 1;
     for (int I = 0; I < cx.nbR; ++I)
         if (Cnu > I) chain_wait(cx.ctl.xready(I, Cnu), cx.gen, cx.dm + D_STATUS);
-    if (__ldcg(dm + D_STATUS) != 0) return;   // not positive definite: no W, the update is skipped
-    const int kz = min(kpad, (k + 15) & ~15);   // rows k .. end of the last 16-row chunk go back as zeros (TMA-fed downdate)
-    for (int e = tid; e < kz * SW; e += blockDim.x) {
-        const int r = e / SW, c = e % SW;
-        if (c0 + c < n) Bg[(size_t)r * v.ld + c0 + c] = Xs[(size_t)r * SWP + c];
-    }
+    if (__ldcg(dm + D_STATUS) != 0) return;   // not positive definite: the update is skipped
     if (lane < SW) {
         double s = 0.;
         for (int r = w; r < k; r += 8) s += Xs[(size_t)r * SWP + lane] * __ldcg(Sg + (size_t)r * v.ldS + k);
