@@ -74,14 +74,6 @@ __device__ __forceinline__ void chain_signal(int* flag, int gen)
         st_release(flag, gen);            // store; a __threadfence() in front of the st.release paid for the fence twice).  The
                                           // last thread signals: its warp idles through the in-register phases of the factorisation
 }
-// non-blocking: is the flag already raised?  (thread 0 looks, everybody gets the answer)
-__device__ __forceinline__ bool chain_peek(const int* flagA, const int* flagB, int gen, int* sFlag)
-{
-    if (threadIdx.x == 0) *sFlag = (ld_acquire(flagA) == gen) && (flagB == nullptr || ld_acquire(flagB) == gen);
-    __syncthreads();
-    return *sFlag != 0;
-}
-
 constexpr int kChainSmem = (5 * kNB * kSS + 2 * kNB) * (int)sizeof(double);
 
 struct ChainCtx {
