@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- EKF frames/s of the B200-native hot path (BASELINE.json metric) on synthetic sequences.
 
-    python bench.py --gpus N --steps K --warmup W [--workload c3|c3full|c2|c4|c5] [--impl b200|reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c3|c3full|c3k1000|c2|c4|c5] [--impl b200|reference]
 
 A "step" is one frame of the per-frame hot path (EKF::step order: predict, measure, match, 1-point
 RANSAC, low-innovation update, rescue, high-innovation update, map-feature bookkeeping) over this
@@ -11,7 +11,8 @@ rank's filter(s).  Workloads (BASELINE.json configs):
                 The default run ALSO executes a short leg of the north star's batched configuration -- c4: 256 filters of
                 200 features in total, sharded f mod N -- and reports it in `config.c4_sharded` and `c4_sharded` of the
                 same JSON line (strong scaling; `--no-c4-leg` skips it).
-  c3full        c3 without clutter keypoints: every feature is matched (BASELINE.md's C3 row; k ~ 900 + the rescue update).
+  c3full        c3 without clutter keypoints: every feature is matched (BASELINE.md's C3 row; k ~ 700 + the rescue update).
+  c3k1000       c3 without clutter, outliers, descriptor flips: nearly all 500 features are low-innovation inliers (k ~ 1000).
   c2            320x240, 50 features, one filter per GPU.
   c4            the 256-filter batch as the main workload.
   c5            1280x720, --features N' features (update/search stress), one filter per GPU.
@@ -39,6 +40,9 @@ WORKLOADS = {
     "c3": dict(W=640, H=480, N=500, filters=1, desc="synthetic 640x480, 500 features, single filter (P 3013x3013 FP64)"),
     "c3full": dict(W=640, H=480, N=500, filters=1, clutter=0.0,
                    desc="synthetic 640x480, 500 features, single filter, no clutter keypoints: every feature matched (BASELINE.md C3 row)"),
+    "c3k1000": dict(W=640, H=480, N=500, filters=1, clutter=0.0, outliers=0.0, flips=0.0, noise=0.1,
+                    desc="synthetic 640x480, 500 features, single filter, no clutter, no outlier displacements, no descriptor bit "
+                         "flips, 0.1 px noise: (nearly) every feature is a low-innovation inlier, k ~ 1000 update rows"),
     "c4": dict(W=640, H=480, N=200, filters=256, desc="256 independent 640x480 / 200-feature filters, sharded f mod G"),
     "c5": dict(W=1280, H=720, N=1000, filters=1, desc="1280x720 stress, N features, single filter"),
 }
@@ -103,7 +107,8 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 def scenario_for(wl, N, seed_offset=0):
     from openekfmonoslam_b200.scenario import Scenario
-    return Scenario(wl["W"], wl["H"], N, seed_offset=seed_offset, clutter_ratio=wl.get("clutter", 1.0))
+    return Scenario(wl["W"], wl["H"], N, seed_offset=seed_offset, clutter_ratio=wl.get("clutter", 1.0),
+                    outlier_frac=wl.get("outliers", 0.10), noise_px=wl.get("noise", 0.3), flip_p=wl.get("flips", 0.05))
 
 
 def make_scenarios(wl, my_filters, features):

@@ -477,3 +477,30 @@ def test_small_update_kernel_against_the_block_step_path(N):
             assert np.array_equal(ra[key], rb[key])
         assert np.array_equal(ra["inlier"], orc.get_ransac()["inlier"])
         assert a.frame_info(0)["status"] == 0
+
+
+def test_fused_update_with_a_single_buffered_trsm_ring():
+    """704 < k <= 832 update rows: the slab of the fused chain + TRSM launch leaves room for one operand buffer only
+    (k_update_fused<24, 1>).  Same frames through the per-block-step launches (option 3 = 0): equal to rounding, sets identical."""
+    sc = Scenario(640, 480, 500, clutter_ratio=0.0, outlier_frac=0.0, noise_px=0.1, flip_p=0.0)
+    x, P, ft, fo, desc, _ = sc.init_map()
+    a = EkfBatch(sc.params, 1, 500, 1256)
+    b = EkfBatch(sc.params, 1, 500, 1256)
+    b.set_option(3, 0)
+    for g in (a, b):
+        g.set_state(0, x, P, ft, fo, desc)
+    ks = []
+    for t in range(1, 5):
+        kp, ds = sc.frame(t)
+        for g in (a, b):
+            g.set_keypoints(0, kp, ds); g.step()
+        ia, ib = a.frame_info(0), b.frame_info(0)
+        assert ia == ib and ia["status"] == 0
+        ks.append(2 * ia["n_inliers"])
+        (xa, Pa), (xb, Pb) = a.get_state(0), b.get_state(0)
+        assert rel_err(xa, xb) < 1e-12 and rel_err(Pa, Pb) < 1e-12, t
+        assert np.array_equal(Pa, Pa.T)
+        ra, rb = a.feature_results(0), b.feature_results(0)
+        for key in ("matched", "inlier", "rescued"):
+            assert np.array_equal(ra[key], rb[key])
+    assert any(704 < k <= 832 for k in ks), ks
