@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     return OUT
 
 
-HOST_SRCS = [os.path.join(HERE, "host", f) for f in ("EKF.cpp", "config_yaml.cpp", "new_features.cpp", "trace_yaml.cpp")]
+HOST_SRCS = [os.path.join(HERE, "host", f) for f in ("EKF.cpp", "config_yaml.cpp", "new_features.cpp", "trace_yaml.cpp", "image_generator.cpp")]
 SAMPLE_SRC = os.path.join(HERE, "..", "samples", "ekf_main.cpp")
 SAMPLE_OUT = os.path.join(OUT_DIR, "ekf_sample")
 HOST_OUT = os.path.join(OUT_DIR, "libekf_host.so")
@@ -41,11 +41,12 @@ def build_host(force=False):
     """g++ build of the C++ host side (the drop-in EKF class of include/EKF.h) and the sample driver, linked against
     libekf_b200.so.  Output: openekfmonoslam_b200/lib/ekf_sample."""
     build()
-    deps = HOST_SRCS + [SAMPLE_SRC, os.path.join(HERE, "..", "include", "EKF.h"), os.path.join(HERE, "..", "include", "ekfb_cv_compat.hpp"), OUT]
+    deps = HOST_SRCS + [SAMPLE_SRC, os.path.join(HERE, "..", "include", "EKF.h"), os.path.join(HERE, "..", "include", "ekfb_cv_compat.hpp"),
+                        os.path.join(HERE, "..", "include", "ImageGenerator.h"), OUT]
     if not force and os.path.exists(SAMPLE_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(SAMPLE_OUT) for d in deps):
         return SAMPLE_OUT
     link = ["-L" + OUT_DIR, "-lekf_b200", "-Wl,-rpath,$ORIGIN"]
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-shared", "-fPIC", "-o", HOST_OUT] + HOST_SRCS + link)
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-shared", "-fPIC", "-o", HOST_OUT] + HOST_SRCS + link + ["-lz"])
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", SAMPLE_OUT, SAMPLE_SRC, "-lekf_host"] + link)
     return SAMPLE_OUT
 
