@@ -375,6 +375,7 @@ static int create_impl(const ekfb_params* p, int device, int n_filters, int max_
     CK(cudaFuncSetAttribute(k_update_fused<24, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_fused<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_fused<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CK(cudaFuncSetAttribute(k_update_fused<24, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_small<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_small_smem_bytes(24)));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
@@ -934,8 +935,11 @@ static int run_update(ekfb_ctx* c, int which)
         const int fusedSlabs = cdiv(n, 24);
         // operand ring of the TRSM role as deep as the shared memory beside the slab allows: 3 stages up to k = 640, 2 up to 704,
         // a single buffer (load, then use) up to k = 832 -- slower TRSM, but it still runs under the chain instead of behind it
-        const int fusedNS = trsm_smem_bytes(k, 24, 3) <= (size_t)kFusedSmemMax ? 3 : (trsm_smem_bytes(k, 24, 2) <= (size_t)kFusedSmemMax ? 2 :
-                            (trsm_smem_bytes(k, 24, 1) <= (size_t)kFusedSmemMax ? 1 : 0));
+        // ... and with a dense slab pitch (bank conflicts on the operand loads) up to k = 1024
+        int fusedNS = trsm_smem_bytes(k, 24, 3) <= (size_t)kFusedSmemMax ? 3 : (trsm_smem_bytes(k, 24, 2) <= (size_t)kFusedSmemMax ? 2 :
+                      (trsm_smem_bytes(k, 24, 1) <= (size_t)kFusedSmemMax ? 1 : 0));
+        int fusedPad = 4;
+        if (fusedNS == 0 && trsm_smem_bytes(k, 24, 1, 0) <= (size_t)kFusedSmemMax) { fusedNS = 1; fusedPad = 0; }
         const bool fusedOk = c->F == 1 && !c->force_generic && fusedNS > 0 && fusedSlabs + 1 + 8 <= c->smCount;
         // automatic choice (measured on B200, profiles/r02_chain_downdate_variants.txt): the fused launch wins once the chain has
         // three or more block steps; below that (and for batches) one launch per block step is faster
@@ -947,13 +951,15 @@ static int run_update(ekfb_ctx* c, int which)
             CK(launch_pdl(k_update_small<24>, dim3(cdiv(n, 24), c->F), dim3(256), update_small_smem_bytes(24), c->stream, v));
             count_launch(c);
         } else if (c->schain_eff == 4 && fusedOk) {
-            const size_t sm = std::max<size_t>(kChainSmem, trsm_smem_bytes(k, 24, fusedNS));
+            const size_t sm = std::max<size_t>(kChainSmem, trsm_smem_bytes(k, 24, fusedNS, fusedPad));
             if (fusedNS == 3)
                 CK(launch_pdl(k_update_fused<24, 3>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
             else if (fusedNS == 2)
                 CK(launch_pdl(k_update_fused<24, 2>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
-            else
+            else if (fusedPad == 4)
                 CK(launch_pdl(k_update_fused<24, 1>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
+            else
+                CK(launch_pdl(k_update_fused<24, 1, 0>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
             count_launch(c);   // (its last block also advances the chain's generation and applies the state correction)
         } else if (smem16 <= smemMax && !c->force_generic) {
             // fast path: S-only chain, diagonal-block inverses, slab TRSM

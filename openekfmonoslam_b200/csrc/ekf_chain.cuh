@@ -496,10 +496,12 @@ __global__ void k_chain_finish(int* ctlBase, int nbMax, int F)
 // tickets H+1 .. = one slab of SW columns of B each (the algorithm of k_trsm_slab, ekf_linalg.cuh, with a flag wait in
 // front of every row block).  When the chain ends only the last row block of the TRSM is left.
 // =====================================================================================================================
-template <int SW, int NS>
+// PAD = 4: conflict-free pitch SW + 4 for the K-major slab; PAD = 0: dense pitch (two-way bank conflicts on the operand loads) for
+// updates whose slab would not fit otherwise (k > 832 rows)
+template <int SW, int NS, int PAD>
 __device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, ChainCtx& cx)
 {
-    constexpr int SWP = SW + 4, NT = SW / 8;
+    constexpr int SWP = SW + PAD, NT = SW / 8;
     const int* dm = cx.dm;
     const int k = cx.k, n = dm[D_N_STATE];
     const int c0 = slab * SW;
@@ -628,7 +630,7 @@ __device__ void trsm_slab_role(const DevView& v, int f, int slab, double* tsm, C
     }
 }
 
-template <int SW, int NS>
+template <int SW, int NS, int PAD>
 __device__ __forceinline__ void update_fused_body(const DevView& v, int* ctlBase, int nbMax, int nSlabs, double* csm)
 {
     __shared__ int sTicket, sPos, bad, sFlag;
@@ -660,7 +662,7 @@ __device__ __forceinline__ void update_fused_body(const DevView& v, int* ctlBase
         return;
     }
     if (ticket > H) {
-        trsm_slab_role<SW, NS>(v, f, ticket - H - 1, csm, cx);
+        trsm_slab_role<SW, NS, PAD>(v, f, ticket - H - 1, csm, cx);
         return;
     }
     for (;;) {
@@ -677,11 +679,11 @@ __device__ __forceinline__ void update_fused_body(const DevView& v, int* ctlBase
 // The block that finishes last (every flag of the dataflow has been consumed by then) advances the chain's generation and
 // clears its counters -- what k_chain_finish does as a launch of its own -- and applies the state correction
 // (state_apply_tail): the update is ONE launch from S to x.
-template <int SW, int NS>
+template <int SW, int NS, int PAD = 4>
 __global__ void __launch_bounds__(256, 1) k_update_fused(DevView v, int* ctlBase, int nbMax, int nSlabs)
 {
     extern __shared__ __align__(16) double csm[];
-    update_fused_body<SW, NS>(v, ctlBase, nbMax, nSlabs, csm);
+    update_fused_body<SW, NS, PAD>(v, ctlBase, nbMax, nSlabs, csm);
     if (!last_block_done(fdims(v, 0) + D_TICKET_UPD, (int)gridDim.x)) return;
     if (threadIdx.x == 0 && ctlBase[CH_TICKET] != 0) {
         ctlBase[CH_GEN] += 1;

@@ -939,10 +939,10 @@ __device__ inline void state_apply_tail(const DevView& v, int f)
 template <int SW>
 __host__ __device__ constexpr int trsm_pitch() { return SW + 4; }
 
-inline size_t trsm_smem_bytes(int k, int SW, int stages = 2)
+inline size_t trsm_smem_bytes(int k, int SW, int stages = 2, int pad = 4)
 {
     const int kpad = (k + kNB - 1) / kNB * kNB;
-    return sizeof(double) * ((size_t)kpad * (SW + 4) + (size_t)stages * 32 * 68 + (size_t)kNB * (SW + 4) + 8 * SW);
+    return sizeof(double) * ((size_t)kpad * (SW + pad) + (size_t)stages * 32 * 68 + (size_t)kNB * (SW + pad) + 8 * SW);
 }
 
 // NS = depth of the cp.async ring of 32-row operand chunks.  A chunk feeds only 8 x SW/8 DMMAs per warp, far less than

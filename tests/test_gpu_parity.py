@@ -504,3 +504,32 @@ def test_fused_update_with_a_single_buffered_trsm_ring():
         for key in ("matched", "inlier", "rescued"):
             assert np.array_equal(ra[key], rb[key])
     assert any(704 < k <= 832 for k in ks), ks
+
+
+def test_fused_update_with_a_dense_slab_pitch():
+    """832 < k <= 1024 update rows: the slab only fits beside the chain's tiles with a dense pitch (k_update_fused<24, 1, 0>).
+    500 features on a grid (gates that do not overlap, so the reference's 2-best rule lets nearly all of them through), no
+    clutter: k ~ 950.  Same frames through the per-block-step launches: equal to rounding, sets identical."""
+    sc = Scenario(640, 480, 500, clutter_ratio=0.0, outlier_frac=0.0, noise_px=0.1, flip_p=0.0)
+    p = sc.params
+    gx, gy = np.meshgrid(np.linspace(0.16 * 640, 0.84 * 640, 25), np.linspace(0.10 * 480, 0.90 * 480, 20))
+    d = np.random.default_rng(3).uniform(3.0, 6.0, 500)
+    sc.points = np.stack([(gx.ravel() - p.cx) / p.fx * d, (gy.ravel() - p.cy) / p.fy * d, d], axis=1)
+    x, P, ft, fo, desc, _ = sc.init_map()
+    a = EkfBatch(sc.params, 1, 500, 1256)
+    b = EkfBatch(sc.params, 1, 500, 1256)
+    b.set_option(3, 0)
+    for g in (a, b):
+        g.set_state(0, x, P, ft, fo, desc)
+    ks = []
+    for t in range(1, 5):
+        kp, ds = sc.frame(t)
+        for g in (a, b):
+            g.set_keypoints(0, kp, ds); g.step()
+        ia, ib = a.frame_info(0), b.frame_info(0)
+        assert ia == ib and ia["status"] == 0
+        ks.append(2 * ia["n_inliers"])
+        (xa, Pa), (xb, Pb) = a.get_state(0), b.get_state(0)
+        assert rel_err(xa, xb) < 1e-12 and rel_err(Pa, Pb) < 1e-12, t
+        assert np.array_equal(Pa, Pa.T)
+    assert any(k > 832 for k in ks), ks
