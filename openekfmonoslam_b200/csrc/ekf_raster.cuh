@@ -172,37 +172,58 @@ __device__ inline void raster_ellipse_warp(uint8_t* img, int W, int H, int cx, i
         sc->raw[t] = p;
     }
     __syncwarp();
-    if (lane == 0) {  // drop consecutive duplicates
+    {   // drop consecutive duplicates: a vertex is compared with the last one KEPT, which (by induction) always equals its raw
+        // predecessor, so "keep" is a local test and the new positions are a ballot prefix sum -- all lanes, three rounds
         int nv = 0;
-        for (int t = 0; t < nraw; ++t) {
-            const RasterPt p = sc->raw[t];
-            if (nv == 0 || p.x != sc->v[nv - 1].x || p.y != sc->v[nv - 1].y) sc->v[nv++] = p;
+        for (int base = 0; base < nraw; base += 32) {
+            const int t = base + lane;
+            bool keep = false;
+            RasterPt p = {0, 0};
+            if (t < nraw) {
+                p = sc->raw[t];
+                keep = (t == 0) || p.x != sc->raw[t - 1].x || p.y != sc->raw[t - 1].y;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) sc->v[nv + __popc(bal & ((1u << lane) - 1))] = p;
+            nv += __popc(bal);
         }
         if (nv <= 1) {
-            sc->v[0].x = ctrx; sc->v[0].y = ctry;
-            sc->v[1] = sc->v[0];
+            if (lane == 0) {
+                sc->v[0].x = ctrx; sc->v[0].y = ctry;
+                sc->v[1] = sc->v[0];
+            }
             nv = 2;
         }
-        sc->nv = nv;
+        if (lane == 0) sc->nv = nv;
     }
     __syncwarp();
     const int npts = sc->nv;
     // outline: edge e joins v[e-1] (v[npts-1] for e = 0) and v[e]
     for (int e = lane; e < npts; e += 32) draw_edge(img, W, H, sc->v[e == 0 ? npts - 1 : e - 1], sc->v[e], val);
 
+    // bounding box and the topmost vertex (the FIRST index of the smallest y, as a serial scan finds it): warp reduction
+    long long xmin = sc->v[0].x, xmax = xmin, ymin = sc->v[0].y, ymax = ymin;
+    int imin = 0;
+    for (int t = lane; t < npts; t += 32) {
+        const RasterPt p = sc->v[t];
+        if (p.y < ymin) { ymin = p.y; imin = t; }   // (t ascends within a lane: the first index of the lane's minimum is kept)
+        if (p.y > ymax) ymax = p.y;
+        if (p.x > xmax) xmax = p.x;
+        if (p.x < xmin) xmin = p.x;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long oy = __shfl_xor_sync(0xffffffffu, ymin, o), oY = __shfl_xor_sync(0xffffffffu, ymax, o);
+        const long long ox = __shfl_xor_sync(0xffffffffu, xmin, o), oX = __shfl_xor_sync(0xffffffffu, xmax, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, imin, o);
+        if (oy < ymin || (oy == ymin && oi < imin)) { ymin = oy; imin = oi; }
+        if (oY > ymax) ymax = oY;
+        if (ox < xmin) xmin = ox;
+        if (oX > xmax) xmax = oX;
+    }
     if (lane == 0) {  // convex scanline walk -> spans
         sc->y_first = 0;
         sc->y_last = -1;
         const int dlt = 1 << kXYShift >> 1;
-        long long xmin = sc->v[0].x, xmax = xmin, ymin = sc->v[0].y, ymax = ymin;
-        int imin = 0;
-        for (int t = 0; t < npts; ++t) {
-            const RasterPt p = sc->v[t];
-            if (p.y < ymin) { ymin = p.y; imin = t; }
-            if (p.y > ymax) ymax = p.y;
-            if (p.x > xmax) xmax = p.x;
-            if (p.x < xmin) xmin = p.x;
-        }
         xmin = (xmin + dlt) >> kXYShift;
         xmax = (xmax + dlt) >> kXYShift;
         ymin = (ymin + dlt) >> kXYShift;
