@@ -248,8 +248,9 @@ int ekfb_profile_enable(ekfb_handle h, int on);
  * rescue, misc (9 floats), plus launch counts (9 ints) */
 int ekfb_profile_read(ekfb_handle h, float* ms9, int32_t* launches9);
 int64_t ekfb_kernel_launches(ekfb_handle h);     /* kernels launched by this handle so far */
-/* tuning / test switches.  EKFB_OPT_FORCE_GENERIC_FACTOR = 1 forces the right-looking factorisation over
- * the whole augmented matrix (the path used when k is too large for the shared-memory slab TRSM). */
+/* tuning / test switches.  EKFB_OPT_FORCE_GENERIC_FACTOR forces the paths used when k is too large for the shared-memory slab
+ * TRSM: 2 = S-chain + blocked TRSM on the global-memory resident B (tensor-map fed DMMA kernel; the default for a single
+ * filter), 1 = right-looking factorisation over the whole augmented matrix (batches, or no tensor-map support). */
 enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* covariance downdate: 0 = 64x64 tiles fed by cp.async, 1 = 128x64 tiles, 2 = single filter: persistent
                                         TMA-fed kernel (tensor-map loads / stores, mbarrier ring, 128-byte swizzle), 3 = as 2 without swizzle */,
        EKFB_OPT_SCHAIN_VARIANT = 3 /* factorisation of S: 0 = one fused launch per 64-row step, 1 = panel + trail launches,

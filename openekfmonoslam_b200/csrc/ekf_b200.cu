@@ -19,6 +19,7 @@
 #include "ekf_frontend.cuh"
 #include "ekf_downdate_tma.cuh"
 #include "ekf_update_small.cuh"
+#include "ekf_gemm_tma.cuh"
 
 using namespace ekf;
 
@@ -102,7 +103,7 @@ struct ekfb_ctx {
     // L2 flush scratch and the per-launch event pool of the downdate kernel
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
-    bool force_generic = false;
+    int force_generic = 0;     // option 1: 1 = right-looking factorisation over the augmented matrix, 2 = S-chain + global-memory TRSM (ekf_gemm_tma.cuh)
     int downdate_variant = 2;   // 2 = TMA-fed persistent kernel (default), 3 = same without swizzle, 0 = cp.async 64x64 tiles, 1 = 128x64
     // updates with at most this many rows run the downdate as 64x64 tiles, 4 CTAs per SM.  Measured on B200 (profiles/
     // r01_downdate_sweep.txt) that variant wins at every k and n tried (16 resident warps hide the tile read-modify-write
@@ -376,6 +377,7 @@ static int create_impl(const ekfb_params* p, int device, int n_filters, int max_
     CK(cudaFuncSetAttribute(k_update_fused<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_fused<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_update_fused<24, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    CK(cudaFuncSetAttribute(k_gemm_tn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kGtSmemBytes));
     CK(cudaFuncSetAttribute(k_update_small<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_small_smem_bytes(24)));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     CK(cudaFuncSetAttribute(k_trsm_slab<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
@@ -987,6 +989,47 @@ static int run_update(ekfb_ctx* c, int which)
                 k_chain_finish<<<cdiv(c->F, 128), 128, 0, c->stream>>>(c->chainCtl, c->nbMax, c->F);
                 count_launch(c);
             }
+        } else if (c->F == 1 && c->tmaEncode && c->force_generic != 1) {
+            // large k (the slab of the TRSM does not fit in shared memory): S-chain, one launch per block step, then the
+            // blocked left-looking TRSM on the global-memory resident B (ekf_gemm_tma.cuh): per 64-row block one long
+            // contraction over the rows already solved and one 64-row product with the inverse of the diagonal block
+            c->schain_eff = 0;
+            { int rcC = launch_schain(c, k); if (rcC != EKFB_OK) return rcC; }
+            const int kpad = steps * kNB;
+            if (kpad > k)   // padding rows of the last block: finite (they meet the identity padding of Uinv)
+                CK(cudaMemsetAsync(v.Bu + (size_t)k * c->ld, 0, sizeof(double) * (size_t)(kpad - k) * c->ld, c->stream));
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            auto encode = [&](CUtensorMap* m, void* base, cuuint64_t cols, cuuint64_t rows, cuuint64_t pitchDoubles, cuuint32_t boxRows) {
+                const cuuint64_t dims[2] = {cols, rows};
+                const cuuint64_t strides[1] = {pitchDoubles * sizeof(double)};
+                const cuuint32_t box[2] = {16u, boxRows}, es[2] = {1, 1};
+                return ((EncodeFn)c->tmaEncode)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            };
+            GemmMaps mU, mI;   // contraction with rows of U (factor buffer) / with the inverse of a diagonal block
+            bool ok = encode(&mU.A, v.Sf, (cuuint64_t)c->ldS, (cuuint64_t)c->kmax, (cuuint64_t)c->ldS, 16) &&
+                      encode(&mU.B, v.Bu, (cuuint64_t)n, (cuuint64_t)c->kmax, (cuuint64_t)c->ld, 16) &&
+                      encode(&mU.C, v.Bu, (cuuint64_t)n, (cuuint64_t)c->kmax, (cuuint64_t)c->ld, 64) &&
+                      encode(&mI.A, v.Uinv, (cuuint64_t)kNB, (cuuint64_t)c->kmax, (cuuint64_t)kNB, 16);
+            if (!ok) {
+                g_err = "cuTensorMapEncodeTiled failed for the global-memory TRSM operands";
+                return EKFB_ERR_CUDA;
+            }
+            mI.B = mU.B;
+            mI.C = mU.C;
+            const dim3 tgrid(cdiv(n, 64));
+            for (int J = 0; J < steps; ++J) {
+                const int J0 = J * kNB;
+                if (J > 0) CK(launch_k(c, k_gemm_tn_tma, tgrid, dim3(160), (size_t)kGtSmemBytes, mU, J0, 0, 0, J0, J0, 1));
+                CK(launch_k(c, k_gemm_tn_tma, tgrid, dim3(160), (size_t)kGtSmemBytes, mI, 0, J0, J0, J0, kNB, 0));
+                count_launch(c, J > 0 ? 2 : 1);
+            }
+            CK(launch_k(c, k_wy, dim3(cdiv(n, 256)), dim3(256), 0, v));   // dx = W y; clears the rows the downdate reads beyond k
+            CK(launch_k(c, k_state_apply, dim3(cdiv(n, 256), c->F), dim3(256), 0, v));
+            count_launch(c, 2);
         } else {
             // generic path (very large k): right-looking over the whole augmented matrix
             usedGeneric = true;
@@ -1956,7 +1999,7 @@ extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
     if (option == EKFB_OPT_TRSM_PAIR) { c->trsm_pair = value; return EKFB_OK; }
     if (option == EKFB_OPT_PDL) { c->use_pdl = value; return EKFB_OK; }
     if (option == EKFB_OPT_RANSAC_CHUNK) { c->ransac_chunk = value; return EKFB_OK; }
-    if (option == EKFB_OPT_FORCE_GENERIC_FACTOR) c->force_generic = value != 0;
+    if (option == EKFB_OPT_FORCE_GENERIC_FACTOR) c->force_generic = value;
     else if (option == EKFB_OPT_SCHAIN_VARIANT) c->schain_variant = value;
     else c->downdate_variant = value;
     return EKFB_OK;

@@ -103,11 +103,13 @@ def test_phase_by_phase_after_warmup_multi_block_update():
     assert gpu.frame_info(0)["n_inliers"] > 40
 
 
-def test_generic_factorisation_path():
-    """The right-looking factorisation over the whole augmented matrix (used when k is too large for the
-    slab TRSM) must agree with the oracle as well; forced here at a size where k spans several blocks."""
+@pytest.mark.parametrize("path", [1, 2])
+def test_generic_factorisation_path(path):
+    """The two paths for updates too large for the shared-memory slab TRSM must agree with the oracle as well; forced here at a
+    size where k spans several blocks: 1 = right-looking factorisation over the whole augmented matrix, 2 = S-chain + blocked
+    TRSM on the global-memory resident B (tensor-map fed DMMA kernel, ekf_gemm_tma.cuh)."""
     sc, orc, gpu = make_pair(640, 480, 100, warm=3)
-    gpu.set_option(1, 1)
+    gpu.set_option(1, path)
     for t in range(4, 7):
         phase_by_phase(sc, orc, gpu, t)
 
