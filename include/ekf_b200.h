@@ -275,7 +275,9 @@ enum { EKFB_OPT_FORCE_GENERIC_FACTOR = 1, EKFB_OPT_DOWNDATE_VARIANT = 2 /* covar
                                 by ekfb_add_features or supplied with ekfb_ncc_set_templates) */,
        EKFB_OPT_NCC_WARP = 15 /* 1 (default): templates with an anchor are warped to the current camera before the comparison */,
        EKFB_OPT_NCC_TMA_WINDOW = 16 /* 1 (default): the NCC search stages its window by one tensor-map TMA load per level, 0 = by
-                                       bulk row copies (the results are identical) */ };
+                                       bulk row copies (the results are identical) */,
+       EKFB_OPT_SLAB_TRSM_MAX_K = 17 /* single filter: updates with more rows than this use the TRSM on the global-memory resident B
+                                        instead of 16-column shared-memory slabs (default 1152 = as long as the slabs fit) */ };
 int ekfb_set_option(ekfb_handle h, int option, int value);
 /* developer aid: 64 device-side cycle counters written by instrumented kernels */
 int ekfb_debug_read(ekfb_handle h, long long* out64);

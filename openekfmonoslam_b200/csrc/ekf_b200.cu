@@ -103,6 +103,8 @@ struct ekfb_ctx {
     // L2 flush scratch and the per-launch event pool of the downdate kernel
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
+    int slab_trsm_max_k = 1152;   // single filter: above this many rows the TRSM on the global-memory resident B takes over from the
+                                  // 16-column shared-memory slabs (option 17; measured equal at k = 1028: 3.005 vs 3.000 ms per C5 frame)
     int force_generic = 0;     // option 1: 1 = right-looking factorisation over the augmented matrix, 2 = S-chain + global-memory TRSM (ekf_gemm_tma.cuh)
     int downdate_variant = 2;   // 2 = TMA-fed persistent kernel (default), 3 = same without swizzle, 0 = cp.async 64x64 tiles, 1 = 128x64
     // updates with at most this many rows run the downdate as 64x64 tiles, 4 CTAs per SM.  Measured on B200 (profiles/
@@ -963,7 +965,7 @@ static int run_update(ekfb_ctx* c, int which)
             else
                 CK(launch_pdl(k_update_fused<24, 1, 0>, dim3(c->smCount), dim3(256), sm, c->stream, v, c->chainCtl, c->nbMax, fusedSlabs));
             count_launch(c);   // (its last block also advances the chain's generation and applies the state correction)
-        } else if (smem16 <= smemMax && !c->force_generic) {
+        } else if (smem16 <= smemMax && !c->force_generic && (k <= c->slab_trsm_max_k || c->F > 1 || !c->tmaEncode)) {
             // fast path: S-only chain, diagonal-block inverses, slab TRSM
             { int rcC = launch_schain(c, k); if (rcC != EKFB_OK) return rcC; }
             // widest slab that fits, then the deepest operand ring beside it (4, 3 or 2 stages of 32 rows)
@@ -1985,13 +1987,14 @@ extern "C" int64_t ekfb_kernel_launches(ekfb_handle c) { return c ? c->launches 
 extern "C" int ekfb_set_option(ekfb_handle c, int option, int value)
 {
     REQUIRE(c, "null handle");
-    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_NCC_TMA_WINDOW, "unknown option");
+    REQUIRE(option >= EKFB_OPT_FORCE_GENERIC_FACTOR && option <= EKFB_OPT_SLAB_TRSM_MAX_K, "unknown option");
     if (option == EKFB_OPT_SMALL_UPDATE) { c->small_update = value; return EKFB_OK; }
     if (option == EKFB_OPT_LANES) { c->lanes_opt = value; return EKFB_OK; }
     if (option == 13) { c->dd_probe = value; return EKFB_OK; }
     if (option == EKFB_OPT_MATCHER) { c->matcher = value; return EKFB_OK; }
     if (option == EKFB_OPT_NCC_WARP) { c->ncc_warp = value; return EKFB_OK; }
     if (option == EKFB_OPT_NCC_TMA_WINDOW) { c->ncc_tma_window = value; return EKFB_OK; }
+    if (option == EKFB_OPT_SLAB_TRSM_MAX_K) { c->slab_trsm_max_k = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_CTAS) { c->dd_ctas_per_sm = value == 1 ? 1 : 2; return EKFB_OK; }
     if (option == EKFB_OPT_FAULT_INJECT) { c->v.faultInject = value; return EKFB_OK; }
     if (option == EKFB_OPT_DOWNDATE_SMALL_K) { c->downdate_small_k = value; return EKFB_OK; }
